@@ -1,0 +1,147 @@
+/*
+ * msm_b200 — C ABI of the B200-native fixed-base MSM for BLS12-381 G1/G2.
+ *
+ * Drop-in boundary for the hot path of LuoGuiwen/MSM_blst. Every entry point names the
+ * reference interface it replaces (paths relative to the reference root). Plain pointers and sizes only.
+ *
+ * Data encodings are the reference's own (bindings/blst.h:53-62,:164-165,:191-192,:251-252):
+ *   field element  = 6 x u64 little-endian limbs, Montgomery form, fully reduced  (48 B; Fp2 = re,im 96 B)
+ *   affine point   = {x, y}            96 B (G1) / 192 B (G2); infinity = all zero
+ *   Jacobian point = {x, y, z}         144 B / 288 B;          infinity: z = 0
+ *   scalar         = 32 bytes little-endian (blst_scalar / uint256_t::data[4]), < r, nbits = 255
+ *
+ * All msmb200_* functions return 0 on success, a negative MSMB200_E* code otherwise; the message is
+ * available from msmb200_last_error(). There is no CPU fallback: without a usable CUDA device every
+ * compute entry point fails with MSMB200_ECUDA.
+ */
+#ifndef MSM_B200_H
+#define MSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSMB200_OK 0
+#define MSMB200_EINVAL (-1)  /* bad argument / unknown config / call order */
+#define MSMB200_ECUDA (-2)   /* CUDA runtime error (no device, OOM, launch failure) */
+#define MSMB200_ESTATE (-3)  /* required table / points not built yet */
+
+typedef struct msmb200_ctx msmb200_ctx;
+
+/* MSM methods = the four methods of main_p1.cpp / main_p2.cpp (README.md:80-84) */
+enum {
+    MSMB200_CHES = 1,          /* pippenger_variant_q_over_5_CHES                               main_p1.cpp:192-246 */
+    MSMB200_CHES_INTEGRAL = 2, /* pippenger_variant_q_over_5_CHES_integral_scalar_conversion    main_p1.cpp:249-291 */
+    MSMB200_BGMW95 = 3,        /* pippenger_variant_BGMW95                                      main_p1.cpp:294-398 */
+    MSMB200_PIPPENGER = 4      /* pippenger_blst_built_in -> blst_p1s_mult_pippenger            main_p1.cpp:400-436 */
+};
+
+/* One row of ches_config_files/config_file_n_exp_*.h:5-17 (compile-time constants there, run-time here). */
+typedef struct {
+    int n_exp;    /* N_EXP */
+    int e;        /* EXPONENT_OF_q       (q = 2^e) */
+    int h;        /* h_LEN_SCALAR */
+    int a;        /* a_LEADING_TERM */
+    int d;        /* d_MAX_DIFF */
+    int bsize;    /* B_SIZE (0 = compute) */
+    int e_bgmw;   /* EXPONENT_OF_q_BGMW95 */
+    int h_bgmw;   /* h_BGMW95 */
+} msmb200_config;
+
+/* Look up a reference configuration by the name used on its command line (`./run.sh config=NAME`,
+ * makefile:15-18): "8".."21", "16_beta", "17_beta", "20_beta". */
+int msmb200_config_lookup(const char *name, msmb200_config *out);
+
+/* ---- context ------------------------------------------------------------------------------------ */
+
+/* group: 1 = G1 (main_p1.cpp), 2 = G2 (main_p2.cpp). npoints: number of fixed points owned by this
+ * context (N_POINTS, or the shard n/G of one GPU). device: CUDA ordinal. Builds BUCKET_SET,
+ * BUCKET_VALUE_TO_ITS_INDEX and DIGIT_CONVERSION_HASH_TABLE (main_p1.cpp:128-153) and uploads them. */
+int msmb200_ctx_create(msmb200_ctx **out, int group, const msmb200_config *cfg, size_t npoints, int device);
+void msmb200_ctx_destroy(msmb200_ctx *ctx);
+const char *msmb200_last_error(const msmb200_ctx *ctx); /* ctx may be NULL: last create() error */
+/* Use the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream). */
+int msmb200_set_stream(msmb200_ctx *ctx, void *cuda_stream);
+
+/* FIX_POINTS_LIST (main_p1.cpp:47): upload caller's affine points (host memory, npoints entries). */
+int msmb200_set_points(msmb200_ctx *ctx, const void *points_affine_host);
+/* init_fix_point_list (main_p1.cpp:52-66): P_i = 2^(first+i+1) * G computed on the device. */
+int msmb200_generate_fix_points(msmb200_ctx *ctx, size_t first);
+/* init_pippenger_CHES_q_over_5 table loop (main_p1.cpp:156-172): T3nh[3(i*h+j)+m-1] = m q^j P_i. */
+int msmb200_table_build_ches(msmb200_ctx *ctx);
+/* init_pippenger_BGMW95 (main_p1.cpp:94-122): TBGMW[i*h'+j] = q'^j P_i. */
+int msmb200_table_build_bgmw95(msmb200_ctx *ctx);
+/* Copy `count` affine entries starting at `first` back to host. which: 0 = fixed points, 1 = T3nh, 2 = TBGMW. */
+int msmb200_download(msmb200_ctx *ctx, int which, size_t first, size_t count, void *out_host);
+/* bucket set (BUCKET_SET, ascending, [0] = 0); returns |B| (or negative error); fills out if cap >= |B| */
+long msmb200_bucket_set(msmb200_ctx *ctx, int *out, long cap);
+
+/* ---- the MSM: one call = one method body of main_p1.cpp:192-436 incl. blst_p1_to_affine ----------- */
+
+/* scalars_host: npoints x 32 bytes LE in host memory. out_affine_host: 96 B / 192 B affine struct
+ * (Montgomery limbs, canonical) — the value the reference methods return. */
+int msmb200_msm(msmb200_ctx *ctx, int method, const void *scalars_host, void *out_affine_host);
+/* Same with scalars already resident in device memory (device pointer); result still lands on the host. */
+int msmb200_msm_device(msmb200_ctx *ctx, int method, const void *scalars_dev, void *out_affine_host);
+/* Multi-GPU leg: this context's partial sum as a Jacobian point written to DEVICE memory (144 B / 288 B),
+ * asynchronously on the context's stream, ready for one NCCL all-gather. */
+int msmb200_msm_partial_device(msmb200_ctx *ctx, int method, const void *scalars_dev, void *out_jacobian_dev);
+/* Sum `count` Jacobian partials (device memory, contiguous) and normalise: the G-1 dadds + blst_p1_to_affine. */
+int msmb200_sum_partials_device(msmb200_ctx *ctx, const void *partials_dev, int count, void *out_affine_host);
+/* blst_p1_affine_serialize / blst_p2_affine_serialize (src/e1.c:153-162, src/e2.c:194-203): 96 / 192 bytes. */
+int msmb200_affine_serialize(int group, const void *affine_host, unsigned char *out);
+
+/* Per-phase device times (ms) of the last msm call, CUDA events on the context's stream:
+ * [0] digits+histogram [1] sort (scan, scatter, items) [2] bucket accumulation [3] bucket reduction
+ * [4] window combine + to_affine [5] total device time. */
+int msmb200_last_timings(msmb200_ctx *ctx, float out_ms[6]);
+/* Number of kernels launched by the last msm call. */
+int msmb200_last_launches(msmb200_ctx *ctx);
+
+/* ---- blst-named drop-ins (signatures of bindings/blst.h:238-240,:274-283,:299-304) ------------------
+ * Exported under an msmb200_ prefix so the library can be linked next to libblst.a; build the reference
+ * drivers with -Dblst_p1s_mult_pippenger=msmb200_blst_p1s_mult_pippenger etc.. Pointer
+ * arrays follow the blst convention: a NULL entry means "contiguous after the previous one". */
+size_t msmb200_blst_p1s_mult_pippenger_scratch_sizeof(size_t npoints);
+void msmb200_blst_p1s_mult_pippenger(void *ret_jacobian, const void *const points[], size_t npoints,
+                                     const unsigned char *const scalars[], size_t nbits, void *scratch);
+size_t msmb200_blst_p2s_mult_pippenger_scratch_sizeof(size_t npoints);
+void msmb200_blst_p2s_mult_pippenger(void *ret_jacobian, const void *const points[], size_t npoints,
+                                     const unsigned char *const scalars[], size_t nbits, void *scratch);
+void msmb200_blst_p1_tile_pippenger_d_CHES(void *ret_jacobian, const void *const points[], size_t npoints,
+                                           const int scalars[], const unsigned char booth_signs[], void *buckets,
+                                           int bucket_set_ascend[], int bucket_value_to_its_index[],
+                                           size_t bucket_set_size, int d_max);
+void msmb200_blst_p2_tile_pippenger_d_CHES(void *ret_jacobian, const void *const points[], size_t npoints,
+                                           const int scalars[], const unsigned char booth_signs[], void *buckets,
+                                           int bucket_set_ascend[], int bucket_value_to_its_index[],
+                                           size_t bucket_set_size, int d_max);
+void msmb200_blst_p1_tile_pippenger_BGMW95(void *ret_jacobian, const void *const points[], size_t npoints,
+                                           const int scalars[], const unsigned char booth_signs[], void *buckets,
+                                           size_t q_exponent);
+void msmb200_blst_p2_tile_pippenger_BGMW95(void *ret_jacobian, const void *const points[], size_t npoints,
+                                           const int scalars[], const unsigned char booth_signs[], void *buckets,
+                                           size_t q_exponent);
+
+/* ---- building blocks exposed for parity tests (each is a batched CUDA kernel launch; host buffers) ---
+ * field ops on n elements. field: 1 = Fp (48 B), 2 = Fp2 (96 B).
+ * op: 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 5 mul_by_3, 6 inverse        (blst_fp_mul ... bindings/blst.h:108-137) */
+int msmb200_test_field_op(int device, int field, int op, const void *a, const void *b, void *out, size_t n);
+/* point ops on n elements, group 1|2. op: 0 jac add-or-double (blst_p1_add_or_double), 1 jac double,
+ * 2 xyzz += affine with sign flags (blst_p1xyzz_dadd_affine), 3 xyzz += xyzz (blst_p1xyzz_dadd),
+ * 4 xyzz -> jacobian, 5 jacobian -> affine (blst_p1_to_affine) */
+int msmb200_test_point_op(int device, int group, int op, const void *a, const void *b, const unsigned char *flags,
+                          void *out, size_t n);
+/* digit decomposition of the context's configuration for n scalars (host). kind 0: CHES -> out_key = bucket
+ * index, out_val = table index | sign<<31 (h entries per scalar); kind 1: BGMW95 (h' entries);
+ * kind 2: Pippenger windows (tiles entries, key = window*(2^(w-1)+1) + |digit|). */
+int msmb200_test_digits(msmb200_ctx *ctx, int kind, const void *scalars_host, size_t n, uint32_t *out_key,
+                        uint32_t *out_val);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSM_B200_H */

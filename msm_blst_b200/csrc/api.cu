@@ -1,0 +1,431 @@
+// C ABI of libmsm_b200.so (include/msm_b200.h): context management, table builds, the four MSM methods,
+// multi-GPU partial/sum entry points, blst-named shims and parity-test hooks. Host code only orchestrates;
+// every computation is a CUDA kernel in msm_kernels.cuh. No CPU fallback exists: CUDA errors are returned.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include "engine.hpp"
+
+using namespace msmb200;
+
+namespace msmb200 {
+
+static thread_local std::string g_create_err;
+
+int ctx_fail(Ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg; else g_create_err = msg;
+    return code;
+}
+int ensure(Ctx *c, DevBuf &b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return 0;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.bytes = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { ctx_fail(c, MSMB200_ECUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); b.p = nullptr; return MSMB200_ECUDA; }
+    b.bytes = want;
+    return 0;
+}
+
+static int ctx_init_common(Ctx *c, int group, int device) {
+    c->group = group;
+    c->device = device;
+    c->ops = group == 1 ? group_ops_g1() : group_ops_g2();
+    MSM_CUDA(c, cudaSetDevice(device));
+    MSM_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    for (auto &e : c->ev) MSM_CUDA(c, cudaEventCreate(&e));
+    MSM_CUDA(c, cudaMallocHost(&c->h_result, 512));
+    return MSMB200_OK;
+}
+
+static void ctx_free(Ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->scalars, &c->keys, &c->vals, &c->sorted, &c->count, &c->packed, &c->scanned, &c->tile_sums, &c->seg_start,
+                      &c->item_start, &c->cursor, &c->item_begin, &c->item_cnt, &c->order, &c->len_hist, &c->len_start, &c->len_cursor,
+                      &c->partial, &c->chunk_a, &c->chunk_b, &c->result, &c->flat, &c->signs, &c->pidx};
+    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    void *ptrs[] = {c->d_bucket_vals, c->d_v2i, c->d_dtab, c->d_points, c->d_table_ches, c->d_table_bgmw};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (c->h_result) cudaFreeHost(c->h_result);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// lazily created context used by the context-free blst-named shims
+static std::mutex g_shim_mu;
+static Ctx *g_shim[3] = {nullptr, nullptr, nullptr};
+static Ctx *shim_ctx(int group) {
+    std::lock_guard<std::mutex> lk(g_shim_mu);
+    if (!g_shim[group]) {
+        Ctx *c = new Ctx();
+        const char *dev = getenv("MSMB200_DEVICE");
+        if (ctx_init_common(c, group, dev ? atoi(dev) : 0) != MSMB200_OK) {
+            fprintf(stderr, "msm_b200: cannot initialise CUDA for blst shim: %s\n", c->err.c_str());
+            abort();  // the blst signatures have no error channel; never fall back to the CPU
+        }
+        g_shim[group] = c;
+    }
+    return g_shim[group];
+}
+
+}  // namespace msmb200
+
+struct msmb200_ctx { Ctx c; };
+static inline Ctx *C(msmb200_ctx *x) { return &x->c; }
+
+extern "C" {
+
+int msmb200_config_lookup(const char *name, msmb200_config *out) {
+    const msmb200_config *c = name ? find_config(name) : nullptr;
+    if (!c || !out) return MSMB200_EINVAL;
+    *out = *c;
+    return MSMB200_OK;
+}
+
+const char *msmb200_last_error(const msmb200_ctx *ctx) { return ctx ? ctx->c.err.c_str() : g_create_err.c_str(); }
+
+int msmb200_ctx_create(msmb200_ctx **out, int group, const msmb200_config *cfg, size_t npoints, int device) {
+    if (!out || !cfg || (group != 1 && group != 2) || npoints == 0) return ctx_fail(nullptr, MSMB200_EINVAL, "bad arguments");
+    if (cfg->e < 4 || cfg->e > 22 || cfg->h < 1 || cfg->h * cfg->e < 255 || cfg->h > 64 || cfg->e_bgmw < 2 || cfg->e_bgmw > 22 ||
+        cfg->h_bgmw * cfg->e_bgmw < 255 || cfg->h_bgmw > 128 || cfg->d < 1 || cfg->d > 8)
+        return ctx_fail(nullptr, MSMB200_EINVAL, "configuration out of range");
+    if ((double)npoints * cfg->h * 3 >= 2147483648.0 || (double)npoints * cfg->h_bgmw >= 2147483648.0)
+        return ctx_fail(nullptr, MSMB200_EINVAL, "table index would exceed 31 bits; shard the points over more contexts");
+    msmb200_ctx *x = new msmb200_ctx();
+    Ctx *c = &x->c;
+    c->cfg = *cfg;
+    c->n = npoints;
+    int rc = ctx_init_common(c, group, device);
+    if (rc) { g_create_err = c->err; ctx_free(c); return rc; }
+    // CHES parameters
+    c->q = 1 << cfg->e;
+    c->bucket_set = build_bucket_set(c->q, cfg->a);
+    if (cfg->bsize && (size_t)cfg->bsize != c->bucket_set.size()) {
+        g_create_err = "bucket set size differs from configured B_SIZE";
+        ctx_free(c);
+        return MSMB200_EINVAL;
+    }
+    int gap = 0;
+    for (size_t i = 1; i < c->bucket_set.size(); i++) gap = std::max(gap, c->bucket_set[i] - c->bucket_set[i - 1]);
+    std::vector<uint32_t> dtab = build_digit_table(c->q, c->bucket_set);
+    bool covered = gap <= cfg->d;
+    for (uint32_t v : dtab) covered = covered && v != DT_INVALID;
+    if (!covered) { g_create_err = "bucket set does not cover all digits / max gap exceeds d"; ctx_free(c); return MSMB200_EINVAL; }
+    std::vector<int> v2i(c->q / 2 + 1, 0);
+    for (size_t i = 0; i < c->bucket_set.size(); i++) v2i[c->bucket_set[i]] = (int)i;
+    c->pip_window = (int)pippenger_window_size(npoints);
+    c->pip_tiles = 255 / c->pip_window + 1;
+#define CREATE_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { g_create_err = std::string(#call) + ": " + cudaGetErrorString(e__); ctx_free(c); return MSMB200_ECUDA; } } while (0)
+    CREATE_CUDA(cudaMalloc(&c->d_bucket_vals, c->bucket_set.size() * sizeof(int)));
+    CREATE_CUDA(cudaMalloc(&c->d_v2i, v2i.size() * sizeof(int)));
+    CREATE_CUDA(cudaMalloc(&c->d_dtab, dtab.size() * sizeof(uint32_t)));
+    CREATE_CUDA(cudaMalloc(&c->d_points, npoints * c->ops->aff_bytes));
+    CREATE_CUDA(cudaMemcpy(c->d_bucket_vals, c->bucket_set.data(), c->bucket_set.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CREATE_CUDA(cudaMemcpy(c->d_v2i, v2i.data(), v2i.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CREATE_CUDA(cudaMemcpy(c->d_dtab, dtab.data(), dtab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+#undef CREATE_CUDA
+    *out = x;
+    return MSMB200_OK;
+}
+
+void msmb200_ctx_destroy(msmb200_ctx *ctx) {
+    if (!ctx) return;
+    Ctx *c = new Ctx(std::move(ctx->c));  // ctx_free deletes a heap Ctx
+    delete ctx;
+    ctx_free(c);
+}
+
+int msmb200_set_stream(msmb200_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    cudaSetDevice(c->device);
+    if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    return MSMB200_OK;
+}
+
+int msmb200_set_points(msmb200_ctx *ctx, const void *points_affine_host) {
+    if (!ctx || !points_affine_host) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    MSM_CUDA(c, cudaSetDevice(c->device));
+    MSM_CUDA(c, cudaMemcpyAsync(c->d_points, points_affine_host, c->n * c->ops->aff_bytes, cudaMemcpyHostToDevice, c->stream));
+    MSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->have_points = true;
+    c->have_ches = c->have_bgmw = false;
+    return MSMB200_OK;
+}
+int msmb200_generate_fix_points(msmb200_ctx *ctx, size_t first) {
+    if (!ctx) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    MSM_CUDA(c, cudaSetDevice(c->device));
+    c->have_ches = c->have_bgmw = false;
+    return c->ops->generate_fix_points(c, first);
+}
+int msmb200_table_build_ches(msmb200_ctx *ctx) {
+    if (!ctx) return MSMB200_EINVAL;
+    MSM_CUDA(C(ctx), cudaSetDevice(C(ctx)->device));
+    return C(ctx)->ops->table_build(C(ctx), 0);
+}
+int msmb200_table_build_bgmw95(msmb200_ctx *ctx) {
+    if (!ctx) return MSMB200_EINVAL;
+    MSM_CUDA(C(ctx), cudaSetDevice(C(ctx)->device));
+    return C(ctx)->ops->table_build(C(ctx), 1);
+}
+int msmb200_download(msmb200_ctx *ctx, int which, size_t first, size_t count, void *out_host) {
+    if (!ctx || !out_host) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    const void *src = nullptr;
+    size_t total = 0;
+    if (which == 0) { src = c->have_points ? c->d_points : nullptr; total = c->n; }
+    else if (which == 1) { src = c->have_ches ? c->d_table_ches : nullptr; total = c->n * (size_t)c->cfg.h * 3; }
+    else if (which == 2) { src = c->have_bgmw ? c->d_table_bgmw : nullptr; total = c->n * (size_t)c->cfg.h_bgmw; }
+    else return ctx_fail(c, MSMB200_EINVAL, "which must be 0, 1 or 2");
+    if (!src) return ctx_fail(c, MSMB200_ESTATE, "requested array not built");
+    if (first + count > total) return ctx_fail(c, MSMB200_EINVAL, "range out of bounds");
+    MSM_CUDA(c, cudaSetDevice(c->device));
+    size_t ab = c->ops->aff_bytes;
+    MSM_CUDA(c, cudaMemcpyAsync(out_host, (const char *)src + first * ab, count * ab, cudaMemcpyDeviceToHost, c->stream));
+    MSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MSMB200_OK;
+}
+long msmb200_bucket_set(msmb200_ctx *ctx, int *out, long cap) {
+    if (!ctx) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    if (out && cap >= (long)c->bucket_set.size()) memcpy(out, c->bucket_set.data(), c->bucket_set.size() * sizeof(int));
+    return (long)c->bucket_set.size();
+}
+
+int msmb200_msm_device(msmb200_ctx *ctx, int method, const void *scalars_dev, void *out_affine_host) {
+    if (!ctx || !scalars_dev || !out_affine_host) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    MSM_CUDA(c, cudaSetDevice(c->device));
+    int rc = c->ops->msm(c, method, scalars_dev, nullptr, true);
+    if (rc) return rc;
+    memcpy(out_affine_host, c->h_result, c->ops->aff_bytes);
+    return MSMB200_OK;
+}
+int msmb200_msm(msmb200_ctx *ctx, int method, const void *scalars_host, void *out_affine_host) {
+    if (!ctx || !scalars_host || !out_affine_host) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    MSM_CUDA(c, cudaSetDevice(c->device));
+    if (ensure(c, c->scalars, c->n * 32)) return MSMB200_ECUDA;
+    MSM_CUDA(c, cudaMemcpyAsync(c->scalars.p, scalars_host, c->n * 32, cudaMemcpyHostToDevice, c->stream));
+    return msmb200_msm_device(ctx, method, c->scalars.p, out_affine_host);
+}
+int msmb200_msm_partial_device(msmb200_ctx *ctx, int method, const void *scalars_dev, void *out_jacobian_dev) {
+    if (!ctx || !scalars_dev || !out_jacobian_dev) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    MSM_CUDA(c, cudaSetDevice(c->device));
+    return c->ops->msm(c, method, scalars_dev, out_jacobian_dev, false);
+}
+int msmb200_sum_partials_device(msmb200_ctx *ctx, const void *partials_dev, int count, void *out_affine_host) {
+    if (!ctx || !partials_dev || count < 1 || !out_affine_host) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    MSM_CUDA(c, cudaSetDevice(c->device));
+    int rc = c->ops->sum_partials(c, partials_dev, count);
+    if (rc) return rc;
+    memcpy(out_affine_host, c->h_result, c->ops->aff_bytes);
+    return MSMB200_OK;
+}
+
+int msmb200_last_timings(msmb200_ctx *ctx, float out_ms[6]) {
+    if (!ctx || !out_ms) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    MSM_CUDA(c, cudaSetDevice(c->device));
+    MSM_CUDA(c, cudaEventSynchronize(c->ev[5]));
+    for (int k = 0; k < 5; k++) MSM_CUDA(c, cudaEventElapsedTime(&c->last_ms[k], c->ev[k], c->ev[k + 1]));
+    MSM_CUDA(c, cudaEventElapsedTime(&c->last_ms[5], c->ev[0], c->ev[5]));
+    memcpy(out_ms, c->last_ms, sizeof(c->last_ms));
+    return MSMB200_OK;
+}
+int msmb200_last_launches(msmb200_ctx *ctx) { return ctx ? C(ctx)->launches : MSMB200_EINVAL; }
+
+// Serialisation is a pure byte shuffle of one 96/192-byte result plus a from-Montgomery multiplication; it is
+// done on the device like everything else (point_op 6 would be overkill) — here via the field-op kernel.
+int msmb200_affine_serialize(int group, const void *affine_host, unsigned char *out) {
+    if ((group != 1 && group != 2) || !affine_host || !out) return MSMB200_EINVAL;
+    size_t nfp = group == 1 ? 2 : 4, nbytes = nfp * 48;
+    bool inf = true;
+    for (size_t i = 0; i < nbytes; i++) inf = inf && ((const unsigned char *)affine_host)[i] == 0;
+    if (inf) { memset(out, 0, nbytes); out[0] = 0x40; return MSMB200_OK; }
+    // from_fp: multiply by 1 (non-Montgomery) on the device
+    std::vector<uint64_t> one(nfp * 6, 0), res(nfp * 6);
+    for (size_t i = 0; i < nfp; i++) one[6 * i] = 1;
+    int rc = msmb200_test_field_op(-1, 1, 0, affine_host, one.data(), res.data(), nfp);
+    if (rc) return rc;
+    // G1: X | Y.  G2: X.im | X.re | Y.im | Y.re   (src/e2.c:176-192), each 48 bytes big-endian
+    static const int order1[2] = {0, 1}, order2[4] = {1, 0, 3, 2};
+    const int *ord = group == 1 ? order1 : order2;
+    for (size_t k = 0; k < nfp; k++) {
+        const uint64_t *l = &res[6 * ord[k]];
+        for (int b = 0; b < 48; b++) out[48 * k + b] = (unsigned char)(l[(47 - b) / 8] >> (8 * ((47 - b) % 8)));
+    }
+    return MSMB200_OK;
+}
+
+// ---- parity-test hooks ------------------------------------------------------------------------------
+static int with_device_buffers(int device, const void *a, size_t abytes, const void *b, size_t bbytes, const unsigned char *flags,
+                               size_t fbytes, void *out, size_t obytes, int (*fn)(const void *, const void *, const unsigned char *, void *, void *),
+                               void *arg) {
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return MSMB200_ECUDA;
+    void *da = nullptr, *db = nullptr, *df = nullptr, *dout = nullptr;
+    int rc = MSMB200_ECUDA;
+    do {
+        if (cudaMalloc(&da, abytes) != cudaSuccess) break;
+        if (b && cudaMalloc(&db, bbytes) != cudaSuccess) break;
+        if (flags && cudaMalloc(&df, fbytes) != cudaSuccess) break;
+        if (cudaMalloc(&dout, obytes) != cudaSuccess) break;
+        if (cudaMemcpy(da, a, abytes, cudaMemcpyHostToDevice) != cudaSuccess) break;
+        if (b && cudaMemcpy(db, b, bbytes, cudaMemcpyHostToDevice) != cudaSuccess) break;
+        if (flags && cudaMemcpy(df, flags, fbytes, cudaMemcpyHostToDevice) != cudaSuccess) break;
+        rc = fn(da, db, (const unsigned char *)df, dout, arg);
+        if (rc) break;
+        rc = MSMB200_ECUDA;
+        if (cudaDeviceSynchronize() != cudaSuccess) break;
+        if (cudaMemcpy(out, dout, obytes, cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        rc = MSMB200_OK;
+    } while (0);
+    cudaFree(da); cudaFree(db); cudaFree(df); cudaFree(dout);
+    return rc;
+}
+struct FieldArg { int field, op; size_t n; };
+static int field_fn(const void *a, const void *b, const unsigned char *, void *out, void *arg) {
+    FieldArg *f = (FieldArg *)arg;
+    return group_ops_g1()->field_op(f->field, f->op, a, b, out, f->n);
+}
+int msmb200_test_field_op(int device, int field, int op, const void *a, const void *b, void *out, size_t n) {
+    if ((field != 1 && field != 2) || op < 0 || op > 6 || !a || !out || n == 0) return MSMB200_EINVAL;
+    size_t eb = field == 1 ? 48 : 96;
+    FieldArg arg{field, op, n};
+    return with_device_buffers(device, a, n * eb, b, n * eb, nullptr, 0, out, n * eb, field_fn, &arg);
+}
+struct PointArg { int group, op; size_t n; };
+static int point_fn(const void *a, const void *b, const unsigned char *flags, void *out, void *arg) {
+    PointArg *p = (PointArg *)arg;
+    const GroupOps *ops = p->group == 1 ? group_ops_g1() : group_ops_g2();
+    return ops->point_op(p->op, a, b, flags, out, p->n);
+}
+int msmb200_test_point_op(int device, int group, int op, const void *a, const void *b, const unsigned char *flags, void *out, size_t n) {
+    if ((group != 1 && group != 2) || op < 0 || op > 5 || !a || !out || n == 0) return MSMB200_EINVAL;
+    const GroupOps *ops = group == 1 ? group_ops_g1() : group_ops_g2();
+    size_t A = ops->aff_bytes, J = ops->jac_bytes, X = ops->xyzz_bytes;
+    size_t ab[6] = {J, J, X, X, X, J}, bb[6] = {J, 0, A, X, 0, 0}, ob[6] = {J, J, X, X, J, A};
+    if (bb[op] && !b) return MSMB200_EINVAL;
+    PointArg arg{group, op, n};
+    return with_device_buffers(device, a, n * ab[op], bb[op] ? b : nullptr, n * bb[op], flags, n, out, n * ob[op], point_fn, &arg);
+}
+int msmb200_test_digits(msmb200_ctx *ctx, int kind, const void *scalars_host, size_t n, uint32_t *out_key, uint32_t *out_val) {
+    if (!ctx || kind < 0 || kind > 2 || !scalars_host || !out_key || !out_val || n == 0 || n > C(ctx)->n) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    MSM_CUDA(c, cudaSetDevice(c->device));
+    size_t per = kind == 0 ? c->cfg.h : kind == 1 ? c->cfg.h_bgmw : c->pip_tiles;
+    size_t m = n * per;
+    if (ensure(c, c->scalars, n * 32) || ensure(c, c->keys, m * 4) || ensure(c, c->vals, m * 4)) return MSMB200_ECUDA;
+    MSM_CUDA(c, cudaMemcpyAsync(c->scalars.p, scalars_host, n * 32, cudaMemcpyHostToDevice, c->stream));
+    int rc = c->ops->digits(c, kind, c->scalars.p, n, (uint32_t *)c->keys.p, (uint32_t *)c->vals.p);
+    if (rc) return rc;
+    MSM_CUDA(c, cudaMemcpy(out_key, c->keys.p, m * 4, cudaMemcpyDeviceToHost));
+    MSM_CUDA(c, cudaMemcpy(out_val, c->vals.p, m * 4, cudaMemcpyDeviceToHost));
+    return MSMB200_OK;
+}
+
+// ---- blst-named shims ---------------------------------------------------------------------------------
+// blst pointer-array convention (src/multi_scalar.c:401,:413): NULL means "next contiguous element".
+static void gather_ptr_array(std::vector<unsigned char> &dst, const void *const ptrs[], size_t count, size_t elem, size_t out_elem) {
+    dst.assign(count * out_elem, 0);
+    const unsigned char *cur = nullptr;
+    size_t pi = 0;
+    for (size_t i = 0; i < count; i++) {
+        if (i == 0) cur = (const unsigned char *)ptrs[pi++];
+        else if (ptrs[pi] != nullptr) cur = (const unsigned char *)ptrs[pi++];
+        else cur += elem;
+        memcpy(&dst[i * out_elem], cur, elem);
+    }
+}
+static void shim_fail(Ctx *c, const char *what) {
+    fprintf(stderr, "msm_b200: %s failed: %s\n", what, c->err.c_str());
+    abort();  // void blst signature: no error channel, and never a CPU fallback
+}
+static void shim_mult_pippenger(int group, void *ret, const void *const points[], size_t npoints, const unsigned char *const scalars[],
+                                size_t nbits) {
+    Ctx *c = shim_ctx(group);
+    size_t ab = c->ops->aff_bytes, jb = c->ops->jac_bytes;
+    if (npoints == 0 || nbits == 0 || nbits > 255) { memset(ret, 0, jb); return; }
+    cudaSetDevice(c->device);
+    std::vector<unsigned char> hp, hs;
+    gather_ptr_array(hp, points, npoints, ab, ab);
+    gather_ptr_array(hs, (const void *const *)scalars, npoints, (nbits + 7) / 8, 32);
+    void *dp = nullptr, *ds = nullptr, *dj = nullptr;
+    if (cudaMalloc(&dp, hp.size()) != cudaSuccess || cudaMalloc(&ds, hs.size()) != cudaSuccess || cudaMalloc(&dj, jb) != cudaSuccess) {
+        c->err = "cudaMalloc"; shim_fail(c, "blst_pNs_mult_pippenger");
+    }
+    cudaMemcpyAsync(dp, hp.data(), hp.size(), cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(ds, hs.data(), hs.size(), cudaMemcpyHostToDevice, c->stream);
+    if (c->ops->pippenger(c, dp, npoints, ds, (int)nbits, dj, false)) shim_fail(c, "blst_pNs_mult_pippenger");
+    cudaMemcpyAsync(ret, dj, jb, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pNs_mult_pippenger"); }
+    cudaFree(dp); cudaFree(ds); cudaFree(dj);
+}
+static void shim_tile(int group, void *ret, const void *const points[], size_t npoints, const int scalars[], const unsigned char signs[],
+                      const int *bucket_set_ascend, const int *v2i, size_t nbuckets, int d_max) {
+    Ctx *c = shim_ctx(group);
+    size_t ab = c->ops->aff_bytes, jb = c->ops->jac_bytes;
+    cudaSetDevice(c->device);
+    // points[k] are arbitrary host pointers (main_p1.cpp:219,:224 point into the 3nh table): gather them
+    std::vector<unsigned char> hp(npoints * ab);
+    std::vector<uint32_t> pidx(npoints);
+    for (size_t k = 0; k < npoints; k++) { memcpy(&hp[k * ab], points[k], ab); pidx[k] = (uint32_t)k; }
+    size_t v2i_len = bucket_set_ascend ? (size_t)bucket_set_ascend[nbuckets - 1] + 1 : 0;
+    void *dp = nullptr, *dsc = nullptr, *dsg = nullptr, *dpi = nullptr, *dj = nullptr, *dbs = nullptr, *dv = nullptr;
+    bool ok = cudaMalloc(&dp, hp.size()) == cudaSuccess && cudaMalloc(&dsc, npoints * 4) == cudaSuccess && cudaMalloc(&dsg, npoints) == cudaSuccess &&
+              cudaMalloc(&dpi, npoints * 4) == cudaSuccess && cudaMalloc(&dj, jb) == cudaSuccess;
+    if (ok && bucket_set_ascend) ok = cudaMalloc(&dbs, nbuckets * 4) == cudaSuccess && cudaMalloc(&dv, v2i_len * 4) == cudaSuccess;
+    if (!ok) { c->err = "cudaMalloc"; shim_fail(c, "blst_pN_tile_pippenger"); }
+    cudaMemcpyAsync(dp, hp.data(), hp.size(), cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(dsc, scalars, npoints * 4, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(dsg, signs, npoints, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(dpi, pidx.data(), npoints * 4, cudaMemcpyHostToDevice, c->stream);
+    if (bucket_set_ascend) {
+        cudaMemcpyAsync(dbs, bucket_set_ascend, nbuckets * 4, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(dv, v2i, v2i_len * 4, cudaMemcpyHostToDevice, c->stream);
+    }
+    if (c->ops->tile(c, dp, (const int *)dsc, (const unsigned char *)dsg, (const uint32_t *)dpi, npoints, (const int *)dv, (const int *)dbs, nbuckets,
+                     d_max, dj))
+        shim_fail(c, "blst_pN_tile_pippenger");
+    cudaMemcpyAsync(ret, dj, jb, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pN_tile_pippenger"); }
+    cudaFree(dp); cudaFree(dsc); cudaFree(dsg); cudaFree(dpi); cudaFree(dj); cudaFree(dbs); cudaFree(dv);
+}
+
+size_t msmb200_blst_p1s_mult_pippenger_scratch_sizeof(size_t npoints) { return (size_t)192 << (pippenger_window_size(npoints) - 1); }
+size_t msmb200_blst_p2s_mult_pippenger_scratch_sizeof(size_t npoints) { return (size_t)384 << (pippenger_window_size(npoints) - 1); }
+void msmb200_blst_p1s_mult_pippenger(void *ret, const void *const points[], size_t npoints, const unsigned char *const scalars[], size_t nbits, void *) {
+    shim_mult_pippenger(1, ret, points, npoints, scalars, nbits);
+}
+void msmb200_blst_p2s_mult_pippenger(void *ret, const void *const points[], size_t npoints, const unsigned char *const scalars[], size_t nbits, void *) {
+    shim_mult_pippenger(2, ret, points, npoints, scalars, nbits);
+}
+void msmb200_blst_p1_tile_pippenger_d_CHES(void *ret, const void *const points[], size_t npoints, const int scalars[], const unsigned char booth_signs[],
+                                           void *, int bucket_set_ascend[], int bucket_value_to_its_index[], size_t bucket_set_size, int d_max) {
+    shim_tile(1, ret, points, npoints, scalars, booth_signs, bucket_set_ascend, bucket_value_to_its_index, bucket_set_size, d_max);
+}
+void msmb200_blst_p2_tile_pippenger_d_CHES(void *ret, const void *const points[], size_t npoints, const int scalars[], const unsigned char booth_signs[],
+                                           void *, int bucket_set_ascend[], int bucket_value_to_its_index[], size_t bucket_set_size, int d_max) {
+    shim_tile(2, ret, points, npoints, scalars, booth_signs, bucket_set_ascend, bucket_value_to_its_index, bucket_set_size, d_max);
+}
+void msmb200_blst_p1_tile_pippenger_BGMW95(void *ret, const void *const points[], size_t npoints, const int scalars[], const unsigned char booth_signs[],
+                                           void *, size_t q_exponent) {
+    shim_tile(1, ret, points, npoints, scalars, booth_signs, nullptr, nullptr, ((size_t)1 << (q_exponent - 1)) + 1, 1);
+}
+void msmb200_blst_p2_tile_pippenger_BGMW95(void *ret, const void *const points[], size_t npoints, const int scalars[], const unsigned char booth_signs[],
+                                           void *, size_t q_exponent) {
+    shim_tile(2, ret, points, npoints, scalars, booth_signs, nullptr, nullptr, ((size_t)1 << (q_exponent - 1)) + 1, 1);
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// Host-side state of one MSM context (one per GPU / per point shard) and the per-group entry table.
+// The context is the device-resident form of the globals of the reference driver (main_p1.cpp:41-50):
+// FIX_POINTS_LIST, BUCKET_SET, BUCKET_VALUE_TO_ITS_INDEX, DIGIT_CONVERSION_HASH_TABLE and the two
+// PRECOMPUTATION_POINTS_LISTs live in HBM; pointer arrays into host tables become table indices.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "params.hpp"
+
+namespace msmb200 {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct GroupOps;
+
+struct Ctx {
+    int group = 0;
+    msmb200_config cfg{};
+    size_t n = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    const GroupOps *ops = nullptr;
+    std::string err;
+
+    // parameters
+    std::vector<int> bucket_set;  // host copy of BUCKET_SET
+    int q = 0;
+    int pip_window = 0, pip_tiles = 0;
+    int *d_bucket_vals = nullptr;     // BUCKET_SET
+    int *d_v2i = nullptr;             // BUCKET_VALUE_TO_ITS_INDEX  [q/2+1]
+    uint32_t *d_dtab = nullptr;       // packed DIGIT_CONVERSION_HASH_TABLE [q+1]
+
+    // points and tables (affine, Montgomery)
+    void *d_points = nullptr;      bool have_points = false;
+    void *d_table_ches = nullptr;  bool have_ches = false;
+    void *d_table_bgmw = nullptr;  bool have_bgmw = false;
+
+    // workspace (grow-only)
+    DevBuf scalars, keys, vals, sorted, count, packed, scanned, tile_sums, seg_start, item_start, cursor,
+        item_begin, item_cnt, order, len_hist, len_start, len_cursor, partial, chunk_a, chunk_b, result,
+        flat, signs, pidx;
+    void *h_result = nullptr;  // pinned staging for the result
+
+    // timing
+    cudaEvent_t ev[8] = {};
+    float last_ms[6] = {0, 0, 0, 0, 0, 0};
+    int launches = 0;
+};
+
+struct GroupOps {
+    size_t aff_bytes, jac_bytes, xyzz_bytes;
+    // method 1..4; scalars in device memory; writes Jacobian partial to d_out_jac (device) and/or affine to
+    // ctx->h_result (host, synchronises the stream) when want_affine.
+    int (*msm)(Ctx *, int method, const void *d_scalars, void *d_out_jac, bool want_affine);
+    int (*generate_fix_points)(Ctx *, size_t first);
+    int (*table_build)(Ctx *, int which);  // 0 CHES 3nh, 1 BGMW95
+    int (*sum_partials)(Ctx *, const void *d_partials, int count);
+    // generic tile: device arrays of bucket index (or value when v2i given) / sign / point index into d_table
+    int (*tile)(Ctx *, const void *d_table, const int *d_bvals, const unsigned char *d_signs, const uint32_t *d_pidx,
+                size_t m, const int *d_v2i, const int *d_bucket_vals, size_t nbuckets, int d_max, void *d_out_jac);
+    int (*pippenger)(Ctx *, const void *d_points, size_t npoints, const void *d_scalars, int nbits, void *d_out_jac,
+                     bool want_affine);
+    int (*field_op)(int field, int op, const void *a, const void *b, void *out, size_t n);
+    int (*point_op)(int op, const void *a, const void *b, const unsigned char *flags, void *out, size_t n);
+    int (*digits)(Ctx *, int kind, const void *d_scalars, size_t n, uint32_t *d_keys, uint32_t *d_vals);
+};
+
+const GroupOps *group_ops_g1();
+const GroupOps *group_ops_g2();
+
+int ctx_fail(Ctx *c, int code, const std::string &msg);
+int ensure(Ctx *c, DevBuf &b, size_t bytes);
+
+#define MSM_CUDA(c, call)                                                                              \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return ctx_fail((c), MSMB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));  \
+    } while (0)
+
+}  // namespace msmb200

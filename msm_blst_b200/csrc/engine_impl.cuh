@@ -1,0 +1,311 @@
+// Host orchestration of the MSM pipeline for one group (F = fp_t: G1, F = fp2_t: G2). Included by
+// engine_g1.cu / engine_g2.cu, which instantiate it once each (separate translation units so the two
+// groups compile in parallel). All work is enqueued on the context's stream; nothing here computes on the CPU.
+#pragma once
+#include <algorithm>
+#include "engine.hpp"
+#include "msm_kernels.cuh"
+
+namespace msmb200 {
+
+static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+struct Layout {
+    size_t m;            // number of (key, val) entries
+    uint32_t nbw;        // buckets per window (local index 0 unused)
+    uint32_t nwindows;
+    uint32_t wbits;      // doublings between windows
+    const int *bucket_vals;  // device, or nullptr for dense (value = local index)
+    int d_max;
+};
+
+// sort + accumulate + reduce + finalize over entries already in c->keys / c->vals with histogram in c->count
+// F: field type of the hot kernels (multiplier inlined); FC: same layout, out-of-line multiplier, for the rest
+template <class F, class FC>
+static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d_out_jac, bool want_affine) {
+    cudaStream_t st = c->stream;
+    const size_t nb = (size_t)L.nbw * L.nwindows;
+    const size_t m = L.m;
+    // work-item length: a few times the mean bucket load, bounded
+    size_t avg = std::max<size_t>(1, m / std::max<size_t>(1, nb));
+    uint32_t item_len = (uint32_t)std::min<size_t>(1024, std::max<size_t>(128, 8 * avg));
+    const size_t max_items = std::min(nb, m) + m / item_len + 1;
+    const size_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
+
+    if (ensure(c, c->packed, nb * 8) || ensure(c, c->scanned, nb * 8) || ensure(c, c->tile_sums, (ntiles + 1) * 8) ||
+        ensure(c, c->seg_start, nb * 4) || ensure(c, c->item_start, nb * 4) || ensure(c, c->cursor, nb * 4) ||
+        ensure(c, c->sorted, m * 4) || ensure(c, c->item_begin, max_items * 4) || ensure(c, c->item_cnt, max_items * 4) ||
+        ensure(c, c->order, max_items * 4) || ensure(c, c->len_hist, (item_len + 1) * 4) ||
+        ensure(c, c->len_start, (item_len + 1) * 4) || ensure(c, c->len_cursor, (item_len + 1) * 4) ||
+        ensure(c, c->partial, max_items * sizeof(xyzz_t<F>)) || ensure(c, c->result, sizeof(jac_t<F>) + sizeof(aff_t<F>)))
+        return MSMB200_ECUDA;
+
+    uint32_t *count = (uint32_t *)c->count.p;
+    // ---- sort by bucket ----
+    prep_counts_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, (uint64_t *)c->packed.p, nb, item_len);
+    scan_tiles_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>((const uint64_t *)c->packed.p, (uint64_t *)c->scanned.p,
+                                                                   (uint64_t *)c->tile_sums.p, nb);
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>((uint64_t *)c->tile_sums.p, ntiles);
+    scan_finish_kernel<<<blocks_for(nb, 256), 256, 0, st>>>((const uint64_t *)c->scanned.p, (const uint64_t *)c->tile_sums.p,
+                                                            (uint32_t *)c->seg_start.p, (uint32_t *)c->item_start.p,
+                                                            (uint32_t *)c->cursor.p, nb);
+    scatter_kernel<<<blocks_for(m, 256), 256, 0, st>>>((const uint32_t *)c->keys.p, (const uint32_t *)c->vals.p, m,
+                                                       (const uint32_t *)c->seg_start.p, (uint32_t *)c->cursor.p,
+                                                       (uint32_t *)c->sorted.p);
+    MSM_CUDA(c, cudaMemsetAsync(c->len_hist.p, 0, (item_len + 1) * 4, st));
+    itemize_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, (const uint32_t *)c->seg_start.p, (const uint32_t *)c->item_start.p,
+                                                        nb, item_len, (uint32_t *)c->item_begin.p, (uint32_t *)c->item_cnt.p,
+                                                        (uint32_t *)c->len_hist.p);
+    len_scan_kernel<<<1, 32, 0, st>>>((const uint32_t *)c->len_hist.p, (uint32_t *)c->len_start.p, (uint32_t *)c->len_cursor.p, item_len);
+    const uint64_t *totals = (const uint64_t *)c->tile_sums.p + ntiles;
+    order_items_kernel<<<blocks_for(max_items, 256), 256, 0, st>>>((const uint32_t *)c->item_cnt.p, totals,
+                                                                   (const uint32_t *)c->len_start.p, (uint32_t *)c->len_cursor.p,
+                                                                   (uint32_t *)c->order.p);
+    c->launches += 8;
+    MSM_CUDA(c, cudaEventRecord(c->ev[2], st));
+    // ---- accumulate ----
+    accumulate_kernel<F><<<blocks_for(max_items, 128), 128, 0, st>>>(d_table, (const uint32_t *)c->sorted.p,
+                                                                     (const uint32_t *)c->item_begin.p, (const uint32_t *)c->item_cnt.p,
+                                                                     (const uint32_t *)c->order.p, totals, (xyzz_t<F> *)c->partial.p);
+    combine_items_kernel<FC><<<blocks_for(nb, 128), 128, 0, st>>>(count, (const uint32_t *)c->item_start.p, nb, item_len,
+                                                                  (xyzz_t<FC> *)c->partial.p);
+    c->launches += 2;
+    MSM_CUDA(c, cudaEventRecord(c->ev[3], st));
+    // ---- reduce ----
+    uint32_t chunk = 32;
+    // keep at least ~4 warps per SM busy, but never fewer than 8 buckets per chunk
+    while (chunk > 8 && (size_t)L.nwindows * ((L.nbw + chunk - 1) / chunk) < 148 * 128) chunk >>= 1;
+    uint32_t cpw = (L.nbw - 1 + chunk - 1) / chunk;
+    if (cpw == 0) cpw = 1;
+    size_t nchunks = (size_t)cpw * L.nwindows;
+    if (ensure(c, c->chunk_a, nchunks * sizeof(xyzz_t<F>)) || ensure(c, c->chunk_b, (nchunks / 8 + L.nwindows + 1) * sizeof(xyzz_t<F>)))
+        return MSMB200_ECUDA;
+    if (L.bucket_vals)
+        reduce_chunks_kernel<F, false><<<blocks_for(nchunks, 128), 128, 0, st>>>(
+            (const xyzz_t<F> *)c->partial.p, count, (const uint32_t *)c->item_start.p, L.bucket_vals, L.nbw, L.nwindows, chunk, cpw,
+            L.d_max, (xyzz_t<F> *)c->chunk_a.p);
+    else
+        reduce_chunks_kernel<F, true><<<blocks_for(nchunks, 128), 128, 0, st>>>(
+            (const xyzz_t<F> *)c->partial.p, count, (const uint32_t *)c->item_start.p, nullptr, L.nbw, L.nwindows, chunk, cpw, 1,
+            (xyzz_t<F> *)c->chunk_a.p);
+    c->launches += 1;
+    xyzz_t<F> *cur = (xyzz_t<F> *)c->chunk_a.p, *nxt = (xyzz_t<F> *)c->chunk_b.p;
+    uint32_t per = cpw;
+    while (per > 1) {
+        uint32_t groups = (per + 7) / 8;
+        sum_groups_kernel<FC><<<blocks_for((size_t)groups * L.nwindows, 128), 128, 0, st>>>((const xyzz_t<FC> *)cur, per, L.nwindows, 8, groups, (xyzz_t<FC> *)nxt);
+        c->launches += 1;
+        std::swap(cur, nxt);
+        per = groups;
+    }
+    MSM_CUDA(c, cudaEventRecord(c->ev[4], st));
+    // ---- finalize ----
+    jac_t<F> *d_jac = d_out_jac ? (jac_t<F> *)d_out_jac : (jac_t<F> *)c->result.p;
+    aff_t<F> *d_aff = (aff_t<F> *)((char *)c->result.p + sizeof(jac_t<F>));
+    finalize_kernel<FC><<<1, 32, 0, st>>>((const xyzz_t<FC> *)cur, L.nwindows, L.wbits, (jac_t<FC> *)d_jac, want_affine ? (aff_t<FC> *)d_aff : nullptr);
+    c->launches += 1;
+    if (want_affine) MSM_CUDA(c, cudaMemcpyAsync(c->h_result, d_aff, sizeof(aff_t<F>), cudaMemcpyDeviceToHost, st));
+    MSM_CUDA(c, cudaEventRecord(c->ev[5], st));
+    MSM_CUDA(c, cudaGetLastError());
+    if (want_affine) MSM_CUDA(c, cudaStreamSynchronize(st));
+    return MSMB200_OK;
+}
+
+static int prepare_entries(Ctx *c, size_t m, size_t nb) {
+    if (ensure(c, c->keys, m * 4) || ensure(c, c->vals, m * 4) || ensure(c, c->count, nb * 4)) return MSMB200_ECUDA;
+    MSM_CUDA(c, cudaMemsetAsync(c->count.p, 0, nb * 4, c->stream));
+    return MSMB200_OK;
+}
+
+static inline bool bgmw_trick(const msmb200_config &cfg) {
+    return cfg.n_exp == 13 || cfg.n_exp == 14 || cfg.n_exp == 16 || cfg.n_exp == 17;  // main_p1.cpp:311
+}
+
+template <class F, class FC>
+static int pippenger_impl(Ctx *c, const void *d_points, size_t npoints, const void *d_scalars, int nbits, void *d_out_jac,
+                          bool want_affine) {
+    cudaStream_t st = c->stream;
+    c->launches = 0;
+    MSM_CUDA(c, cudaEventRecord(c->ev[0], st));
+    int w = (int)pippenger_window_size(npoints);
+    int tiles = nbits / w + 1;
+    uint32_t nbw = (1u << (w - 1)) + 1u;
+    size_t m = npoints * (size_t)tiles, nb = (size_t)nbw * tiles;
+    int rc = prepare_entries(c, m, nb);
+    if (rc) return rc;
+    digits_booth_kernel<<<blocks_for(npoints, 256), 256, 0, st>>>((const uint32_t *)d_scalars, npoints, nbits, w, tiles,
+                                                                  (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p);
+    c->launches += 1;
+    MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
+    Layout L{m, nbw, (uint32_t)tiles, (uint32_t)w, nullptr, 1};
+    return run_buckets<F, FC>(c, L, (const aff_t<F> *)d_points, d_out_jac, want_affine);
+}
+
+template <class F, class FC> static int msm_impl(Ctx *c, int method, const void *d_scalars, void *d_out_jac, bool want_affine) {
+    cudaStream_t st = c->stream;
+    const msmb200_config &cfg = c->cfg;
+    const size_t n = c->n;
+    if (method == MSMB200_PIPPENGER) {
+        if (!c->have_points) return ctx_fail(c, MSMB200_ESTATE, "fixed points not set");
+        return pippenger_impl<F, FC>(c, c->d_points, n, d_scalars, 255, d_out_jac, want_affine);
+    }
+    c->launches = 0;
+    MSM_CUDA(c, cudaEventRecord(c->ev[0], st));
+    if (method == MSMB200_CHES || method == MSMB200_CHES_INTEGRAL) {
+        if (!c->have_ches) return ctx_fail(c, MSMB200_ESTATE, "CHES table not built");
+        size_t m = n * (size_t)cfg.h, nb = c->bucket_set.size();
+        int rc = prepare_entries(c, m, nb);
+        if (rc) return rc;
+        if (method == MSMB200_CHES) {
+            digits_ches_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab,
+                                                                   (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p);
+            c->launches += 1;
+        } else {
+            if (ensure(c, c->flat, (m + 2) * 4) || ensure(c, c->signs, m) || ensure(c, c->pidx, m * 4)) return MSMB200_ECUDA;
+            digits_std_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, (int *)c->flat.p);
+            construct_nh_kernel<<<blocks_for(n, 256), 256, 0, st>>>((int *)c->flat.p, (unsigned char *)c->signs.p, (uint32_t *)c->pidx.p,
+                                                                    n, cfg.h, c->d_dtab, c->d_bucket_vals);
+            tile_lookup_kernel<<<blocks_for(m, 256), 256, 0, st>>>((const int *)c->flat.p, (const unsigned char *)c->signs.p,
+                                                                   (const uint32_t *)c->pidx.p, m, c->d_v2i, (uint32_t *)c->keys.p,
+                                                                   (uint32_t *)c->vals.p, (uint32_t *)c->count.p);
+            c->launches += 3;
+        }
+        MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
+        Layout L{m, (uint32_t)nb, 1, 0, c->d_bucket_vals, cfg.d};
+        return run_buckets<F, FC>(c, L, (const aff_t<F> *)c->d_table_ches, d_out_jac, want_affine);
+    }
+    if (method == MSMB200_BGMW95) {
+        if (!c->have_bgmw) return ctx_fail(c, MSMB200_ESTATE, "BGMW95 table not built");
+        size_t m = n * (size_t)cfg.h_bgmw;
+        uint32_t nbw = (1u << (cfg.e_bgmw - 1)) + 1u;
+        int rc = prepare_entries(c, m, nbw);
+        if (rc) return rc;
+        digits_bgmw_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h_bgmw, cfg.e_bgmw,
+                                                               bgmw_trick(cfg) ? 1 : 0, (uint32_t *)c->keys.p, (uint32_t *)c->vals.p,
+                                                               (uint32_t *)c->count.p);
+        c->launches += 1;
+        MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
+        Layout L{m, nbw, 1, 0, nullptr, 1};
+        return run_buckets<F, FC>(c, L, (const aff_t<F> *)c->d_table_bgmw, d_out_jac, want_affine);
+    }
+    return ctx_fail(c, MSMB200_EINVAL, "unknown method");
+}
+
+// generic tile over caller-provided (bucket value|index, sign, point index) arrays: the device half of the
+// blst_p1_tile_pippenger_d_CHES / _BGMW95 shims
+template <class F, class FC>
+static int tile_impl(Ctx *c, const void *d_table, const int *d_bvals, const unsigned char *d_signs, const uint32_t *d_pidx, size_t m,
+                     const int *d_v2i, const int *d_bucket_vals, size_t nbuckets, int d_max, void *d_out_jac) {
+    cudaStream_t st = c->stream;
+    c->launches = 0;
+    MSM_CUDA(c, cudaEventRecord(c->ev[0], st));
+    int rc = prepare_entries(c, m, nbuckets);
+    if (rc) return rc;
+    tile_lookup_kernel<<<blocks_for(m, 256), 256, 0, st>>>(d_bvals, d_signs, d_pidx, m, d_v2i, (uint32_t *)c->keys.p, (uint32_t *)c->vals.p,
+                                                           (uint32_t *)c->count.p);
+    c->launches += 1;
+    MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
+    Layout L{m, (uint32_t)nbuckets, 1, 0, d_bucket_vals, d_max};
+    return run_buckets<F, FC>(c, L, (const aff_t<F> *)d_table, d_out_jac, false);
+}
+
+template <class F> static int sum_partials_impl(Ctx *c, const void *d_partials, int count) {
+    if (ensure(c, c->result, sizeof(jac_t<F>) + sizeof(aff_t<F>))) return MSMB200_ECUDA;
+    aff_t<F> *d_aff = (aff_t<F> *)((char *)c->result.p + sizeof(jac_t<F>));
+    sum_partials_kernel<F><<<1, 32, 0, c->stream>>>((const jac_t<F> *)d_partials, count, d_aff);
+    MSM_CUDA(c, cudaMemcpyAsync(c->h_result, d_aff, sizeof(aff_t<F>), cudaMemcpyDeviceToHost, c->stream));
+    MSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MSMB200_OK;
+}
+
+template <class F> static int table_build_impl(Ctx *c, int which) {
+    if (!c->have_points) return ctx_fail(c, MSMB200_ESTATE, "fixed points not set");
+    const msmb200_config &cfg = c->cfg;
+    int h = which == 0 ? cfg.h : cfg.h_bgmw, e = which == 0 ? cfg.e : cfg.e_bgmw, nmult = which == 0 ? 3 : 1;
+    size_t entries = c->n * (size_t)h * nmult;
+    void **slot = which == 0 ? &c->d_table_ches : &c->d_table_bgmw;
+    if (!*slot) MSM_CUDA(c, cudaMalloc(slot, entries * sizeof(aff_t<F>)));
+    table_build_kernel<F><<<blocks_for(c->n, 128), 128, 0, c->stream>>>((const aff_t<F> *)c->d_points, c->n, h, e, nmult, (aff_t<F> *)*slot);
+    MSM_CUDA(c, cudaGetLastError());
+    MSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    (which == 0 ? c->have_ches : c->have_bgmw) = true;
+    return MSMB200_OK;
+}
+
+// 2^k mod r on the host (k up to ~2^22): plain double-and-reduce on 4 x u64
+static void pow2_mod_r(uint64_t out[4], size_t k) {
+    static const uint64_t R[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
+    uint64_t v[4] = {1, 0, 0, 0};
+    for (size_t i = 0; i < k; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 4; j++) { uint64_t nc = v[j] >> 63; v[j] = (v[j] << 1) | carry; carry = nc; }
+        bool ge = carry != 0;
+        if (!ge) { ge = true; for (int j = 3; j >= 0; j--) { if (v[j] != R[j]) { ge = v[j] > R[j]; break; } } }
+        if (ge) { unsigned __int128 b = 0; for (int j = 0; j < 4; j++) { unsigned __int128 t = (unsigned __int128)v[j] - R[j] - (uint64_t)b; v[j] = (uint64_t)t; b = (t >> 64) & 1; } }
+    }
+    memcpy(out, v, 32);
+}
+
+template <class F> static const uint32_t *generator_words();
+template <class F> static int generate_fix_points_impl(Ctx *c, size_t first) {
+    const uint32_t chunk = 48;  // doublings per thread (multiple of 3)
+    size_t nthreads = (c->n + chunk - 1) / chunk;
+    // seeds: 2^(first + t*chunk) mod r as scalars, multiplied by G on the device
+    std::vector<uint64_t> sc(nthreads * 4);
+    {
+        // incremental: s_{t+1} = s_t * 2^chunk
+        uint64_t cur[4];
+        pow2_mod_r(cur, first);
+        static const uint64_t R[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
+        for (size_t t = 0; t < nthreads; t++) {
+            memcpy(&sc[4 * t], cur, 32);
+            for (uint32_t k = 0; k < chunk; k++) {
+                uint64_t carry = 0;
+                for (int j = 0; j < 4; j++) { uint64_t nc = cur[j] >> 63; cur[j] = (cur[j] << 1) | carry; carry = nc; }
+                bool ge = carry != 0;
+                if (!ge) { ge = true; for (int j = 3; j >= 0; j--) { if (cur[j] != R[j]) { ge = cur[j] > R[j]; break; } } }
+                if (ge) { unsigned __int128 b = 0; for (int j = 0; j < 4; j++) { unsigned __int128 x = (unsigned __int128)cur[j] - R[j] - (uint64_t)b; cur[j] = (uint64_t)x; b = (x >> 64) & 1; } }
+            }
+        }
+    }
+    void *d_sc = nullptr, *d_gen = nullptr, *d_seeds = nullptr;
+    MSM_CUDA(c, cudaMalloc(&d_sc, nthreads * 32));
+    MSM_CUDA(c, cudaMalloc(&d_gen, sizeof(aff_t<F>)));
+    MSM_CUDA(c, cudaMalloc(&d_seeds, nthreads * sizeof(jac_t<F>)));
+    MSM_CUDA(c, cudaMemcpyAsync(d_sc, sc.data(), nthreads * 32, cudaMemcpyHostToDevice, c->stream));
+    MSM_CUDA(c, cudaMemcpyAsync(d_gen, generator_words<F>(), sizeof(aff_t<F>), cudaMemcpyHostToDevice, c->stream));
+    scalar_mul_kernel<F><<<blocks_for(nthreads, 128), 128, 0, c->stream>>>((const aff_t<F> *)d_gen, 0, (const uint32_t *)d_sc, nthreads,
+                                                                           (jac_t<F> *)d_seeds);
+    fix_points_kernel<F><<<blocks_for(nthreads, 128), 128, 0, c->stream>>>((const jac_t<F> *)d_seeds, nthreads, chunk, c->n,
+                                                                           (aff_t<F> *)c->d_points);
+    MSM_CUDA(c, cudaGetLastError());
+    MSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_sc); cudaFree(d_gen); cudaFree(d_seeds);
+    c->have_points = true;
+    return MSMB200_OK;
+}
+
+template <class F> static int digits_impl(Ctx *c, int kind, const void *d_scalars, size_t n, uint32_t *d_keys, uint32_t *d_vals) {
+    cudaStream_t st = c->stream;
+    const msmb200_config &cfg = c->cfg;
+    size_t nb = kind == 0 ? c->bucket_set.size() : kind == 1 ? ((size_t)1 << (cfg.e_bgmw - 1)) + 1 : (size_t)c->pip_tiles * (((size_t)1 << (c->pip_window - 1)) + 1);
+    if (ensure(c, c->count, nb * 4)) return MSMB200_ECUDA;
+    MSM_CUDA(c, cudaMemsetAsync(c->count.p, 0, nb * 4, st));
+    if (kind == 0)
+        digits_ches_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab, d_keys, d_vals, (uint32_t *)c->count.p);
+    else if (kind == 1)
+        digits_bgmw_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h_bgmw, cfg.e_bgmw, bgmw_trick(cfg) ? 1 : 0, d_keys, d_vals, (uint32_t *)c->count.p);
+    else
+        digits_booth_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, 255, c->pip_window, c->pip_tiles, d_keys, d_vals, (uint32_t *)c->count.p);
+    MSM_CUDA(c, cudaGetLastError());
+    MSM_CUDA(c, cudaStreamSynchronize(st));
+    return MSMB200_OK;
+}
+
+template <class F, class FC> static int point_op_impl(int op, const void *a, const void *b, const unsigned char *flags, void *out, size_t n) {
+    if (op == 2 || op == 3) point_op_xyzz_kernel<F><<<blocks_for(n, 128), 128>>>(op, a, b, flags, out, n);
+    else point_op_misc_kernel<FC><<<blocks_for(n, 128), 128>>>(op, a, b, out, n);
+    return cudaGetLastError() == cudaSuccess ? 0 : MSMB200_ECUDA;
+}
+
+}  // namespace msmb200

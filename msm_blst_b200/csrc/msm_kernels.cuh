@@ -1,0 +1,667 @@
+// CUDA kernels of the bucket-method MSM pipeline (sm_100a), shared by all four methods of the reference:
+//
+//   scalars --digits_*--> (bucket key, table index | sign) pairs + per-bucket histogram      [subsystem 2]
+//           --scan / scatter / itemize / order--> per-bucket contiguous segments, work items sorted by length
+//           --accumulate--> one XYZZ partial per work item (gathers 96 B / 192 B affine table entries)  [3]
+//           --combine / reduce_chunks / sum_groups--> one XYZZ sum per window                           [4]
+//           --finalize--> Horner over windows, Jacobian partial or canonical affine result               [5]
+//
+// Reference functions replaced are cited at each kernel. The field/curve math is in fp.cuh/fp2.cuh/ec.cuh.
+#pragma once
+#include <cstdint>
+#include "ec.cuh"
+
+namespace msmb200 {
+
+constexpr uint32_t KEY_SKIP = 0xffffffffu;
+constexpr uint32_t DTAB_IDX_MASK = (1u << 22) - 1;
+
+// ------------------------------------------------------------------------------------------------
+// 256-bit scalar helpers (8 x u32 little-endian) — uint256_t of src_from_aztec replaced by plain limbs
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t scalar_bits(const uint32_t s[8], int off, int nbits) {
+    // bits [off, off+nbits), nbits <= 25, zero beyond bit 255
+    int w = off >> 5, sh = off & 31;
+    uint64_t lo = w < 8 ? s[w] : 0u;
+    uint64_t hi = (w + 1) < 8 ? s[w + 1] : 0u;
+    uint64_t v = (lo | (hi << 32)) >> sh;
+    return (uint32_t)v & ((1u << nbits) - 1u);
+}
+__device__ __forceinline__ void load_scalar(uint32_t s[8], const uint32_t *scalars, size_t i) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(scalars + 8 * i);
+    uint4 a = p[0], b = p[1];
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
+    s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// [2] digit decomposition
+// ------------------------------------------------------------------------------------------------
+
+// CHES "MB radix-q" digits. Replaces trans_uint256_t_to_MB_radixq_expr (auxiliaryfunc.h:92-118) and the
+// per-digit bookkeeping of pippenger_variant_q_over_5_CHES (main_p1.cpp:208-228): one thread per scalar,
+// h table lookups with the alpha carry; emits the bucket INDEX (BUCKET_VALUE_TO_ITS_INDEX already folded
+// into the packed table) and table entry 3(i*h+j)+m-1 with the sign in bit 31; entries whose bucket value
+// is 0 are skipped like `if(booth_idx)` in src/multi_scalar.c:445,:457.
+static __global__ void digits_ches_kernel(const uint32_t *__restrict__ scalars, size_t n, int h, int e,
+                                   const uint32_t *__restrict__ dtab, uint32_t *__restrict__ keys,
+                                   uint32_t *__restrict__ vals, uint32_t *__restrict__ count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    load_scalar(s, scalars, i);
+    uint32_t carry = 0;
+    for (int j = 0; j < h; j++) {
+        uint32_t d = scalar_bits(s, e * j, e) + carry;
+        uint32_t ent = dtab[d];
+        uint32_t idx = ent & DTAB_IDX_MASK;
+        uint32_t m1 = (ent >> 22) & 3u;
+        uint32_t alpha = (ent >> 24) & 1u;
+        carry = alpha;
+        size_t slot = i * h + j;
+        uint32_t key = KEY_SKIP;
+        if (idx != 0) {
+            key = idx;
+            atomicAdd(&count[idx], 1u);
+        }
+        keys[slot] = key;
+        vals[slot] = (uint32_t)(3 * slot + m1) | (alpha << 31);
+    }
+}
+
+// Integral-scalar-conversion front end, step (a): standard q-ary digits into one flat int array
+// (trans_uint256_t_to_standard_q_ary_expr, auxiliaryfunc.h:83-90; main_p1.cpp:259-266).
+static __global__ void digits_std_kernel(const uint32_t *__restrict__ scalars, size_t n, int h, int e, int *__restrict__ flat) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    load_scalar(s, scalars, i);
+    for (int j = 0; j < h; j++) flat[i * h + j] = (int)scalar_bits(s, e * j, e);
+}
+// step (b): in-place conversion of the flat digit array, replaces blst_p1_construct_nh_scalars_nh_points
+// (src/multi_scalar.c:748-775): slot k becomes the bucket VALUE b, booth_signs[k] = alpha, the point
+// "pointer" becomes table index 3k+m-1, and alpha carries into slot k+1. The top digit of a scalar never
+// carries (bucket-set step 4), so scalars are independent and one thread walks the h slots of one scalar.
+static __global__ void construct_nh_kernel(int *__restrict__ flat, unsigned char *__restrict__ signs,
+                                    uint32_t *__restrict__ pidx, size_t n, int h,
+                                    const uint32_t *__restrict__ dtab, const int *__restrict__ bucket_vals) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int carry = 0;
+    for (int j = 0; j < h; j++) {
+        size_t k = i * h + j;
+        uint32_t ent = dtab[flat[k] + carry];
+        uint32_t idx = ent & DTAB_IDX_MASK;
+        carry = (ent >> 24) & 1u;
+        flat[k] = bucket_vals[idx];
+        signs[k] = (unsigned char)carry;
+        pidx[k] = (uint32_t)(3 * k + ((ent >> 22) & 3u));
+    }
+}
+// Front half of blst_p1_tile_pippenger_d_CHES (src/multi_scalar.c:437-461): booth_idx =
+// bucket_value_to_its_index[scalars[k]], skip when 0. Also serves the literal blst-named shim.
+static __global__ void tile_lookup_kernel(const int *__restrict__ bvals, const unsigned char *__restrict__ signs,
+                                   const uint32_t *__restrict__ pidx, size_t m, const int *__restrict__ v2i,
+                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    int idx = v2i ? v2i[bvals[k]] : bvals[k];
+    uint32_t key = KEY_SKIP;
+    if (idx != 0) {
+        key = (uint32_t)idx;
+        atomicAdd(&count[idx], 1u);
+    }
+    keys[k] = key;
+    vals[k] = pidx[k] | ((uint32_t)(signs[k] != 0) << 31);
+}
+
+// BGMW95 signed radix-q' digits. Replaces trans_uint256_t_to_qhalf_expr (auxiliaryfunc.h:130-145) and the
+// front end of pippenger_variant_BGMW95 (main_p1.cpp:311-375) including the r - a switch for the
+// configurations with e'*h' == 255 (`trick`). r = group order (auxiliaryfunc.h:5-7).
+static __global__ void digits_bgmw_kernel(const uint32_t *__restrict__ scalars, size_t n, int h, int e, int trick,
+                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    load_scalar(s, scalars, i);
+    uint32_t flip = 0;
+    if (trick) {
+        // data[3] > 2^62  (64-bit top limb = s[7]:s[6])
+        bool cond = (s[7] > 0x40000000u) || (s[7] == 0x40000000u && s[6] != 0u);
+        if (cond) {
+            const uint32_t r[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+            uint32_t borrow = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                uint64_t t = (uint64_t)r[k] - s[k] - borrow;
+                s[k] = (uint32_t)t;
+                borrow = (uint32_t)(t >> 32) & 1u;
+            }
+            flip = 1;
+        }
+    }
+    const int q = 1 << e, qhalf = q >> 1;
+    int carry = 0;
+    for (int j = 0; j < h; j++) {
+        int d = (int)scalar_bits(s, e * j, e) + carry;
+        carry = 0;
+        if (j < h - 1 && d > qhalf) { d -= q; carry = 1; }
+        uint32_t sign = d < 0 ? 1u : 0u;
+        int mag = d < 0 ? -d : d;
+        if (mag > qhalf) mag = qhalf;  // unreachable for scalars < r except with prob 2^-62; clamp
+        size_t slot = i * h + j;
+        uint32_t key = KEY_SKIP;
+        if (mag != 0) {
+            key = (uint32_t)mag;
+            atomicAdd(&count[mag], 1u);
+        }
+        keys[slot] = key;
+        vals[slot] = (uint32_t)slot | ((sign ^ flip) << 31);
+    }
+}
+
+// blst Pippenger signed windows. Replaces get_wval_limb + booth_encode (src/ec_mult.h:23-56) as driven by
+// POINTonE1s_mult_pippenger / s_tile_pippenger (src/multi_scalar.c:549-576,:383-419): tile t covers bits
+// [t*w, t*w + wb) plus the bit below it; the top tile has wb = nbits % w (possibly 0) and is unsigned.
+// key = t * (2^(w-1) + 1) + |digit|; all tiles are emitted at once (ntiles entries per scalar).
+static __global__ void digits_booth_kernel(const uint32_t *__restrict__ scalars, size_t n, int nbits, int w, int ntiles,
+                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    load_scalar(s, scalars, i);
+    const uint32_t nbw = (1u << (w - 1)) + 1u;
+    for (int t = 0; t < ntiles; t++) {
+        int bit0 = t * w;
+        int wb = (t == ntiles - 1) ? (nbits - bit0) : w;  // bits in this tile
+        int cbits = (t == ntiles - 1) ? wb + 1 : w;
+        uint32_t wval;
+        if (bit0 == 0) wval = (scalar_bits(s, 0, wb) << 1);
+        else wval = scalar_bits(s, bit0 - 1, wb + 1);
+        uint32_t sign = (wval >> cbits) & 1u;
+        int d = (int)((wval + 1u) >> 1) - (sign ? (1 << cbits) : 0);
+        int mag = d < 0 ? -d : d;
+        size_t slot = i * ntiles + t;
+        uint32_t key = KEY_SKIP;
+        if (mag != 0) {
+            key = (uint32_t)t * nbw + (uint32_t)mag;
+            atomicAdd(&count[key], 1u);
+        }
+        keys[slot] = key;
+        vals[slot] = (uint32_t)i | (sign << 31);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sort by bucket: histogram (fused above) -> exclusive scan -> scatter; work items; order by length
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;  // per thread
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+// packs (count, nitems) into one u64 so one scan yields segment starts and item starts
+static __global__ void prep_counts_kernel(const uint32_t *__restrict__ count, uint64_t *__restrict__ packed, size_t nb, uint32_t item_len) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t c = count[b];
+    uint32_t items = (c + item_len - 1) / item_len;
+    packed[b] = (uint64_t)c | ((uint64_t)items << 32);
+}
+__device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t *total) {
+    __shared__ uint64_t warp_sums[SCAN_THREADS / 32];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+            uint64_t y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    uint64_t base = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[SCAN_THREADS / 32 - 1];
+    __syncthreads();
+    return base + x - v;
+}
+static __global__ void scan_tiles_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t *__restrict__ tile_sums, size_t n) {
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    uint64_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? in[base + k] : 0; sum += v[k]; }
+    uint64_t total;
+    uint64_t ex = block_exclusive_scan_u64(sum, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// single block: exclusive scan of the tile sums in place; grand total to tile_sums[ntiles]
+static __global__ void scan_sums_kernel(uint64_t *tile_sums, size_t ntiles) {
+    uint64_t carry = 0;
+    for (size_t base = 0; base < ntiles; base += SCAN_THREADS) {
+        size_t i = base + threadIdx.x;
+        uint64_t v = i < ntiles ? tile_sums[i] : 0;
+        uint64_t total;
+        uint64_t ex = block_exclusive_scan_u64(v, &total);
+        if (i < ntiles) tile_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) tile_sums[ntiles] = carry;
+}
+// adds tile offsets and splits the packed scan into seg_start / item_start; also clears the cursors
+static __global__ void scan_finish_kernel(const uint64_t *__restrict__ scanned, const uint64_t *__restrict__ tile_sums,
+                                   uint32_t *__restrict__ seg_start, uint32_t *__restrict__ item_start,
+                                   uint32_t *__restrict__ cursor, size_t nb) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint64_t v = scanned[b] + tile_sums[b / SCAN_TILE];
+    seg_start[b] = (uint32_t)v;
+    item_start[b] = (uint32_t)(v >> 32);
+    cursor[b] = 0;
+}
+static __global__ void scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, size_t m,
+                               const uint32_t *__restrict__ seg_start, uint32_t *__restrict__ cursor,
+                               uint32_t *__restrict__ sorted) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    uint32_t key = keys[k];
+    if (key == KEY_SKIP) return;
+    uint32_t pos = seg_start[key] + atomicAdd(&cursor[key], 1u);
+    sorted[pos] = vals[k];
+}
+// One work item = up to item_len consecutive entries of one bucket (a bucket with a huge count is split so
+// that no thread serialises more than item_len additions). Also builds the histogram of item lengths.
+static __global__ void itemize_kernel(const uint32_t *__restrict__ count, const uint32_t *__restrict__ seg_start,
+                               const uint32_t *__restrict__ item_start, size_t nb, uint32_t item_len,
+                               uint32_t *__restrict__ item_begin, uint32_t *__restrict__ item_cnt,
+                               uint32_t *__restrict__ len_hist) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t c = count[b];
+    if (c == 0) return;
+    uint32_t s = seg_start[b], it = item_start[b];
+    for (uint32_t off = 0; off < c; off += item_len, it++) {
+        uint32_t len = min(item_len, c - off);
+        item_begin[it] = s + off;
+        item_cnt[it] = len;
+        // warp-aggregated histogram update
+        uint32_t peers = __match_any_sync(__activemask(), len);
+        if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&len_hist[len], (uint32_t)__popc(peers));
+    }
+}
+// single block: len_start[len] = number of items strictly longer than len (descending order => longest first)
+static __global__ void len_scan_kernel(const uint32_t *__restrict__ len_hist, uint32_t *__restrict__ len_start,
+                                uint32_t *__restrict__ len_cursor, uint32_t item_len) {
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int l = (int)item_len; l >= 0; l--) { len_start[l] = acc; acc += len_hist[l]; len_cursor[l] = 0; }
+    }
+}
+static __global__ void order_items_kernel(const uint32_t *__restrict__ item_cnt, const uint64_t *__restrict__ totals,
+                                   const uint32_t *__restrict__ len_start, uint32_t *__restrict__ len_cursor,
+                                   uint32_t *__restrict__ order) {
+    size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= (size_t)(*totals >> 32)) return;
+    uint32_t len = item_cnt[it];
+    uint32_t peers = __match_any_sync(__activemask(), len);
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&len_cursor[len], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    order[len_start[len] + base + rank] = (uint32_t)it;
+}
+
+// ------------------------------------------------------------------------------------------------
+// [3] bucket accumulation (XYZZ path): replaces the hot loop of POINTonE1_tile_pippenger_d_CHES /
+// _BGMW95 / s_tile_pippenger (src/multi_scalar.c:437-461,:522-544,:397-417 -> xyzz_dadd_affine).
+// One thread per work item; items sorted longest-first so the warps of a block have equal trip counts.
+// Each table entry (96 B / 192 B, 32-byte aligned) is fetched with 16-byte vector loads.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void load_affine(aff_t<F> &p, const aff_t<F> *__restrict__ table, uint32_t idx) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(table + idx);
+    uint4 *dst = reinterpret_cast<uint4 *>(&p);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(aff_t<F>) / 16); k++) dst[k] = __ldg(src + k);
+}
+template <class F>
+static __global__ void __launch_bounds__(128) accumulate_kernel(const aff_t<F> *__restrict__ table, const uint32_t *__restrict__ sorted,
+                                                         const uint32_t *__restrict__ item_begin, const uint32_t *__restrict__ item_cnt,
+                                                         const uint32_t *__restrict__ order, const uint64_t *__restrict__ totals,
+                                                         xyzz_t<F> *__restrict__ partial) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)(*totals >> 32)) return;  // number of work items (high half of the packed scan total)
+    uint32_t it = order[t];
+    uint32_t beg = item_begin[it], cnt = item_cnt[it];
+    xyzz_t<F> acc;
+    xyzz_set_inf(acc);
+#pragma unroll 1
+    for (uint32_t k = 0; k < cnt; k++) {
+        uint32_t v = sorted[beg + k];
+        aff_t<F> p;
+        load_affine(p, table, v & 0x7fffffffu);
+        xyzz_add_affine(acc, p, (v >> 31) != 0);
+    }
+    partial[it] = acc;
+}
+// buckets that were split into several items: fold the partials into the first one
+template <class F>
+static __global__ void __launch_bounds__(128) combine_items_kernel(const uint32_t *__restrict__ count, const uint32_t *__restrict__ item_start,
+                                                            size_t nb, uint32_t item_len, xyzz_t<F> *__restrict__ partial) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t c = count[b];
+    if (c <= item_len) return;
+    uint32_t items = (c + item_len - 1) / item_len, it = item_start[b];
+    xyzz_t<F> acc = partial[it];
+    for (uint32_t k = 1; k < items; k++) {
+        xyzz_t<F> q = partial[it + k];
+        xyzz_add(acc, q);
+    }
+    partial[it] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// [4] bucket reduction. Replaces POINTonE1_integrate_buckets_accumulation_d_CHES (src/multi_scalar.c:301-321)
+// and POINTonE1_integrate_buckets (:281-297) with the chunked form of SURVEY App. B.6: window `w` has nbw
+// buckets (local index 0 unused) with ascending values val(l) (bucket_vals[l] for CHES, l itself when
+// bucket_vals == nullptr); chunk c covers locals [1 + c*chunk, 1 + (c+1)*chunk) and produces
+//     sum_{l in chunk} val(l) * S_l = W + base * T,   base = val(first-1),
+// W by the reference's running sums over gaps (<= d_max, kept in tmp_d[]), base*T by double-and-add.
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_GAP = 8;
+
+// out-of-line copies for the cold paths (keeps the instruction footprint of the hot loops small)
+template <class F> __device__ __noinline__ void xyzz_add_cold(xyzz_t<F> &acc, const xyzz_t<F> &q) { xyzz_add(acc, q); }
+
+template <class F>
+__device__ __forceinline__ void load_xyzz(xyzz_t<F> &p, const xyzz_t<F> *src_) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(src_);
+    uint4 *dst = reinterpret_cast<uint4 *>(&p);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(xyzz_t<F>) / 16); k++) dst[k] = src[k];
+}
+template <class F, bool DENSE>
+static __global__ void __launch_bounds__(128) reduce_chunks_kernel(const xyzz_t<F> *__restrict__ partial, const uint32_t *__restrict__ count,
+                                                            const uint32_t *__restrict__ item_start, const int *__restrict__ bucket_vals,
+                                                            uint32_t nbw, uint32_t nwindows, uint32_t chunk, uint32_t chunks_per_window,
+                                                            int d_max, xyzz_t<F> *__restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nwindows * chunks_per_window) return;
+    uint32_t w = t / chunks_per_window, c = t % chunks_per_window;
+    uint32_t lo = 1 + c * chunk, hi = min(nbw, lo + chunk);  // locals [lo, hi)
+    xyzz_t<F> tmp, W;
+    xyzz_set_inf(tmp);
+    xyzz_set_inf(W);
+    xyzz_t<F> tmp_d[DENSE ? 1 : MAX_GAP + 1];
+    if (!DENSE) {
+        for (int g = 0; g <= d_max; g++) xyzz_set_inf(tmp_d[g]);
+    }
+    int base = 0;
+    if (lo < hi) {
+        base = DENSE ? (int)(lo - 1) : bucket_vals[lo - 1];
+#pragma unroll 1
+        for (uint32_t l = hi; l-- > lo;) {
+            size_t b = (size_t)w * nbw + l;
+            if (count[b] != 0) {
+                xyzz_t<F> s;
+                load_xyzz(s, partial + item_start[b]);
+                xyzz_add(tmp, s);
+            }
+            if (DENSE) {
+                xyzz_add_cold(W, tmp);
+            } else {
+                int gap = bucket_vals[l] - bucket_vals[l - 1];
+                xyzz_add_cold(tmp_d[gap], tmp);
+            }
+        }
+        if (!DENSE) {
+            xyzz_t<F> acc;
+            xyzz_set_inf(acc);
+#pragma unroll 1
+            for (int g = d_max; g > 0; g--) {
+                xyzz_add_cold(acc, tmp_d[g]);
+                xyzz_add_cold(W, acc);
+            }
+        }
+        // W += base * tmp  (MSB-first double-and-add; base < 2^22)
+        if (base != 0 && !xyzz_is_inf(tmp)) {
+            xyzz_t<F> r;
+            xyzz_set_inf(r);
+            int top = 31 - __clz(base);
+#pragma unroll 1
+            for (int bit = top; bit >= 0; bit--) {
+                if (!xyzz_is_inf(r)) xyzz_double(r, r);
+                if ((base >> bit) & 1) xyzz_add_cold(r, tmp);
+            }
+            xyzz_add_cold(W, r);
+        }
+    }
+    out[t] = W;
+}
+// out[w*groups + g] = sum of in[w*per_window + g*r .. +r)
+template <class F>
+static __global__ void __launch_bounds__(128) sum_groups_kernel(const xyzz_t<F> *__restrict__ in, uint32_t per_window, uint32_t nwindows,
+                                                         uint32_t r, uint32_t groups, xyzz_t<F> *__restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nwindows * groups) return;
+    uint32_t w = t / groups, g = t % groups;
+    uint32_t lo = g * r, hi = min(per_window, lo + r);
+    xyzz_t<F> acc;
+    xyzz_set_inf(acc);
+    for (uint32_t k = lo; k < hi; k++) {
+        xyzz_t<F> q;
+        load_xyzz(q, in + (size_t)w * per_window + k);
+        xyzz_add(acc, q);
+    }
+    out[t] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// [5] window combination + output. Replaces the outer loop of POINTonE1s_mult_pippenger
+// (src/multi_scalar.c:565-575: ret = (ret + tile) * 2^window, top tile first), xyzz_to_Jacobian
+// (src/ec_ops.h:771-777) and, when want_affine, blst_p1_to_affine (src/e1.c:80-92). One thread.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+static __global__ void finalize_kernel(const xyzz_t<F> *__restrict__ window_sums, uint32_t nwindows, uint32_t wbits,
+                                jac_t<F> *__restrict__ out_jac, aff_t<F> *__restrict__ out_aff) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    xyzz_t<F> acc;
+    xyzz_set_inf(acc);
+    for (int w = (int)nwindows - 1; w >= 0; w--) {
+        xyzz_t<F> s = window_sums[w];
+        xyzz_add_cold(acc, s);
+        if (w > 0)
+            for (uint32_t k = 0; k < wbits; k++)
+                if (!xyzz_is_inf(acc)) xyzz_double(acc, acc);
+    }
+    jac_t<F> j;
+    if (xyzz_is_inf(acc)) jac_set_inf(j);
+    else xyzz_to_jac(j, acc);
+    if (out_jac) *out_jac = j;
+    if (out_aff) {
+        aff_t<F> a;
+        jac_to_affine(a, j);
+        *out_aff = a;
+    }
+}
+// sum of Jacobian partials (one per GPU) + to_affine: the G-1 dadds after the NCCL all-gather
+template <class F>
+static __global__ void sum_partials_kernel(const jac_t<F> *__restrict__ partials, int count, aff_t<F> *__restrict__ out_aff) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    jac_t<F> acc;
+    jac_set_inf(acc);
+    for (int k = 0; k < count; k++) {
+        jac_t<F> p = partials[k];
+        jac_add(acc, acc, p);
+    }
+    aff_t<F> a;
+    jac_to_affine(a, acc);
+    *out_aff = a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// precomputation tables and fixed points
+// ------------------------------------------------------------------------------------------------
+// Normalise up to 3 Jacobian points with one inversion (Montgomery's trick); Z == 0 -> (0,0).
+template <class F>
+__device__ __forceinline__ void to_affine3(aff_t<F> *o0, const jac_t<F> &p0, aff_t<F> *o1, const jac_t<F> &p1,
+                                           aff_t<F> *o2, const jac_t<F> &p2) {
+    F one;
+    f_set_one(one);
+    bool z0 = f_is_zero(p0.z), z1 = f_is_zero(p1.z), z2 = f_is_zero(p2.z);
+    F a = z0 ? one : p0.z, b = z1 ? one : p1.z, c = z2 ? one : p2.z;
+    F ab, abc, inv, t, ia, ib, ic;
+    f_mul(ab, a, b);
+    f_mul(abc, ab, c);
+    f_inv(inv, abc);
+    f_mul(ic, inv, ab);    // 1/c
+    f_mul(t, inv, c);      // 1/(ab)
+    f_mul(ib, t, a);       // 1/b
+    f_mul(ia, t, b);       // 1/a
+    F zi2;
+    f_sqr(zi2, ia); f_mul(o0->x, p0.x, zi2); f_mul(zi2, zi2, ia); f_mul(o0->y, p0.y, zi2);
+    f_sqr(zi2, ib); f_mul(o1->x, p1.x, zi2); f_mul(zi2, zi2, ib); f_mul(o1->y, p1.y, zi2);
+    f_sqr(zi2, ic); f_mul(o2->x, p2.x, zi2); f_mul(zi2, zi2, ic); f_mul(o2->y, p2.y, zi2);
+    if (z0) { f_set_zero(o0->x); f_set_zero(o0->y); }
+    if (z1) { f_set_zero(o1->x); f_set_zero(o1->y); }
+    if (z2) { f_set_zero(o2->x); f_set_zero(o2->y); }
+}
+template <class F> __device__ __forceinline__ void jac_from_affine(jac_t<F> &j, const aff_t<F> &a) {
+    j.x = a.x; j.y = a.y;
+    if (aff_is_inf(a)) f_set_zero(j.z); else f_set_one(j.z);
+}
+// Table build. Replaces the loops of init_pippenger_CHES_q_over_5 (main_p1.cpp:156-172, nmult = 3:
+// T[3(i*h+j)+m-1] = m q^j P_i) and init_pippenger_BGMW95 (main_p1.cpp:108-115, nmult = 1: T[i*h+j] = q^j P_i),
+// i.e. h * (e doublings + 2 additions) per point instead of single_scalar_multiplication + one inversion per
+// entry; one thread per fixed point, one shared inversion per (i, j).
+template <class F>
+static __global__ void __launch_bounds__(128) table_build_kernel(const aff_t<F> *__restrict__ points, size_t n, int h, int e, int nmult,
+                                                          aff_t<F> *__restrict__ table) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    aff_t<F> q = points[i];
+#pragma unroll 1
+    for (int j = 0; j < h; j++) {
+        size_t base = (i * h + j) * nmult;
+        table[base] = q;
+        jac_t<F> jq, d, t3;
+        jac_from_affine(jq, q);
+        jac_double(d, jq);                        // 2Q (Z stays 0 for infinity)
+        if (nmult == 3) jac_add(t3, d, jq);       // 3Q
+        else jac_set_inf(t3);
+        jac_t<F> nx = d;                          // q * Q = 2^(e-1) * 2Q
+#pragma unroll 1
+        for (int k = 1; k < e; k++) jac_double(nx, nx);
+        aff_t<F> a2, a3, an;
+        to_affine3(&a2, d, &a3, t3, &an, nx);
+        if (nmult == 3) { table[base + 1] = a2; table[base + 2] = a3; }
+        q = an;
+    }
+}
+// out[i] = k_i * G_i for 256-bit scalars (MSB-first double-and-add), Jacobian; used to seed the fixed-point
+// chains and for test vectors.
+template <class F>
+static __global__ void __launch_bounds__(128) scalar_mul_kernel(const aff_t<F> *__restrict__ bases, int base_stride,
+                                                         const uint32_t *__restrict__ scalars, size_t n, jac_t<F> *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    load_scalar(s, scalars, i);
+    jac_t<F> b, acc;
+    jac_from_affine(b, bases[i * base_stride]);
+    jac_set_inf(acc);
+#pragma unroll 1
+    for (int bit = 255; bit >= 0; bit--) {
+        jac_double(acc, acc);
+        if ((s[bit >> 5] >> (bit & 31)) & 1) jac_add(acc, acc, b);
+    }
+    out[i] = acc;
+}
+// init_fix_point_list (main_p1.cpp:52-66) in parallel: thread t starts from seeds[t] = 2^(first + t*chunk) G and
+// emits the next `chunk` doublings, each normalised (3 at a time) to canonical affine.
+template <class F>
+static __global__ void __launch_bounds__(128) fix_points_kernel(const jac_t<F> *__restrict__ seeds, size_t nthreads, uint32_t chunk, size_t n,
+                                                         aff_t<F> *__restrict__ points) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    jac_t<F> cur = seeds[t];
+    size_t i0 = t * chunk;
+#pragma unroll 1
+    for (uint32_t k = 0; k < chunk; k += 3) {
+        jac_t<F> p0, p1, p2;
+        jac_double(p0, cur);
+        jac_double(p1, p0);
+        jac_double(p2, p1);
+        cur = p2;
+        aff_t<F> a0, a1, a2;
+        to_affine3(&a0, p0, &a1, p1, &a2, p2);
+        if (k + 0 < chunk && i0 + k + 0 < n) points[i0 + k + 0] = a0;
+        if (k + 1 < chunk && i0 + k + 1 < n) points[i0 + k + 1] = a1;
+        if (k + 2 < chunk && i0 + k + 2 < n) points[i0 + k + 2] = a2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched building blocks for parity tests (msmb200_test_field_op / msmb200_test_point_op)
+// ------------------------------------------------------------------------------------------------
+template <class F>
+static __global__ void field_op_kernel(int op, const F *__restrict__ a, const F *__restrict__ b, F *__restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = a[i], y, r;
+    if (b) y = b[i]; else f_set_zero(y);
+    switch (op) {
+    case 0: f_mul(r, x, y); break;
+    case 1: f_sqr(r, x); break;
+    case 2: f_add(r, x, y); break;
+    case 3: f_sub(r, x, y); break;
+    case 4: f_cneg(r, x, true); break;
+    case 5: f_mul3(r, x); break;
+    case 6: f_inv(r, x); break;
+    default: f_set_zero(r);
+    }
+    out[i] = r;
+}
+// ops 2,3 (the XYZZ additions of the two hot loops) are instantiated with the hot field type, the rest cold
+template <class F>
+static __global__ void __launch_bounds__(128) point_op_xyzz_kernel(int op, const void *__restrict__ a, const void *__restrict__ b,
+                                                                   const unsigned char *__restrict__ flags, void *__restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (op == 2) {
+        xyzz_t<F> x = ((const xyzz_t<F> *)a)[i];
+        aff_t<F> y = ((const aff_t<F> *)b)[i];
+        xyzz_add_affine(x, y, flags && flags[i]);
+        ((xyzz_t<F> *)out)[i] = x;
+    } else {
+        xyzz_t<F> x = ((const xyzz_t<F> *)a)[i], y = ((const xyzz_t<F> *)b)[i];
+        xyzz_add(x, y);
+        ((xyzz_t<F> *)out)[i] = x;
+    }
+}
+template <class F>
+static __global__ void __launch_bounds__(128) point_op_misc_kernel(int op, const void *__restrict__ a, const void *__restrict__ b,
+                                                                   void *__restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    switch (op) {
+    case 0: { jac_t<F> x = ((const jac_t<F> *)a)[i], y = ((const jac_t<F> *)b)[i], r; jac_add(r, x, y); ((jac_t<F> *)out)[i] = r; break; }
+    case 1: { jac_t<F> x = ((const jac_t<F> *)a)[i], r; jac_double(r, x); ((jac_t<F> *)out)[i] = r; break; }
+    case 4: { xyzz_t<F> x = ((const xyzz_t<F> *)a)[i]; jac_t<F> r; if (xyzz_is_inf(x)) jac_set_inf(r); else xyzz_to_jac(r, x); ((jac_t<F> *)out)[i] = r; break; }
+    case 5: { jac_t<F> x = ((const jac_t<F> *)a)[i]; aff_t<F> r; jac_to_affine(r, x); ((aff_t<F> *)out)[i] = r; break; }
+    }
+}
+
+}  // namespace msmb200
