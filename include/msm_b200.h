@@ -55,6 +55,15 @@ typedef struct {
  * makefile:15-18): "8".."21", "16_beta", "17_beta", "20_beta". */
 int msmb200_config_lookup(const char *name, msmb200_config *out);
 
+/* Host-only parameter construction (no CUDA needed), the run-time form of construct_bucket_set
+ * (auxiliaryfunc.h:257-288) and of the DIGIT_CONVERSION_HASH_TABLE fill (main_p1.cpp:140-152).
+ * msmb200_host_bucket_set returns |B| (fills out[] when cap >= |B|). msmb200_host_digit_table writes q+1
+ * triples (m, b, alpha) in the reference's digit_decomposition layout (bindings/blst.h:253). */
+long msmb200_host_bucket_set(int e, int a, int *out, long cap);
+int msmb200_host_digit_table(int e, int a, int *out_triples);
+/* pippenger_window_size (src/multi_scalar.c:268-275) */
+size_t msmb200_pippenger_window_size(size_t npoints);
+
 /* ---- context ------------------------------------------------------------------------------------ */
 
 /* group: 1 = G1 (main_p1.cpp), 2 = G2 (main_p2.cpp). npoints: number of fixed points owned by this

@@ -12,12 +12,14 @@ from .api import (  # noqa: F401
     affine_serialize,
     build_library,
     config_lookup,
+    host_bucket_set,
+    host_digit_table,
     lib,
     test_field_op,
     test_point_op,
 )
 
 __all__ = [
-    "LIB_PATH", "MsmB200Error", "MsmContext", "affine_serialize", "build_library", "config_lookup", "lib",
+    "LIB_PATH", "MsmB200Error", "MsmContext", "affine_serialize", "build_library", "config_lookup", "host_bucket_set", "host_digit_table", "lib",
     "test_field_op", "test_point_op",
 ]

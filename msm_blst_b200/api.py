@@ -55,6 +55,11 @@ def lib():
         L = C.CDLL(LIB_PATH)
         vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
         L.msmb200_config_lookup.argtypes = [C.c_char_p, C.POINTER(_Config)]
+        L.msmb200_host_bucket_set.argtypes = [ci, ci, vp, C.c_long]
+        L.msmb200_host_bucket_set.restype = C.c_long
+        L.msmb200_host_digit_table.argtypes = [ci, ci, vp]
+        L.msmb200_pippenger_window_size.argtypes = [sz]
+        L.msmb200_pippenger_window_size.restype = sz
         L.msmb200_ctx_create.argtypes = [C.POINTER(vp), ci, C.POINTER(_Config), sz, ci]
         L.msmb200_ctx_destroy.argtypes = [vp]
         L.msmb200_ctx_destroy.restype = None
@@ -105,6 +110,22 @@ def config_lookup(name):
     if lib().msmb200_config_lookup(str(name).encode(), C.byref(cfg)) != 0:
         raise KeyError("unknown configuration %r" % (name,))
     return cfg
+
+
+def host_bucket_set(e, a):
+    n = lib().msmb200_host_bucket_set(e, a, None, 0)
+    if n < 0:
+        raise MsmB200Error("host_bucket_set(%d, %d) failed" % (e, a))
+    out = np.empty(n, dtype=np.int32)
+    lib().msmb200_host_bucket_set(e, a, _ptr(out), n)
+    return out
+
+
+def host_digit_table(e, a):
+    out = np.empty(((1 << e) + 1, 3), dtype=np.int32)
+    if lib().msmb200_host_digit_table(e, a, _ptr(out)) != 0:
+        raise MsmB200Error("host_digit_table(%d, %d) failed" % (e, a))
+    return out
 
 
 def affine_serialize(group, aff):

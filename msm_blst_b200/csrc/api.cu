@@ -87,6 +87,27 @@ int msmb200_config_lookup(const char *name, msmb200_config *out) {
     return MSMB200_OK;
 }
 
+long msmb200_host_bucket_set(int e, int a, int *out, long cap) {
+    if (e < 4 || e > 24 || a < 0) return MSMB200_EINVAL;
+    std::vector<int> B = build_bucket_set(1 << e, a);
+    if (out && cap >= (long)B.size()) memcpy(out, B.data(), B.size() * sizeof(int));
+    return (long)B.size();
+}
+int msmb200_host_digit_table(int e, int a, int *out_triples) {
+    if (e < 4 || e > 24 || a < 0 || !out_triples) return MSMB200_EINVAL;
+    int q = 1 << e;
+    std::vector<int> B = build_bucket_set(q, a);
+    std::vector<uint32_t> T = build_digit_table(q, B);
+    for (int d = 0; d <= q; d++) {
+        if (T[d] == DT_INVALID) return MSMB200_EINVAL;
+        out_triples[3 * d + 0] = (int)((T[d] >> DT_M_SHIFT) & 3u) + 1;
+        out_triples[3 * d + 1] = B[T[d] & DT_IDX_MASK];
+        out_triples[3 * d + 2] = (int)((T[d] >> DT_A_SHIFT) & 1u);
+    }
+    return MSMB200_OK;
+}
+size_t msmb200_pippenger_window_size(size_t npoints) { return pippenger_window_size(npoints); }
+
 const char *msmb200_last_error(const msmb200_ctx *ctx) { return ctx ? ctx->c.err.c_str() : g_create_err.c_str(); }
 
 int msmb200_ctx_create(msmb200_ctx **out, int group, const msmb200_config *cfg, size_t npoints, int device) {

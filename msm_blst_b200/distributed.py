@@ -1,0 +1,42 @@
+"""Multi-GPU plumbing: one process per GPU, contiguous point shards, one all-gather of partial points.
+
+MSM is a sum over points, so rank g owns points [g*n/G, (g+1)*n/G), builds its own table shard from its own
+P_i (no communication), reduces its scalars to ONE partial Jacobian point (144 B G1 / 288 B G2) on its GPU, and
+the only exchange step is an all-gather of G partials (NCCL over NVLink on the GPU box, gloo in CPU tests),
+followed by G-1 additions and one to_affine. torch.distributed is plumbing only.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world):
+    """Contiguous shard [lo, hi) of n points for `rank`; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_config_name(n_shard):
+    """Reference configuration tuned for the shard size (legal: the output encoding is canonical)."""
+    exp = max(8, min(21, (max(1, n_shard) - 1).bit_length()))
+    return str(exp)
+
+
+def all_gather_partials(partial, world=None):
+    """partial: uint8 tensor of one Jacobian point on this rank's device -> (world, nbytes) tensor on every rank."""
+    world = world or dist.get_world_size()
+    out = torch.empty((world,) + tuple(partial.shape), dtype=partial.dtype, device=partial.device)
+    dist.all_gather_into_tensor(out, partial) if partial.is_cuda else dist.all_gather(list(out.unbind(0)), partial)
+    return out
+
+
+def msm_sharded(ctx, method, scalars_dev, partial_buf):
+    """Run this rank's shard on its GPU and combine: returns the affine result (numpy uint8) on every rank.
+
+    ctx: msm_blst_b200.MsmContext for this rank's shard; scalars_dev: torch uint8 CUDA tensor (n_shard x 32);
+    partial_buf: torch uint8 CUDA tensor of JAC_BYTES.
+    """
+    ctx.msm_partial_device(method, scalars_dev.data_ptr(), partial_buf.data_ptr())
+    torch.cuda.current_stream().synchronize() if False else None
+    gathered = all_gather_partials(partial_buf)
+    return ctx.sum_partials_device(gathered.data_ptr(), gathered.shape[0])

@@ -1,0 +1,88 @@
+"""CPU tests (-m "not gpu"): the C-ABI library loads without a GPU, exports every symbol include/msm_b200.h
+declares, its host-only parameter layer matches the oracle, and compute entry points fail loudly (no fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "msm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(msmb200_[a-zA-Z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(product_lib):
+    L = product_lib.lib()
+    names = declared_symbols()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_config_lookup_matches_oracle(product_lib, oracle_built):
+    for name in ("8", "9", "10", "11", "12", "13", "14", "15", "16", "16_beta", "17", "17_beta", "18", "19", "20",
+                 "20_beta", "21"):
+        c = product_lib.config_lookup(name)
+        oc = O.config(name)
+        for k in ("n_exp", "e", "h", "a", "d", "bsize", "e_bgmw", "h_bgmw"):
+            assert getattr(c, k) == oc[k], (name, k)
+        assert product_lib.lib().msmb200_pippenger_window_size(1 << c.n_exp) == oc["window"]
+    with pytest.raises(KeyError):
+        product_lib.config_lookup("22")
+
+
+def test_host_bucket_set_and_digit_table_match_oracle(product_lib, oracle_built):
+    for name in ("8", "10", "11", "13", "16_beta"):
+        c = O.config(name)
+        oc = O.OracleCtx(1, name, n=2)
+        B = product_lib.host_bucket_set(c["e"], c["a"])
+        assert len(B) == c["bsize"]
+        assert (B == oc.bucket_set()).all()
+        assert (product_lib.host_digit_table(c["e"], c["a"]) == oc.hash_table()).all()
+
+
+def test_host_bucket_set_sizes_all_configs(product_lib, golden):
+    for key, size in golden["kat_appc"]["bsize"].items():
+        e, a = map(int, key.split(","))
+        B = product_lib.host_bucket_set(e, a)
+        assert len(B) == size
+        assert int(np.diff(B).max()) == 6 and B[0] == 0 and B[1] == 1
+
+
+def test_no_cpu_fallback(product_lib):
+    """Without a CUDA device every compute entry point returns an error; with one, bad arguments do."""
+    import torch
+
+    L = product_lib.lib()
+    if not torch.cuda.is_available():
+        with pytest.raises(product_lib.MsmB200Error):
+            product_lib.MsmContext(1, "10")
+        a = np.zeros((4, 6), dtype=np.uint64)
+        with pytest.raises(product_lib.MsmB200Error):
+            product_lib.test_field_op(1, 0, a, a)
+    h = C.c_void_p()
+    cfg = product_lib.config_lookup("10")
+    assert L.msmb200_ctx_create(C.byref(h), 3, C.byref(cfg), 1024, 0) == -1  # bad group
+    assert L.msmb200_ctx_create(C.byref(h), 1, C.byref(cfg), 0, 0) == -1  # no points
+    assert b"bad arguments" in L.msmb200_last_error(None)
+
+
+def test_product_does_not_touch_the_oracle():
+    """The product path must not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "msm_blst_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) == "build":
+            continue
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")) or fn == "Makefile":
+                text = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert "oracle" not in text.lower().replace("test oracle", ""), os.path.join(dirpath, fn)
+    text = open(os.path.join(ROOT, "include", "msm_b200.h")).read()
+    assert "oracle" not in text.lower()

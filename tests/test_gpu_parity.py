@@ -1,0 +1,439 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (libmsm_b200.so), against the oracle, the
+golden vectors generated from the compiled reference, and SURVEY App. C known answers. Bit-exact everywhere."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M(product_lib):
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return product_lib
+
+
+def rand_fp(rng, n):
+    a = rng.integers(0, 2**64, size=(n, 6), dtype=np.uint64)
+    a[:, 5] &= np.uint64(0x0FFFFFFFFFFFFFFF)
+    return a
+
+
+def edge_fp():
+    vals = [0, 1, 2, O.P_MOD - 1, O.P_MOD - 2, (O.P_MOD - 1) // 2, 2**380, 2**381 - 1 - (2**381 - 1 - O.P_MOD + 1) if False else O.P_MOD // 3]
+    return np.array([[(v >> (64 * i)) & (2**64 - 1) for i in range(6)] for v in vals], dtype=np.uint64)
+
+
+# ---------------------------------------------------------------- field layer (a4, a5, a6, a7)
+def test_fp_ops_vs_oracle(M):
+    rng = np.random.default_rng(1)
+    a = np.concatenate([rand_fp(rng, 1 << 16), edge_fp(), edge_fp()[::-1]])
+    b = np.concatenate([rand_fp(rng, 1 << 16), edge_fp()[::-1], edge_fp()])
+    n = a.shape[0]
+    for op in range(6):
+        exp = np.empty_like(a)
+        O.oracle().oracle_fp_op(op, O.ptr(a), O.ptr(b), O.ptr(exp), n)
+        got = M.test_field_op(1, op, a, b)
+        assert (got == exp).all(), "fp op %d" % op
+    exp = np.empty_like(a[:300])
+    x = np.ascontiguousarray(a[-300:])
+    O.oracle().oracle_fp_op(6, O.ptr(x), None, O.ptr(exp), 300)
+    assert (M.test_field_op(1, 6, x) == exp).all()
+
+
+def test_fp_golden_from_reference(M, golden):
+    f = golden["field"]
+    a = np.frombuffer(bytes.fromhex(f["a"]), dtype=np.uint64).reshape(-1, 6).copy()
+    b = np.frombuffer(bytes.fromhex(f["b"]), dtype=np.uint64).reshape(-1, 6).copy()
+    for name, op in (("mul", 0), ("sqr", 1), ("add", 2), ("sub", 3), ("mul_by_3", 5), ("inverse", 6)):
+        assert M.test_field_op(1, op, a, b).tobytes().hex() == f[name], name
+    a2, b2 = a.reshape(-1, 12), b.reshape(-1, 12)
+    for name, op in (("fp2_mul", 0), ("fp2_sqr", 1), ("fp2_add", 2), ("fp2_sub", 3)):
+        assert M.test_field_op(2, op, a2, b2).tobytes().hex() == f[name], name
+
+
+def test_fp2_ops_vs_oracle(M):
+    rng = np.random.default_rng(2)
+    a = rand_fp(rng, 1 << 15).reshape(-1, 12)
+    b = rand_fp(rng, 1 << 15).reshape(-1, 12)
+    for op in range(6):
+        exp = np.empty_like(a)
+        O.oracle().oracle_fp2_op(op, O.ptr(a), O.ptr(b), O.ptr(exp), a.shape[0])
+        assert (M.test_field_op(2, op, a, b) == exp).all(), "fp2 op %d" % op
+    x = np.ascontiguousarray(a[:200])
+    exp = np.empty_like(x)
+    O.oracle().oracle_fp2_op(6, O.ptr(x), None, O.ptr(exp), 200)
+    assert (M.test_field_op(2, 6, x) == exp).all()
+
+
+# ---------------------------------------------------------------- curve layer (a8, a9, a10, a22, a23)
+@pytest.mark.parametrize("group", [1, 2])
+def test_point_ops_vs_oracle_with_special_cases(M, group):
+    ab, jb, xb = O.AFF_BYTES[group], O.JAC_BYTES[group], O.XYZZ_BYTES[group]
+    oc = O.OracleCtx(group, "10", n=64)
+    oc.init_fix_points()
+    pts = oc.points().reshape(64, ab)
+    o = O.oracle()
+    # build XYZZ accumulators: inf, P_i, P_i + P_j ...
+    n = 256
+    rng = np.random.default_rng(3)
+    acc = np.zeros((n, xb), dtype=np.uint8)
+    addend = pts[rng.integers(0, 64, size=n)].copy()
+    flags = rng.integers(0, 2, size=n).astype(np.uint8)
+    for rounds in range(4):
+        exp = np.zeros_like(acc)
+        o.oracle_point_op(group, 2, O.ptr(acc), O.ptr(addend), O.ptr(flags), O.ptr(exp), n)
+        got = M.test_point_op(group, 2, acc, addend, flags).reshape(n, xb)
+        half = xb // 2
+        assert (got[:, half:] == exp[:, half:]).all()
+        finite = exp[:, half:].any(axis=1)
+        assert (got[finite] == exp[finite]).all()
+        acc = exp
+        # next round: include same point (doubling), opposite (cancellation), infinity addend
+        addend = pts[rng.integers(0, 64, size=n)].copy()
+        flags = rng.integers(0, 2, size=n).astype(np.uint8)
+        if rounds == 0:
+            prev = addend.copy()
+        if rounds == 1:
+            addend[:32] = 0  # affine infinity
+    # force P + P and P - P through xyzz_add_affine
+    single = np.zeros((4, xb), dtype=np.uint8)
+    first = np.stack([pts[3], pts[3], pts[4], pts[4]])
+    z = np.zeros(4, dtype=np.uint8)
+    s1 = np.zeros_like(single)
+    o.oracle_point_op(group, 2, O.ptr(single), O.ptr(first), O.ptr(z), O.ptr(s1), 4)
+    fl = np.array([0, 1, 0, 1], dtype=np.uint8)
+    exp = np.zeros_like(single)
+    o.oracle_point_op(group, 2, O.ptr(s1), O.ptr(first), O.ptr(fl), O.ptr(exp), 4)
+    got = M.test_point_op(group, 2, s1, first, fl).reshape(4, xb)
+    half = xb // 2
+    assert (got[:, half:] == exp[:, half:]).all() and (got[0] == exp[0]).all() and (got[2] == exp[2]).all()
+    assert not exp[1, half:].any() and not exp[3, half:].any()
+    # xyzz + xyzz (general, doubling, cancellation via negated copy is covered by accumulate tests)
+    lhs = acc
+    rhs = np.roll(acc, 1, axis=0).copy()
+    rhs[:16] = lhs[:16]  # doubling
+    exp = np.zeros_like(lhs)
+    o.oracle_point_op(group, 3, O.ptr(lhs), O.ptr(rhs), None, O.ptr(exp), n)
+    got = M.test_point_op(group, 3, lhs, rhs).reshape(n, xb)
+    finite = exp[:, half:].any(axis=1)
+    assert (got[:, half:] == exp[:, half:]).all() and (got[finite] == exp[finite]).all()
+    # xyzz -> jacobian -> affine, jacobian add / double
+    jac = M.test_point_op(group, 4, lhs).reshape(n, jb)
+    ej = np.zeros_like(jac)
+    o.oracle_point_op(group, 4, O.ptr(lhs), None, None, O.ptr(ej), n)
+    fin = lhs[:, half:].any(axis=1)
+    assert (jac[fin] == ej[fin]).all()
+    aff = M.test_point_op(group, 5, jac).reshape(n, ab)
+    ea = np.zeros_like(aff)
+    o.oracle_point_op(group, 5, O.ptr(ej), None, None, O.ptr(ea), n)
+    assert (aff[fin] == ea[fin]).all() and not aff[~fin].any()
+    j2 = np.roll(jac, 3, axis=0).copy()
+    j2[:8] = jac[:8]
+    for op, rhs_ in ((0, j2), (1, None)):
+        exp = np.zeros_like(jac)
+        o.oracle_point_op(group, op, O.ptr(jac), O.ptr(rhs_) if rhs_ is not None else None, None, O.ptr(exp), n)
+        got = M.test_point_op(group, op, jac, rhs_).reshape(n, jb)
+        ga = M.test_point_op(group, 5, got)
+        xa = np.zeros(n * ab, dtype=np.uint8)
+        o.oracle_point_op(group, 5, O.ptr(exp), None, None, O.ptr(xa), n)
+        assert (ga == xa).all()  # compare as group elements (canonical affine)
+
+
+# ---------------------------------------------------------------- digits (a13, a14, a18, a21 front ends)
+@pytest.mark.parametrize("cfgname", ["10", "13", "16", "21"])
+def test_digit_decomposition_vs_oracle(M, cfgname):
+    n = 512
+    ctx = M.MsmContext(1, cfgname, npoints=n)
+    oc = O.OracleCtx(1, cfgname, n=n)
+    cfg = O.config(cfgname)
+    sc = O.gen_scalars(5, n)
+    sc[0] = 0
+    sc[1] = [1, 0, 0, 0]
+    rm1 = O.R_ORDER - 1
+    sc[2] = [(rm1 >> (64 * i)) & (2**64 - 1) for i in range(4)]
+    B = oc.bucket_set()
+    v2i = {int(b): i for i, b in enumerate(B)}
+    keys, vals = ctx.digits(0, sc)
+    for i in range(n):
+        m, b = oc.digits(0, sc[i])
+        for j in range(cfg["h"]):
+            idx = v2i[int(b[j])]
+            slot = i * cfg["h"] + j
+            assert keys[i, j] == (idx if idx else 0xFFFFFFFF)
+            assert (vals[i, j] & 0x7FFFFFFF) == 3 * slot + abs(int(m[j])) - 1
+            assert (vals[i, j] >> 31) == (1 if m[j] < 0 else 0)
+    keys, vals = ctx.digits(1, sc)
+    trick = cfg["n_exp"] in (13, 14, 16, 17)
+    for i in range(n):
+        d, cond = oc.digits(1, sc[i])
+        for j in range(cfg["h_bgmw"]):
+            mag = abs(int(d[j]))
+            assert keys[i, j] == (mag if mag else 0xFFFFFFFF)
+            sign = (1 if d[j] < 0 else 0) ^ (1 if (trick and cond[0]) else 0)
+            if mag:
+                assert (vals[i, j] >> 31) == sign
+            assert (vals[i, j] & 0x7FFFFFFF) == i * cfg["h_bgmw"] + j
+    # Booth windows: sum_t digit_t 2^(t w) == scalar
+    w, tiles = ctx.pippenger_window(), ctx.pippenger_tiles()
+    assert w == O.config(cfgname)["window"] if n == 1 << cfg["n_exp"] else True
+    keys, vals = ctx.digits(2, sc)
+    nbw = (1 << (w - 1)) + 1
+    ints = O.scalars_to_ints(sc)
+    for i in range(n):
+        acc = 0
+        for t in range(tiles):
+            k = int(keys[i, t])
+            if k != 0xFFFFFFFF:
+                assert k // nbw == t
+                mag = k % nbw
+                acc += (-mag if (vals[i, t] >> 31) else mag) << (t * w)
+        assert acc == ints[i]
+    ctx.close()
+
+
+# ---------------------------------------------------------------- config 10: everything vs the reference driver
+@pytest.mark.parametrize("group", [1, 2])
+def test_c10_tables_and_four_methods_vs_reference_golden(M, golden, group):
+    gd = golden["c10"][str(group)]
+    ctx = M.MsmContext(group, "10")
+    ctx.init_fix_point_list()
+    assert hashlib.sha256(ctx.download(0).tobytes()).hexdigest() == gd["sha256_fix_points"]
+    assert hashlib.sha256(ctx.bucket_set().tobytes()).hexdigest() == gd["sha256_bucket_set"]
+    ctx.init_pippenger_CHES_q_over_5()
+    ctx.init_pippenger_BGMW95()
+    assert hashlib.sha256(ctx.download(1).tobytes()).hexdigest() == gd["sha256_table_3nh"]
+    assert hashlib.sha256(ctx.download(2).tobytes()).hexdigest() == gd["sha256_table_bgmw95"]
+    for seed in (1, 2, 3, 4, 5):
+        sc = O.gen_scalars(seed, ctx.n)
+        res = [ctx.pippenger_variant_q_over_5_CHES(sc),
+               ctx.pippenger_variant_q_over_5_CHES_integral_scalar_conversion(sc),
+               ctx.pippenger_variant_BGMW95(sc),
+               ctx.pippenger_blst_built_in(sc)]
+        for m, r in enumerate(res, 1):
+            assert M.affine_serialize(group, r).hex() == gd["msm"][str(seed)], (seed, m)
+            assert O.serialize(group, r).hex() == gd["msm"][str(seed)]
+    assert ctx.last_launches() > 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_edge_case_scalars(M, group):
+    """zero scalars, ones, r-1, all-equal scalars (one giant bucket, P+P inside buckets), mixed."""
+    n = 1024
+    ctx = M.MsmContext(group, "10")
+    ctx.init_fix_point_list()
+    ctx.init_pippenger_CHES_q_over_5()
+    ctx.init_pippenger_BGMW95()
+    rm1 = [((O.R_ORDER - 1) >> (64 * i)) & (2**64 - 1) for i in range(4)]
+    cases = {}
+    z = np.zeros((n, 4), dtype=np.uint64)
+    cases["all_zero"] = z
+    one = z.copy(); one[:, 0] = 1
+    cases["all_one"] = one
+    cases["all_r_minus_1"] = np.array([rm1] * n, dtype=np.uint64)
+    same = np.repeat(O.gen_scalars(9, 1), n, axis=0)
+    cases["all_equal"] = same
+    mixed = O.gen_scalars(10, n); mixed[::3] = 0; mixed[1::7] = rm1
+    cases["mixed"] = mixed
+    single = z.copy(); single[n - 1] = O.gen_scalars(12, 1)[0]
+    cases["single_nonzero_last"] = single
+    for name, sc in cases.items():
+        exp, _ = O.closed_form(group, sc)
+        for method in (1, 2, 3, 4):
+            r = ctx.msm(method, sc)
+            assert (r == exp).all(), (name, method)
+    assert not ctx.msm(1, cases["all_zero"]).any()  # infinity -> all-zero affine (src/e1.c:60-75)
+    assert M.affine_serialize(group, ctx.msm(1, cases["all_zero"]))[0] == 0x40
+    ctx.close()
+
+
+def test_last_element_bug_inputs_give_true_sum(M):
+    """on inputs where the reference's methods 1-2 drop the last point, the product returns the
+    mathematically correct sum (= reference methods 3-4)."""
+    n = 1024
+    ctx = M.MsmContext(1, "10")
+    ctx.init_fix_point_list()
+    ctx.init_pippenger_CHES_q_over_5()
+    sc = O.gen_scalars(4, n)
+    v = O.scalars_to_ints(sc[n - 1:n])[0]
+    v &= ~(((1 << 26) - 1) << (13 * 17))
+    v |= 1 << (13 * 19)
+    v &= (1 << 255) - 1
+    sc[n - 1] = [(v >> (64 * i)) & (2**64 - 1) for i in range(4)]
+    oc = O.OracleCtx(1, "10", n=n)
+    assert oc.hits_bug(sc)
+    exp, _ = O.closed_form(1, sc)
+    assert (ctx.msm(1, sc) == exp).all() and (ctx.msm(2, sc) == exp).all()
+    ctx.close()
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_unstructured_points_vs_reference_pippenger_golden(M, golden, group):
+    """Caller-supplied (non 2^i G) points incl. an infinity entry: all four methods = compiled reference's
+    blst_pNs_mult_pippenger; table build on arbitrary points checked against the oracle's."""
+    gd = golden["pippenger_unstructured"][str(group)]
+    n = gd["n"]
+    pts = np.frombuffer(bytes.fromhex(gd["points"]), dtype=np.uint8).copy()
+    sc = np.frombuffer(bytes.fromhex(gd["scalars"]), dtype=np.uint64).reshape(n, 4).copy()
+    ctx = M.MsmContext(group, "8", npoints=n)
+    ctx.set_points(pts)
+    ctx.init_pippenger_CHES_q_over_5()
+    ctx.init_pippenger_BGMW95()
+    oc = O.OracleCtx(group, "8", n=n, threads=8)
+    oc.set_points(pts)
+    oc.build_table(0)
+    oc.build_table(1)
+    assert (ctx.download(1) == oc.table(0)).all()
+    assert (ctx.download(2) == oc.table(1)).all()
+    for method in (1, 2, 3, 4):
+        assert M.affine_serialize(group, ctx.msm(method, sc)).hex() == gd["result"], method
+    ctx.close()
+
+
+def test_ragged_sizes(M):
+    """n not a power of two, tiny n."""
+    for n in (2, 3, 37, 1000):
+        ctx = M.MsmContext(1, "10", npoints=n)
+        ctx.init_fix_point_list()
+        ctx.init_pippenger_CHES_q_over_5()
+        ctx.init_pippenger_BGMW95()
+        sc = O.gen_scalars(20 + n, n)
+        exp, _ = O.closed_form(1, sc)
+        for method in (1, 2, 3, 4):
+            assert (ctx.msm(method, sc) == exp).all(), (n, method)
+        ctx.close()
+
+
+def test_state_errors(M):
+    ctx = M.MsmContext(1, "10", npoints=16)
+    sc = O.gen_scalars(1, 16)
+    with pytest.raises(M.MsmB200Error):
+        ctx.msm(1, sc)  # no points/table yet
+    ctx.init_fix_point_list()
+    with pytest.raises(M.MsmB200Error):
+        ctx.msm(3, sc)
+    with pytest.raises(M.MsmB200Error):
+        ctx.msm(7, sc)
+    ctx.msm(4, sc)
+    ctx.close()
+
+
+# ---------------------------------------------------------------- blst-named shims (boundary §8b)
+@pytest.mark.parametrize("group", [1, 2])
+def test_blst_mult_pippenger_shim(M, golden, group):
+    gd = golden["pippenger_unstructured"][str(group)]
+    n = gd["n"]
+    ab, jb = O.AFF_BYTES[group], O.JAC_BYTES[group]
+    pts = np.frombuffer(bytes.fromhex(gd["points"]), dtype=np.uint8).copy()
+    sc = np.frombuffer(bytes.fromhex(gd["scalars"]), dtype=np.uint8).copy()
+    L = M.lib()
+    ret = np.zeros(jb, dtype=np.uint8)
+    # blst convention: {base, NULL} = contiguous
+    pp = (C.c_void_p * 2)(pts.ctypes.data, None)
+    sp = (C.c_void_p * 2)(sc.ctypes.data, None)
+    getattr(L, "msmb200_blst_p%ds_mult_pippenger" % group)(O.ptr(ret), pp, n, sp, 255, None)
+    aff = M.test_point_op(group, 5, ret)
+    assert M.affine_serialize(group, aff).hex() == gd["result"]
+    # one pointer per element (main_p1.cpp:408-418)
+    pp = (C.c_void_p * n)(*[pts.ctypes.data + i * ab for i in range(n)])
+    sp = (C.c_void_p * n)(*[sc.ctypes.data + i * 32 for i in range(n)])
+    ret2 = np.zeros(jb, dtype=np.uint8)
+    getattr(L, "msmb200_blst_p%ds_mult_pippenger" % group)(O.ptr(ret2), pp, n, sp, 255, None)
+    assert M.affine_serialize(group, M.test_point_op(group, 5, ret2)).hex() == gd["result"]
+    sz = getattr(L, "msmb200_blst_p%ds_mult_pippenger_scratch_sizeof" % group)(n)
+    assert sz == O.XYZZ_BYTES[group] << (O.config("8")["window"] - 1 if n == 256 else M.lib().msmb200_pippenger_window_size(n) - 1)
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_blst_tile_shims_ches_and_bgmw95(M, group):
+    """Drive the literal tile entry points the way main_p1.cpp:208-235,:311-388 does (host pointer arrays into a
+    host table, bucket values, signs), table taken from the oracle."""
+    n, cfgname = 64, "10"
+    cfg = O.config(cfgname)
+    ab, jb = O.AFF_BYTES[group], O.JAC_BYTES[group]
+    oc = O.OracleCtx(group, cfgname, n=n, threads=4)
+    oc.init_fix_points()
+    oc.build_table(0)
+    oc.build_table(1)
+    t3 = oc.table(0)
+    tb = oc.table(1)
+    sc = O.gen_scalars(31, n)
+    exp, _ = O.closed_form(group, sc)
+    B = oc.bucket_set()
+    q = 1 << cfg["e"]
+    v2i = np.zeros(q // 2 + 1, dtype=np.int32)
+    v2i[B] = np.arange(len(B), dtype=np.int32)
+    h = cfg["h"]
+    npts = n * h
+    scal = np.zeros(npts + 1, dtype=np.int32)
+    signs = np.zeros(npts, dtype=np.uint8)
+    ptrs = (C.c_void_p * npts)()
+    for i in range(n):
+        m, b = oc.digits(0, sc[i])
+        for j in range(h):
+            k = i * h + j
+            scal[k] = b[j]
+            signs[k] = 1 if m[j] < 0 else 0
+            ptrs[k] = t3.ctypes.data + (3 * k + abs(int(m[j])) - 1) * ab
+    ret = np.zeros(jb, dtype=np.uint8)
+    Bc = B.copy()
+    getattr(M.lib(), "msmb200_blst_p%d_tile_pippenger_d_CHES" % group)(O.ptr(ret), ptrs, npts, O.ptr(scal), O.ptr(signs), None,
+                                                                      O.ptr(Bc), O.ptr(v2i), len(B), cfg["d"])
+    assert (M.test_point_op(group, 5, ret) == exp).all()
+    hb = cfg["h_bgmw"]
+    npts = n * hb
+    scal = np.zeros(npts, dtype=np.int32)
+    signs = np.zeros(npts, dtype=np.uint8)
+    ptrs = (C.c_void_p * npts)()
+    for i in range(n):
+        d, _ = oc.digits(1, sc[i])
+        for j in range(hb):
+            k = i * hb + j
+            scal[k] = abs(int(d[j]))
+            signs[k] = 1 if d[j] < 0 else 0
+            ptrs[k] = tb.ctypes.data + k * ab
+    ret = np.zeros(jb, dtype=np.uint8)
+    getattr(M.lib(), "msmb200_blst_p%d_tile_pippenger_BGMW95" % group)(O.ptr(ret), ptrs, npts, O.ptr(scal), O.ptr(signs), None,
+                                                                      cfg["e_bgmw"])
+    assert (M.test_point_op(group, 5, ret) == exp).all()
+
+
+# ---------------------------------------------------------------- multi-GPU path emulated on one device
+@pytest.mark.parametrize("group", [1, 2])
+def test_sharded_partials_sum_to_full_result(M, group):
+    """G = 3 shards as three contexts on one GPU (B200_PROFILING.md: emulate ranks in one process): each yields a
+    Jacobian partial in device memory; sum_partials == single-context result == closed form."""
+    import torch
+
+    from msm_blst_b200 import distributed as D
+
+    n, world = 1000, 3
+    sc = O.gen_scalars(41, n)
+    exp, _ = O.closed_form(group, sc)
+    jb = O.JAC_BYTES[group]
+    partials = torch.zeros((world, jb), dtype=torch.uint8, device="cuda")
+    ctxs = []
+    for r in range(world):
+        lo, hi = D.shard_range(n, r, world)
+        ctx = M.MsmContext(group, "10", npoints=hi - lo, first=lo)
+        ctx.init_fix_point_list()
+        ctx.init_pippenger_CHES_q_over_5()
+        d_sc = torch.from_numpy(sc[lo:hi].view(np.uint8).copy()).cuda()
+        ctx.msm_partial_device(1, d_sc.data_ptr(), partials[r].data_ptr())
+        ctxs.append((ctx, d_sc))
+    torch.cuda.synchronize()
+    got = ctxs[0][0].sum_partials_device(partials.data_ptr(), world)
+    assert (got == exp).all()
+    host = partials.cpu().numpy().copy()
+    chk = np.zeros(O.AFF_BYTES[group], dtype=np.uint8)
+    O.oracle().oracle_sum_partials(group, O.ptr(host), world, O.ptr(chk))
+    assert (chk == exp).all()
+    for ctx, _ in ctxs:
+        ctx.close()
