@@ -1,0 +1,452 @@
+#!/usr/bin/env python
+"""bench.py — BLS12-381 fixed-base MSM latency (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload g1_n21|g2_n18|g1_n16] [--method 1..4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...       # the reference's CPU path on the host cores (oracle/_ref)
+
+A step = one MSM (method body of main_p1.cpp incl. to_affine) over one fresh set of seeded synthetic scalars.
+`value` is device-resident latency (scalars already in HBM), `e2e` the same call through the C ABI with HOST
+scalars (pinned H2D copy of the step's scalars + D2H of the result inside the timed region). Rank 0 prints ONE
+JSON line. Only the `cpu_baseline` leg and `--impl reference` execute anything under oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (group, reference config, description)
+    "g1_n21": (1, "21", "G1 fixed-base MSM n=2^21, CHES construction (config 21: q=2^22, h=12, |B|=874437)"),
+    "g2_n18": (2, "18", "G2 fixed-base MSM n=2^18, CHES construction (config 18: q=2^20, h=13, |B|=220931)"),
+    "g1_n16": (1, "16", "G1 fixed-base MSM n=2^16, CHES construction (config 16: q=2^19, h=14, |B|=109244)"),
+    "g1_n10": (1, "10", "G1 fixed-base MSM n=2^10, CHES construction (config 10)"),
+}
+METHOD_NAMES = {1: "CHES", 2: "CHES-integral", 3: "BGMW95", 4: "blst-Pippenger"}
+R_ORDER = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
+# ------------------------------------------------------------------------------------------------ inputs
+def gen_scalars(seed, n):
+    """Seeded splitmix64 scalar stream of SURVEY App. C (numpy restatement; vectorised, rejection of >= r)."""
+    def splitmix(state_start, count):
+        idx = np.arange(1, count + 1, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            z = np.uint64(state_start) + idx * np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            return z ^ (z >> np.uint64(31))
+    # a draw of 4 words is rejected as a whole, so accepted rows keep their order: over-draw rows, filter, take n
+    r_limbs = [(R_ORDER >> (64 * i)) & (2**64 - 1) for i in range(4)]
+    rows = int(n * 1.2) + 64
+    while True:
+        raw = splitmix(seed, 4 * rows).reshape(-1, 4).copy()
+        raw[:, 3] >>= np.uint64(1)
+        lt = np.zeros(len(raw), dtype=bool)
+        eq = np.ones(len(raw), dtype=bool)
+        for k in (3, 2, 1, 0):
+            lt |= eq & (raw[:, k] < np.uint64(r_limbs[k]))
+            eq &= raw[:, k] == np.uint64(r_limbs[k])
+        good = raw[lt]
+        if len(good) >= n:
+            return np.ascontiguousarray(good[:n])
+        rows *= 2
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.dev = device_index
+        self.proc = None
+        self.t_start = self.t_stop = None
+
+    def launch(self):
+        """Start the sampler process early (it needs ~0.5 s to print its first line)."""
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=timestamp," + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def start(self):
+        self.t_start = time.time()
+
+    def stop(self):
+        self.t_stop = time.time()
+        time.sleep(0.05)
+        lines = []
+        if self.proc:
+            self.proc.terminate()
+            try:
+                lines = self.proc.communicate(timeout=10)[0].splitlines()
+            except Exception:
+                lines = []
+        import datetime
+        sm, reasons, smax, power = [], set(), None, []
+        for ln in lines:
+            s = [x.strip() for x in ln.split(",")]
+            try:
+                ts = datetime.datetime.strptime(s[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if ts < self.t_start - 0.02 or ts > self.t_stop + 0.02:
+                    continue
+                sm.append(float(s[2]))
+                smax = float(s[3])
+                power.append(float(s[4]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[6:10]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power) if power else None}
+
+
+# ------------------------------------------------------------------------------------------------ cost model
+def cost_model(group, cfg, n, method):
+    """Algorithmic work per MSM from the REFERENCE's formulas."""
+    c_add, c_dadd = (10, 14) if group == 1 else (28, 40)
+    aff = 96 if group == 1 else 192
+    if method in (1, 2):
+        adds, dadds = n * cfg.h, 2 * (cfg.bsize - 1) + 2 * cfg.d
+    elif method == 3:
+        adds, dadds = n * cfg.h_bgmw, 2 * (1 << (cfg.e_bgmw - 1))
+    else:
+        wbits = n.bit_length() - 1
+        w = wbits - 3 if wbits > 12 else (wbits - 2 if wbits > 4 else (2 if wbits else 1))
+        tiles = 255 // w + 1
+        adds, dadds = n * tiles, 2 * (1 << (w - 1)) * tiles
+    w_fp_acc = adds * c_add
+    w_fp = w_fp_acc + dadds * c_dadd
+    return {"adds": adds, "dadds": dadds, "w_fp": w_fp, "w_mac": 300 * w_fp, "w_mac_accumulate": 300 * w_fp_acc,
+            "gather_bytes": adds * aff, "w_bytes": adds * aff + 32 * n}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's CPU path (compiled reference in oracle/_ref driven by the restated driver glue) on the
+    host cores. Rank 0 only; other ranks exit 0 without work."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+
+    group, cfgname, desc = WORKLOADS[args.workload]
+    O.oracle()
+    if not O.has_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (compiled reference) missing and /root/reference absent"}))
+        return 0
+    cfg = O.config(cfgname)
+    n = 1 << cfg["n_exp"]
+    threads = os.cpu_count() or 1
+    method = args.method
+    steps, warmup = args.steps, args.warmup
+    h = cfg["h"]
+    # bounded sample: per-step estimate (1.2 us per bucket add / dadd on one core, G2 x3) -> shrink n_s until the run fits ~200 s
+    unit = 1.2e-6 * (1 if group == 1 else 2.9)
+    def est(ns):
+        return ns * h * unit / threads + 2 * cfg["bsize"] * unit * 1.2
+    n_s = n
+    while n_s > 1024 and (steps + warmup) * est(n_s) > 200:
+        n_s //= 2
+    # the table: entries are canonical affine points, so any correct builder gives the reference's bytes. With a GPU
+    # present it is built there and spot-checked against the reference chain; else on the CPU.
+    oc = O.OracleCtx(group, cfgname, n=n_s, threads=threads)
+    oc.init_fix_points() if n_s <= 4096 else None
+    t0 = time.time()
+    table_src = "cpu (restated single_scalar_multiplication chain, %d threads)" % threads
+    have_gpu = False
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        pass
+    which = 1 if method == 3 else 0
+    if method == 4 or n_s <= 4096 or not have_gpu:
+        if n_s > 4096:
+            oc.init_fix_points()
+        if method != 4:
+            oc.build_table(which)
+    else:
+        import msm_blst_b200 as M
+        g = M.MsmContext(group, cfgname, npoints=n_s)
+        g.init_fix_point_list()
+        oc.set_points(g.download(0))
+        if which == 0:
+            g.init_pippenger_CHES_q_over_5()
+        else:
+            g.init_pippenger_BGMW95()
+        oc.load_table(which, g.download(1 + which))
+        # spot-check sampled rows against the reference's own construction
+        rng = np.random.default_rng(0)
+        hh = h if which == 0 else cfg["h_bgmw"]
+        mult = 3 if which == 0 else 1
+        for i in [0, n_s - 1] + [int(x) for x in rng.integers(0, n_s, size=6)]:
+            chk = O.OracleCtx(group, cfgname, n=1, first=i)
+            chk.init_fix_points()
+            chk.build_table(which)
+            row = oc.table(which).reshape(-1, O.AFF_BYTES[group])[mult * i * hh: mult * (i + 1) * hh].reshape(-1)
+            assert (row == chk.table(which)).all(), "GPU-built table row %d differs from the reference chain" % i
+        g.close()
+        table_src = "gpu-built, 8 rows spot-checked against the reference chain"
+    t_table = time.time() - t0
+    sets = [O.gen_scalars(1 + s, n_s) for s in range(min(3, steps + warmup))]
+    times, phases = [], None
+    ok = True
+    for it in range(warmup + steps):
+        sc = sets[it % len(sets)]
+        t0 = time.perf_counter()
+        r, ph = oc.msm_ref(method, sc, threads=threads)
+        dt = (time.perf_counter() - t0) * 1e3
+        if it >= warmup:
+            times.append(dt)
+            phases = ph
+        if it == 0:
+            cf, _ = O.closed_form(group, sc)
+            ok = bool((r == cf).all())
+    ms = float(np.mean(times))
+    scale = n / n_s
+    if scale > 1:  # extrapolate the sample: glue and bucket accumulation scale with n, the bucket reduction does not
+        ms_full = (phases["glue"] + (phases["tile"] - phases["reduce"])) * scale + phases["reduce"] + phases["finish"]
+    else:
+        ms_full = ms
+    sample = "%s: n_sample=2^%d of 2^%d points (%s), %d host threads each running the reference tile on its slice; table %s" % (
+        METHOD_NAMES[method], int(np.log2(n_s)), cfg["n_exp"], "full workload" if scale == 1 else "extrapolated x%g on the n-proportional phases" % scale,
+        threads, table_src)
+    line = {
+        "impl": "reference", "metric": "BLS12-381 %s fixed-base MSM latency, n=2^%d, %s" % ("G1" if group == 1 else "G2", cfg["n_exp"], METHOD_NAMES[method]),
+        "value": ms_full, "unit": "ms", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms_full,
+        "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u64x6 (384-bit Montgomery, x86-64 ADX asm)",
+        "data": "synthetic: P_i=2^(i+1)G, seeded splitmix64 scalars < r", "result_ok": ok,
+        "config": {"workload": desc, "method": METHOD_NAMES[method], "n": n, "n_sample": n_s},
+        "cpu_baseline": {"value": ms_full, "unit": "ms", "cores": threads, "kind": "reference", "sample": sample,
+                         "measured_ms_on_sample": ms, "phases_ms_on_sample": phases, "table_setup_s": t_table},
+        "e2e": {"value": ms_full, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_baseline_leg(group, cfgname, method, n, sets, gpu_ctx):
+    """Reference CPU path on ONE core (as shipped) next to the GPU run, on a bounded sample (10-30 s of CPU work)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import oracle_lib as O
+        O.oracle()
+        if not O.has_ref():
+            return {"value": None, "unit": "ms", "cores": 1, "kind": "reference", "sample": "oracle/_ref missing"}
+        cfg = O.config(cfgname)
+        unit = 1.2e-6 * (1 if group == 1 else 2.9)
+        n_s = n
+        while n_s > 1024 and n_s * cfg["h"] * unit + 2 * cfg["bsize"] * unit * 1.2 > 30:
+            n_s //= 2
+        oc = O.OracleCtx(group, cfgname, n=n_s)
+        which = 1 if method == 3 else 0
+        oc.set_points(gpu_ctx.download(0, 0, n_s))
+        if method != 4:
+            per = 3 * cfg["h"] if which == 0 else cfg["h_bgmw"]
+            oc.load_table(which, gpu_ctx.download(1 + which, 0, n_s * per))
+        sc = np.ascontiguousarray(sets[0][:n_s])
+        t0 = time.perf_counter()
+        r, ph = oc.msm_ref(method, sc, threads=1)
+        ms = (time.perf_counter() - t0) * 1e3
+        cf, _ = O.closed_form(group, sc)
+        scale = n / n_s
+        ms_full = ms if scale == 1 else (ph["glue"] + ph["tile"] - ph["reduce"]) * scale + ph["reduce"] + ph["finish"]
+        return {"value": ms_full, "unit": "ms", "cores": 1, "kind": "reference", "result_ok": bool((r == cf).all()),
+                "sample": "%s, compiled reference (x86-64 ADX asm) tile functions on 1 core, n_sample=2^%d of 2^%d (%s); table = GPU-built, "
+                          "byte-identical to the reference's (tests)" % (METHOD_NAMES[method], int(np.log2(n_s)), cfg["n_exp"],
+                                                                          "full workload" if scale == 1 else "n-proportional phases x%g" % scale),
+                "measured_ms_on_sample": ms, "phases_ms_on_sample": ph}
+    except Exception as ex:  # the baseline must never break the bench line
+        return {"value": None, "unit": "ms", "cores": 1, "kind": "reference", "sample": "failed: %r" % (ex,)}
+
+
+# ------------------------------------------------------------------------------------------------ main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="g1_n21", choices=sorted(WORKLOADS))
+    ap.add_argument("--method", type=int, default=1, choices=[1, 2, 3, 4])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-config", default="auto", help="reference config used per shard when --gpus > 1 (auto: tuned for n/G)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import msm_blst_b200 as M
+    from msm_blst_b200 import distributed as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: msm_blst_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+    N = world
+
+    group, cfgname, desc = WORKLOADS[args.workload]
+    full_cfg = M.config_lookup(cfgname)
+    n = 1 << full_cfg.n_exp
+    method = args.method
+    lo, hi = D.shard_range(n, rank, N)
+    shard_cfgname = cfgname if N == 1 else (D.shard_config_name(hi - lo) if args.shard_config == "auto" else args.shard_config)
+    ctx = M.MsmContext(group, shard_cfgname, npoints=hi - lo, device=local_rank, first=lo)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    t0 = time.time()
+    ctx.init_fix_point_list()
+    if method in (1, 2):
+        ctx.init_pippenger_CHES_q_over_5()
+    elif method == 3:
+        ctx.init_pippenger_BGMW95()
+    t_setup = time.time() - t0
+
+    # several scalar sets, rotated so that no step re-reads the previous step's inputs
+    nsets = 3
+    sets = [gen_scalars(1 + s, n) for s in range(nsets)]
+    host_sets = [torch.from_numpy(s[lo:hi].view(np.uint8).copy()).pin_memory() for s in sets]
+    dev_sets = [h.cuda(non_blocking=True) for h in host_sets]
+    jb = M.api.JAC_BYTES[group]
+    partial = torch.zeros(jb, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+
+    def step_device(i):
+        if N == 1:
+            return ctx.msm_device(method, dev_sets[i % nsets].data_ptr())
+        return D.msm_sharded(ctx, method, dev_sets[i % nsets], partial)
+
+    def step_e2e(i):
+        if N == 1:
+            return ctx.msm(method, host_sets[i % nsets].numpy())
+        d = dev_sets[i % nsets]
+        d.copy_(host_sets[i % nsets], non_blocking=True)
+        return D.msm_sharded(ctx, method, d, partial)
+
+    def timed(fn, steps, sampler=None):
+        if N > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res = None
+        phase_acc = np.zeros(6)
+        launches = 0
+        for i in range(steps):
+            res = fn(i)
+            if N == 1:
+                t = ctx.last_timings()
+                phase_acc += np.array([t[k] for k in ("digits", "sort", "accumulate", "reduce", "finalize", "total")])
+            launches += ctx.last_launches() + (1 if N > 1 else 0)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if N > 1:
+            dist.barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1)
+        if N > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res, phase_acc / max(1, steps), launches, clocks
+
+    for i in range(args.warmup):
+        step_device(i)
+        step_e2e(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.launch()
+        for i in range(args.warmup):  # keep the GPU busy while the sampler process starts
+            step_device(i)
+        time.sleep(0.6)
+        step_device(0)
+    ms_total, res, phases, launches, clocks = timed(step_device, args.steps, sampler)
+    ms_e2e_total, res_e2e, _, _, _ = timed(step_e2e, args.steps)
+    ms_step = ms_total / args.steps
+    ms_e2e = ms_e2e_total / args.steps
+
+    if rank == 0:
+        # correctness of what was timed: last step's result vs the closed form is checked by the test-suite; here a cheap
+        # self-consistency (device-resident and end-to-end paths agree) plus the known answer for seed 1 when applicable
+        last_set = (args.steps - 1) % nsets
+        result_hex = M.affine_serialize(group, res).hex()
+        consistent = bool((res == res_e2e).all())
+        cm = cost_model(group, full_cfg, n, method)
+        peak_mac, peak_fpmul = M.measure_peaks(local_rank)
+        line = {
+            "metric": "BLS12-381 %s fixed-base MSM latency, n=2^%d, %s" % ("G1" if group == 1 else "G2", full_cfg.n_exp, METHOD_NAMES[method]),
+            "value": ms_step, "unit": "ms", "n_gpus": N, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32x12 (384-bit Montgomery integers)", "data": "synthetic: P_i=2^(i+1)G, seeded splitmix64 scalars < r (SURVEY App. C)",
+            "config": {"workload": desc, "method": METHOD_NAMES[method], "n": n, "shard_config": shard_cfgname, "parallelism": "points sharded x%d" % N,
+                       "l2_policy": "inputs larger than L2: %.2f GB precomputation table gathered at random per step, %d rotating scalar sets" % (
+                           (3 * n * full_cfg.h if method in (1, 2) else n * full_cfg.h_bgmw if method == 3 else n) * (96 if group == 1 else 192) / 1e9, nsets),
+                       "table_setup_s": t_setup},
+            "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": int((hi - lo) * 32) * N, "d2h_bytes_per_step": (96 if group == 1 else 192)},
+            "gpu_launches": launches,
+            "result_hex": result_hex, "result_consistent": consistent, "last_scalar_seed": 1 + last_set,
+            "clocks": clocks,
+            "fp_mul_per_s": cm["w_fp"] / (ms_step * 1e-3),
+            "peaks_measured_live": {"imad_wide_macs_per_s": peak_mac, "dependent_fp_mul_per_s": peak_fpmul},
+        }
+        if N == 1:
+            acc_ms = float(phases[2])
+            achieved = cm["w_mac_accumulate"] / (acc_ms * 1e-3) / 1e12
+            line["phases_ms"] = dict(zip(("digits", "sort", "accumulate", "reduce", "finalize", "device_total"), [float(x) for x in phases]))
+            line["roofline"] = {
+                "bound": "imad", "kernel": "accumulate_kernel (bucket accumulation, xyzz += affine)",
+                "achieved": achieved, "peak": peak_mac / 1e12, "unit": "TMAC/s (32x32+64-bit)", "frac": achieved / (peak_mac / 1e12),
+                "traffic": None,
+                "note": "achieved = ALGORITHMIC MACs (n*h adds x 10 Fp-mul x 300 MAC, reference formulas SURVEY §8d) / CUDA-event time of the "
+                        "accumulate phase; peak = IMAD.WIDE.U32 microbenchmark measured in this run (MEASURED_PEAKS.json has no integer figure)",
+            }
+            line["roofline_path"] = {"bound": "imad", "achieved": cm["w_mac"] / (ms_step * 1e-3) / 1e12, "peak": peak_mac / 1e12,
+                                     "unit": "TMAC/s", "frac": cm["w_mac"] / (ms_step * 1e-3) / peak_mac, "note": "whole MSM, W_MAC = 300*W_Fp"}
+            hbm_peak = 6458.7
+            try:
+                hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+                hbm_src = "measured (MEASURED_PEAKS.json)"
+            except Exception:
+                hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+            gbs = cm["gather_bytes"] / (acc_ms * 1e-3) / 1e9
+            line["roofline_hbm"] = {"bound": "hbm", "kernel": "accumulate_kernel (table gather)", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                    "frac": gbs / hbm_peak, "traffic": None, "peak_source": hbm_src}
+            if not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_baseline_leg(group, cfgname, method, n, sets, ctx)
+        print(json.dumps(line))
+    ctx.close()
+    if N > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

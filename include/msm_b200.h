@@ -110,6 +110,10 @@ int msmb200_last_timings(msmb200_ctx *ctx, float out_ms[6]);
 /* Number of kernels launched by the last msm call. */
 int msmb200_last_launches(msmb200_ctx *ctx);
 
+/* Live roofline denominators (register-only microbenchmarks): full 32x32+64-bit multiply-accumulates
+ * per second with IMAD.WIDE.U32, and dependent-chain mul_mont_384 per second, on `device`. */
+int msmb200_measure_peaks(int device, double *imad_macs_per_s, double *fp_mul_per_s);
+
 /* ---- blst-named drop-ins (signatures of bindings/blst.h:238-240,:274-283,:299-304) ------------------
  * Exported under an msmb200_ prefix so the library can be linked next to libblst.a; build the reference
  * drivers with -Dblst_p1s_mult_pippenger=msmb200_blst_p1s_mult_pippenger etc.. Pointer

@@ -15,11 +15,12 @@ from .api import (  # noqa: F401
     host_bucket_set,
     host_digit_table,
     lib,
+    measure_peaks,
     test_field_op,
     test_point_op,
 )
 
 __all__ = [
-    "LIB_PATH", "MsmB200Error", "MsmContext", "affine_serialize", "build_library", "config_lookup", "host_bucket_set", "host_digit_table", "lib",
+    "LIB_PATH", "MsmB200Error", "MsmContext", "affine_serialize", "build_library", "config_lookup", "host_bucket_set", "host_digit_table", "lib", "measure_peaks",
     "test_field_op", "test_point_op",
 ]

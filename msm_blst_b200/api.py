@@ -80,6 +80,7 @@ def lib():
         L.msmb200_affine_serialize.argtypes = [ci, vp, vp]
         L.msmb200_last_timings.argtypes = [vp, vp]
         L.msmb200_last_launches.argtypes = [vp]
+        L.msmb200_measure_peaks.argtypes = [ci, vp, vp]
         L.msmb200_test_field_op.argtypes = [ci, ci, ci, vp, vp, vp, sz]
         L.msmb200_test_point_op.argtypes = [ci, ci, ci, vp, vp, vp, vp, sz]
         L.msmb200_test_digits.argtypes = [vp, ci, vp, sz, vp, vp]
@@ -110,6 +111,15 @@ def config_lookup(name):
     if lib().msmb200_config_lookup(str(name).encode(), C.byref(cfg)) != 0:
         raise KeyError("unknown configuration %r" % (name,))
     return cfg
+
+
+def measure_peaks(device=0):
+    """(IMAD.WIDE multiply-accumulates/s, dependent fp_mul/s) measured on the device right now."""
+    a, b = C.c_double(), C.c_double()
+    rc = lib().msmb200_measure_peaks(device, C.byref(a), C.byref(b))
+    if rc:
+        raise MsmB200Error("measure_peaks failed (%d)" % rc)
+    return a.value, b.value
 
 
 def host_bucket_set(e, a):

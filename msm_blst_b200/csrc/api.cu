@@ -290,6 +290,12 @@ int msmb200_affine_serialize(int group, const void *affine_host, unsigned char *
     return MSMB200_OK;
 }
 
+int msmb200_measure_peaks(int device, double *imad_macs_per_s, double *fp_mul_per_s) {
+    if (!imad_macs_per_s || !fp_mul_per_s) return MSMB200_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return MSMB200_ECUDA;
+    return measure_peaks(imad_macs_per_s, fp_mul_per_s);
+}
+
 // ---- parity-test hooks ------------------------------------------------------------------------------
 static int with_device_buffers(int device, const void *a, size_t abytes, const void *b, size_t bbytes, const unsigned char *flags,
                                size_t fbytes, void *out, size_t obytes, int (*fn)(const void *, const void *, const unsigned char *, void *, void *),

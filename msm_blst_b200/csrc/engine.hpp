@@ -72,6 +72,7 @@ struct GroupOps {
     int (*digits)(Ctx *, int kind, const void *d_scalars, size_t n, uint32_t *d_keys, uint32_t *d_vals);
 };
 
+int measure_peaks(double *macs_per_s, double *fp_mul_per_s);
 const GroupOps *group_ops_g1();
 const GroupOps *group_ops_g2();
 

@@ -15,6 +15,66 @@ static int field_op_g(int field, int op, const void *a, const void *b, void *out
     return cudaGetLastError() == cudaSuccess ? 0 : MSMB200_ECUDA;
 }
 
+// Register-only microbenchmarks (same kernels as microbench.cu) that give bench.py its integer roofline
+// denominators live: 32x32+64 multiply-accumulates per second (IMAD.WIDE.U32, 8 independent accumulators per
+// thread, 32 warps per SM) and dependent-chain fp_mul throughput.
+static __global__ void peak_imad_wide_kernel(uint64_t *out, uint32_t a, uint32_t b, int iters) {
+    uint64_t acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = threadIdx.x + k;
+    uint32_t x = a + threadIdx.x, y = b + blockIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(x), "r"(y));
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= acc[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+static __global__ void peak_fp_mul_kernel(fp_t *out, int iters) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    fp_t x, y;
+    fp_set_one(x);
+    fp_set_one(y);
+    x.l[0] ^= tid; y.l[1] ^= tid * 2654435761u;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) { fp_mul(x, x, y); fp_mul(y, y, x); }
+    x.l[0] ^= y.l[0];
+    out[tid] = x;
+}
+int measure_peaks(double *macs_per_s, double *fp_mul_per_s) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return MSMB200_ECUDA;
+    void *buf = nullptr;
+    if (cudaMalloc(&buf, (size_t)sms * 8 * 256 * 48) != cudaSuccess) return MSMB200_ECUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int it1 = 4096, it2 = 256;
+    float best1 = 1e30f, best2 = 1e30f, ms;
+    for (int r = 0; r < 7; r++) {
+        cudaEventRecord(e0);
+        peak_imad_wide_kernel<<<sms * 4, 256>>>((uint64_t *)buf, 3u + r, 5u, it1);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r >= 2 && ms < best1) best1 = ms;
+        cudaEventRecord(e0);
+        peak_fp_mul_kernel<<<sms * 8, 128>>>((fp_t *)buf, it2);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r >= 2 && ms < best2) best2 = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf);
+    if (cudaGetLastError() != cudaSuccess) return MSMB200_ECUDA;
+    *macs_per_s = 8.0 * it1 * (double)sms * 4 * 256 / (best1 * 1e-3);
+    *fp_mul_per_s = 2.0 * it2 * (double)sms * 8 * 128 / (best2 * 1e-3);
+    return MSMB200_OK;
+}
+
 static const GroupOps kOps = {
     sizeof(aff_t<fp_t>), sizeof(jac_t<fp_t>), sizeof(xyzz_t<fp_t>),
     msm_impl<fp_t, fpc_t>, generate_fix_points_impl<fpc_t>, table_build_impl<fpc_t>, sum_partials_impl<fpc_t>, tile_impl<fp_t, fpc_t>,

@@ -26,7 +26,12 @@ def all_gather_partials(partial, world=None):
     """partial: uint8 tensor of one Jacobian point on this rank's device -> (world, nbytes) tensor on every rank."""
     world = world or dist.get_world_size()
     out = torch.empty((world,) + tuple(partial.shape), dtype=partial.dtype, device=partial.device)
-    dist.all_gather_into_tensor(out, partial) if partial.is_cuda else dist.all_gather(list(out.unbind(0)), partial)
+    if partial.is_cuda:
+        dist.all_gather_into_tensor(out, partial)
+    else:  # gloo (CPU tests)
+        parts = [torch.empty_like(partial) for _ in range(world)]
+        dist.all_gather(parts, partial)
+        out = torch.stack(parts)
     return out
 
 
@@ -37,6 +42,5 @@ def msm_sharded(ctx, method, scalars_dev, partial_buf):
     partial_buf: torch uint8 CUDA tensor of JAC_BYTES.
     """
     ctx.msm_partial_device(method, scalars_dev.data_ptr(), partial_buf.data_ptr())
-    torch.cuda.current_stream().synchronize() if False else None
     gathered = all_gather_partials(partial_buf)
     return ctx.sum_partials_device(gathered.data_ptr(), gathered.shape[0])

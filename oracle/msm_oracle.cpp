@@ -23,6 +23,7 @@
 #include <string>
 #include <thread>
 #include <chrono>
+#include <algorithm>
 
 typedef unsigned __int128 u128;
 typedef uint64_t limb_t;
@@ -1099,3 +1100,161 @@ void oracle_sum_partials(int group, const void *partials, size_t count, void *ou
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Reference arm: the SAME driver-level glue as above (digit conversion, pointer arrays: main_p1.cpp:192-436)
+// but with the hot loops executed by the COMPILED REFERENCE (oracle/_ref/libblst_ref.so: x86-64 ADX assembly
+// field arithmetic, blst_pN_tile_pippenger_d_CHES / _BGMW95 / blst_pNs_mult_pippenger / blst_pN_to_affine),
+// loaded with dlopen. Used as bench.py's CPU baseline (kind "reference") and to cross-check the restatement.
+// The reference is single-threaded; `threads` > 1 shards the points over host threads the way the upstream
+// Rust/Go bindings do (bindings/rust/src/lib.rs:1840-1866): each thread runs the reference tile on its own
+// contiguous slice with its own bucket array, the partial sums are added with blst_pN_add_or_double.
+// ---------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+struct RefFns {
+    void *lib = nullptr;
+    void (*tile_ches[2])(void *, const void *const *, size_t, const int *, const unsigned char *, void *, int *, int *, size_t, int);
+    void (*tile_bgmw[2])(void *, const void *const *, size_t, const int *, const unsigned char *, void *, size_t);
+    void (*mult_pip[2])(void *, const void *const *, size_t, const unsigned char *const *, size_t, void *);
+    size_t (*pip_scratch[2])(size_t);
+    void (*to_affine[2])(void *, const void *);
+    void (*add_or_double[2])(void *, const void *, const void *);
+    void (*integrate_ches[2])(void *, void *, int *, size_t, int);
+};
+static RefFns g_ref;
+extern "C" int oracle_load_ref(const char *path) {
+    if (g_ref.lib) return 0;
+    void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) return -1;
+    const char *pre[2] = {"blst_p1", "blst_p2"};
+    for (int g = 0; g < 2; g++) {
+        std::string p = pre[g];
+        *(void **)&g_ref.tile_ches[g] = dlsym(h, (p + "_tile_pippenger_d_CHES").c_str());
+        *(void **)&g_ref.tile_bgmw[g] = dlsym(h, (p + "_tile_pippenger_BGMW95").c_str());
+        *(void **)&g_ref.mult_pip[g] = dlsym(h, (p + "s_mult_pippenger").c_str());
+        *(void **)&g_ref.pip_scratch[g] = dlsym(h, (p + "s_mult_pippenger_scratch_sizeof").c_str());
+        *(void **)&g_ref.to_affine[g] = dlsym(h, (p + "_to_affine").c_str());
+        *(void **)&g_ref.add_or_double[g] = dlsym(h, (p + "_add_or_double").c_str());
+        *(void **)&g_ref.integrate_ches[g] = dlsym(h, (p + "_integrate_buckets_accumulation_d_CHES").c_str());
+        if (!g_ref.tile_ches[g] || !g_ref.tile_bgmw[g] || !g_ref.mult_pip[g] || !g_ref.pip_scratch[g] || !g_ref.to_affine[g] ||
+            !g_ref.add_or_double[g] || !g_ref.integrate_ches[g]) { dlclose(h); return -2; }
+    }
+    g_ref.lib = h;
+    return 0;
+}
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// phases_ms: [0] glue (digit conversion + array fill), [1] reference tile calls (max over threads),
+//            [2] bucket-reduction share of [1] (re-timed integrate on thread 0's buckets; CHES only), [3] combine + to_affine
+template <class F> static int ref_msm_impl(const Ctx<F> &c, int gi, int method, const U256 *sc, Aff<F> *out, int threads, double *phases) {
+    if (!g_ref.lib) return -10;
+    int T = threads > 1 ? threads : 1;
+    if ((size_t)T > c.n / 2) T = (int)std::max<size_t>(1, c.n / 2);
+    std::vector<Jac<F>> part(T);
+    std::vector<double> t_glue(T, 0), t_tile(T, 0);
+    double t_reduce = 0;
+    bool trick = (c.cfg.n_exp == 13 || c.cfg.n_exp == 14 || c.cfg.n_exp == 16 || c.cfg.n_exp == 17);
+    auto work = [&](int t) {
+        size_t lo = c.n * t / T, hi = c.n * (t + 1) / T, cnt = hi - lo;
+        double t0 = now_ms();
+        if (method == 1 || method == 2) {
+            int h = c.cfg.h;
+            size_t np = cnt * h;
+            std::vector<int> scalars(np + 2, 0);
+            std::vector<unsigned char> signs(np);
+            std::vector<const void *> ptr(np);
+            if (method == 1) {
+                std::vector<int> em(h), eb(h);
+                for (size_t i = 0; i < cnt; i++) {
+                    mb_radixq(c, em.data(), eb.data(), sc[lo + i]);
+                    for (int j = 0; j < h; j++) {
+                        size_t idx = i * h + j, gidx = (lo + i) * h + j;
+                        int m = em[j];
+                        scalars[idx] = eb[j];
+                        ptr[idx] = &c.table_3nh[3 * gidx + (m > 0 ? m : -m) - 1];
+                        signs[idx] = m > 0 ? 0 : 1;
+                    }
+                }
+            } else {
+                for (size_t i = 0; i < cnt; i++) std_q_ary(&scalars[i * h], sc[lo + i], c.cfg.e, h);
+                for (size_t i = 0; i < np; i++) {
+                    Digit d = c.hash[scalars[i]];
+                    scalars[i] = d.b;
+                    signs[i] = (unsigned char)d.alpha;
+                    if (d.alpha && i + 1 < np) ++scalars[i + 1];
+                    ptr[i] = &c.table_3nh[3 * (lo * h + i) + d.m - 1];
+                }
+            }
+            std::vector<Xyzz<F>> buckets(c.bucket_set.size());
+            double t1 = now_ms();
+            g_ref.tile_ches[gi](&part[t], ptr.data(), np, scalars.data(), signs.data(), buckets.data(),
+                                const_cast<int *>(c.bucket_set.data()), const_cast<int *>(c.value_to_index.data()), c.bucket_set.size(), c.cfg.d);
+            double t2 = now_ms();
+            t_glue[t] = t1 - t0; t_tile[t] = t2 - t1;
+            if (t == 0) {
+                Jac<F> dummy;
+                double r0 = now_ms();
+                g_ref.integrate_ches[gi](&dummy, buckets.data(), const_cast<int *>(c.bucket_set.data()), c.bucket_set.size(), c.cfg.d);
+                t_reduce = now_ms() - r0;
+            }
+        } else if (method == 3) {
+            int h = c.cfg.h_bgmw, e = c.cfg.e_bgmw;
+            size_t np = cnt * h;
+            std::vector<int> scalars(np);
+            std::vector<unsigned char> signs(np);
+            std::vector<const void *> ptr(np);
+            std::vector<int> ex(h);
+            for (size_t i = 0; i < cnt; i++) {
+                U256 aa = sc[lo + i];
+                bool cond = trick && (aa.d[3] > (1ull << 62));
+                if (cond) aa = u256_sub(R_ORDER, aa);
+                qhalf_expr(ex.data(), aa, e, h);
+                for (int j = 0; j < h; j++) {
+                    size_t idx = i * h + j;
+                    int v = ex[j];
+                    ptr[idx] = &c.table_bgmw[(lo + i) * h + j];
+                    if (v > 0) { scalars[idx] = v; signs[idx] = cond ? 1 : 0; }
+                    else { scalars[idx] = -v; signs[idx] = cond ? 0 : 1; }
+                }
+            }
+            std::vector<Xyzz<F>> buckets(((size_t)1 << (e - 1)) + 1);
+            double t1 = now_ms();
+            g_ref.tile_bgmw[gi](&part[t], ptr.data(), np, scalars.data(), signs.data(), buckets.data(), (size_t)e);
+            double t2 = now_ms();
+            t_glue[t] = t1 - t0; t_tile[t] = t2 - t1;
+        } else {
+            std::vector<const void *> pp(cnt);
+            std::vector<const unsigned char *> sp(cnt);
+            for (size_t i = 0; i < cnt; i++) { pp[i] = &c.fix_points[lo + i]; sp[i] = (const unsigned char *)&sc[lo + i]; }
+            std::vector<uint64_t> scratch(g_ref.pip_scratch[gi](cnt) / 8 + 1);
+            double t1 = now_ms();
+            g_ref.mult_pip[gi](&part[t], pp.data(), cnt, sp.data(), 255, scratch.data());
+            double t2 = now_ms();
+            t_glue[t] = t1 - t0; t_tile[t] = t2 - t1;
+        }
+    };
+    if (T == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    double t3 = now_ms();
+    Jac<F> acc = part[0];
+    for (int t = 1; t < T; t++) g_ref.add_or_double[gi](&acc, &acc, &part[t]);
+    g_ref.to_affine[gi](out, &acc);
+    double t4 = now_ms();
+    if (phases) {
+        phases[0] = *std::max_element(t_glue.begin(), t_glue.end());
+        phases[1] = *std::max_element(t_tile.begin(), t_tile.end());
+        phases[2] = t_reduce;
+        phases[3] = t4 - t3;
+    }
+    return 0;
+}
+extern "C" int oracle_ctx_msm_ref(void *hv, int method, const uint64_t *scalars, void *out_affine, int threads, double *phases_ms) {
+    OracleHandle *h = (OracleHandle *)hv;
+    if (method < 1 || method > 4) return -1;
+    if (h->g1) return ref_msm_impl(*h->g1, 0, method, (const U256 *)scalars, (Aff<Fp> *)out_affine, threads, phases_ms);
+    return ref_msm_impl(*h->g2, 1, method, (const U256 *)scalars, (Aff<Fp2> *)out_affine, threads, phases_ms);
+}

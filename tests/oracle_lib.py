@@ -71,6 +71,8 @@ def oracle():
         lib.oracle_closed_form.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
         lib.oracle_naive_msm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         lib.oracle_sum_partials.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.oracle_load_ref.argtypes = [C.c_char_p]
+        lib.oracle_ctx_msm_ref.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _oracle = lib
     return _oracle
 
@@ -90,6 +92,17 @@ def blst_ref():
         name = "libblst_ref.so" if adx else "libblst_ref_noadx.so"
         _blst = C.CDLL(os.path.join(REF_DIR, name))
     return _blst
+
+
+def ref_lib_path():
+    adx = "adx" in open("/proc/cpuinfo").read()
+    return os.path.join(REF_DIR, "libblst_ref.so" if adx else "libblst_ref_noadx.so")
+
+
+def load_ref_into_oracle():
+    rc = oracle().oracle_load_ref(ref_lib_path().encode())
+    if rc != 0:
+        raise RuntimeError("cannot load compiled reference %s (rc=%d)" % (ref_lib_path(), rc))
 
 
 _refdrv = {}
@@ -214,6 +227,17 @@ class OracleCtx:
         rc = oracle().oracle_ctx_msm(self.h, method, ptr(scalars), ptr(out), int(faithful_bug))
         assert rc == 0
         return out
+
+    def msm_ref(self, method, scalars, threads=1):
+        """Same glue, hot loops run by the compiled reference (oracle/_ref/libblst_ref.so). Returns (affine, phases_ms)."""
+        load_ref_into_oracle()
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+        assert scalars.shape == (self.n, 4)
+        out = np.zeros(AFF_BYTES[self.group], dtype=np.uint8)
+        ph = np.zeros(4, dtype=np.float64)
+        rc = oracle().oracle_ctx_msm_ref(self.h, method, ptr(scalars), ptr(out), threads, ptr(ph))
+        assert rc == 0, rc
+        return out, dict(glue=float(ph[0]), tile=float(ph[1]), reduce=float(ph[2]), finish=float(ph[3]))
 
     def hits_bug(self, scalars):
         scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
