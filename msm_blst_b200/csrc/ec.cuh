@@ -96,7 +96,12 @@ template <class F> __device__ __forceinline__ void xyzz_add_affine(xyzz_t<F> &ac
         f_mul(acc.zz, acc.zz, PP);
         f_mul(acc.zzz, acc.zzz, PPP);
     } else if (f_is_zero(R)) {
-        xyzz_double_affine(acc, p.x, p.y, subtract);
+        // rare (P + P): run out of line on COPIES so that neither `acc` nor `p` has its address taken —
+        // otherwise the compiler keeps the hot accumulator in local memory for the whole loop
+        xyzz_t<F> t;
+        F px = p.x, py = p.y;
+        xyzz_double_affine(t, px, py, subtract);
+        acc = t;
     } else {
         xyzz_set_inf(acc);
     }
@@ -131,7 +136,9 @@ template <class F> __device__ __forceinline__ void xyzz_add(xyzz_t<F> &acc, cons
         f_mul(acc.zz, acc.zz, PP);
         f_mul(acc.zzz, acc.zzz, PPP);
     } else if (f_is_zero(R)) {
-        xyzz_double(acc, acc);
+        xyzz_t<F> t, a = acc;  // copies: keep `acc` out of local memory (see xyzz_add_affine)
+        xyzz_double(t, a);
+        acc = t;
     } else {
         xyzz_set_inf(acc);
     }

@@ -437,3 +437,30 @@ def test_sharded_partials_sum_to_full_result(M, group):
     assert (chk == exp).all()
     for ctx, _ in ctxs:
         ctx.close()
+
+
+# ---------------------------------------------------------------- the unmodified reference driver on the CUDA shims
+@pytest.mark.parametrize("group", [1, 2])
+def test_reference_driver_runs_on_the_cuda_shims(M, group):
+    """oracle/_ref/main_p{1,2}_dropin = the reference's own main_p{1,2}.cpp (config 10), compiled in place with its
+    MSM imports re-pointed at libmsm_b200.so. Its four methods run on fresh OpenSSL-random
+    scalars; they use different tables / digit systems, so identical printed points mean the shims are drop-ins."""
+    import os
+    import re
+    import subprocess
+
+    exe = os.path.join(O.REF_DIR, "main_p%d_dropin" % group)
+    if not os.path.exists(exe):
+        pytest.skip("drop-in driver not built (needs /root/reference at build time)")
+    out = subprocess.run("ulimit -s unlimited 2>/dev/null; exec %s" % exe, shell=True, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    text = out.stdout
+    blocks = re.split(r"\n\d\. ", text)[1:]
+    assert len(blocks) >= 4, text[-3000:]
+    pts = []
+    for b in blocks[:4]:
+        coords = re.findall(r"0x[0-9a-f ]{90,}", b)
+        assert len(coords) >= (2 if group == 1 else 4), b[:500]
+        pts.append(tuple(coords[: (2 if group == 1 else 4)]))
+    assert pts[0] == pts[1] == pts[2] == pts[3], pts
+    assert "0x0000000000000000 0000000000000000 0000000000000000 0000000000000000 0000000000000000 0000000000000000" not in pts[0][0]
