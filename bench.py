@@ -383,10 +383,11 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.launch()
-        for i in range(args.warmup):  # keep the GPU busy while the sampler process starts
-            step_device(i)
-        time.sleep(0.6)
-        step_device(0)
+    # every rank runs the same steps (collectives inside): keep the GPUs busy while the sampler process starts
+    for i in range(args.warmup):
+        step_device(i)
+    time.sleep(0.6)
+    step_device(0)
     ms_total, res, phases, launches, clocks = timed(step_device, args.steps, sampler)
     ms_e2e_total, res_e2e, _, _, _ = timed(step_e2e, args.steps)
     ms_step = ms_total / args.steps
