@@ -28,6 +28,26 @@ int ensure(Ctx *c, DevBuf &b, size_t bytes) {
     return 0;
 }
 
+std::vector<int> build_chunk_first(const int *values, size_t count, uint32_t vspan, uint32_t *nchunks_out) {
+    uint32_t maxv = count > 1 ? (uint32_t)values[count - 1] : 0;
+    uint32_t nchunks = (maxv + vspan - 1) / vspan;
+    if (nchunks == 0) nchunks = 1;
+    std::vector<int> cf(nchunks + 1);
+    size_t l = 1;
+    for (uint32_t c = 0; c <= nchunks; c++) {
+        while (l < count && (uint64_t)values[l] <= (uint64_t)c * vspan) l++;
+        cf[c] = (int)l;
+    }
+    cf[nchunks] = (int)count;
+    *nchunks_out = nchunks;
+    return cf;
+}
+uint32_t pick_vspan_host(size_t max_value, uint32_t nwindows) {
+    uint32_t v = 64;
+    while (v > 8 && (max_value / v) * nwindows < 32768) v >>= 1;
+    return v;
+}
+
 static int ctx_init_common(Ctx *c, int group, int device) {
     c->group = group;
     c->device = device;
@@ -48,7 +68,7 @@ static void ctx_free(Ctx *c) {
                       &c->item_start, &c->cursor, &c->item_begin, &c->item_cnt, &c->order, &c->len_hist, &c->len_start, &c->len_cursor,
                       &c->partial, &c->chunk_a, &c->chunk_b, &c->result, &c->flat, &c->signs, &c->pidx};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
-    void *ptrs[] = {c->d_bucket_vals, c->d_v2i, c->d_dtab, c->d_points, c->d_table_ches, c->d_table_bgmw};
+    void *ptrs[] = {c->d_bucket_vals, c->d_v2i, c->d_dtab, c->d_chunk_first, c->d_points, c->d_table_ches, c->d_table_bgmw};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_result) cudaFreeHost(c->h_result);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -145,6 +165,10 @@ int msmb200_ctx_create(msmb200_ctx **out, int group, const msmb200_config *cfg, 
     CREATE_CUDA(cudaMalloc(&c->d_bucket_vals, c->bucket_set.size() * sizeof(int)));
     CREATE_CUDA(cudaMalloc(&c->d_v2i, v2i.size() * sizeof(int)));
     CREATE_CUDA(cudaMalloc(&c->d_dtab, dtab.size() * sizeof(uint32_t)));
+    c->red_vspan = pick_vspan_host((size_t)c->bucket_set.back(), 1);
+    std::vector<int> cf = build_chunk_first(c->bucket_set.data(), c->bucket_set.size(), c->red_vspan, &c->red_nchunks);
+    CREATE_CUDA(cudaMalloc(&c->d_chunk_first, cf.size() * sizeof(int)));
+    CREATE_CUDA(cudaMemcpy(c->d_chunk_first, cf.data(), cf.size() * sizeof(int), cudaMemcpyHostToDevice));
     CREATE_CUDA(cudaMalloc(&c->d_points, npoints * c->ops->aff_bytes));
     CREATE_CUDA(cudaMemcpy(c->d_bucket_vals, c->bucket_set.data(), c->bucket_set.size() * sizeof(int), cudaMemcpyHostToDevice));
     CREATE_CUDA(cudaMemcpy(c->d_v2i, v2i.data(), v2i.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -409,10 +433,19 @@ static void shim_tile(int group, void *ret, const void *const points[], size_t n
     std::vector<uint32_t> pidx(npoints);
     for (size_t k = 0; k < npoints; k++) { memcpy(&hp[k * ab], points[k], ab); pidx[k] = (uint32_t)k; }
     size_t v2i_len = bucket_set_ascend ? (size_t)bucket_set_ascend[nbuckets - 1] + 1 : 0;
-    void *dp = nullptr, *dsc = nullptr, *dsg = nullptr, *dpi = nullptr, *dj = nullptr, *dbs = nullptr, *dv = nullptr;
+    void *dp = nullptr, *dsc = nullptr, *dsg = nullptr, *dpi = nullptr, *dj = nullptr, *dbs = nullptr, *dv = nullptr, *dcf = nullptr;
+    uint32_t vspan, nchunks;
+    std::vector<int> cf;
+    if (bucket_set_ascend) {
+        vspan = pick_vspan_host((size_t)bucket_set_ascend[nbuckets - 1], 1);
+        cf = build_chunk_first(bucket_set_ascend, nbuckets, vspan, &nchunks);
+    } else {
+        vspan = pick_vspan_host(nbuckets - 1, 1);
+        nchunks = (uint32_t)((nbuckets - 1 + vspan - 1) / vspan);
+    }
     bool ok = cudaMalloc(&dp, hp.size()) == cudaSuccess && cudaMalloc(&dsc, npoints * 4) == cudaSuccess && cudaMalloc(&dsg, npoints) == cudaSuccess &&
               cudaMalloc(&dpi, npoints * 4) == cudaSuccess && cudaMalloc(&dj, jb) == cudaSuccess;
-    if (ok && bucket_set_ascend) ok = cudaMalloc(&dbs, nbuckets * 4) == cudaSuccess && cudaMalloc(&dv, v2i_len * 4) == cudaSuccess;
+    if (ok && bucket_set_ascend) ok = cudaMalloc(&dbs, nbuckets * 4) == cudaSuccess && cudaMalloc(&dv, v2i_len * 4) == cudaSuccess && cudaMalloc(&dcf, cf.size() * 4) == cudaSuccess;
     if (!ok) { c->err = "cudaMalloc"; shim_fail(c, "blst_pN_tile_pippenger"); }
     cudaMemcpyAsync(dp, hp.data(), hp.size(), cudaMemcpyHostToDevice, c->stream);
     cudaMemcpyAsync(dsc, scalars, npoints * 4, cudaMemcpyHostToDevice, c->stream);
@@ -421,13 +454,14 @@ static void shim_tile(int group, void *ret, const void *const points[], size_t n
     if (bucket_set_ascend) {
         cudaMemcpyAsync(dbs, bucket_set_ascend, nbuckets * 4, cudaMemcpyHostToDevice, c->stream);
         cudaMemcpyAsync(dv, v2i, v2i_len * 4, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(dcf, cf.data(), cf.size() * 4, cudaMemcpyHostToDevice, c->stream);
     }
     if (c->ops->tile(c, dp, (const int *)dsc, (const unsigned char *)dsg, (const uint32_t *)dpi, npoints, (const int *)dv, (const int *)dbs, nbuckets,
-                     d_max, dj))
+                     d_max, (const int *)dcf, vspan, nchunks, dj))
         shim_fail(c, "blst_pN_tile_pippenger");
     cudaMemcpyAsync(ret, dj, jb, cudaMemcpyDeviceToHost, c->stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pN_tile_pippenger"); }
-    cudaFree(dp); cudaFree(dsc); cudaFree(dsg); cudaFree(dpi); cudaFree(dj); cudaFree(dbs); cudaFree(dv);
+    cudaFree(dp); cudaFree(dsc); cudaFree(dsg); cudaFree(dpi); cudaFree(dj); cudaFree(dbs); cudaFree(dv); cudaFree(dcf);
 }
 
 size_t msmb200_blst_p1s_mult_pippenger_scratch_sizeof(size_t npoints) { return (size_t)192 << (pippenger_window_size(npoints) - 1); }

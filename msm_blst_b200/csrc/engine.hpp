@@ -36,6 +36,8 @@ struct Ctx {
     int *d_bucket_vals = nullptr;     // BUCKET_SET
     int *d_v2i = nullptr;             // BUCKET_VALUE_TO_ITS_INDEX  [q/2+1]
     uint32_t *d_dtab = nullptr;       // packed DIGIT_CONVERSION_HASH_TABLE [q+1]
+    int *d_chunk_first = nullptr;     // bucket-reduction chunk boundaries of BUCKET_SET (value-aligned chunks)
+    uint32_t red_vspan = 0, red_nchunks = 0;
 
     // points and tables (affine, Montgomery)
     void *d_points = nullptr;      bool have_points = false;
@@ -64,7 +66,8 @@ struct GroupOps {
     int (*sum_partials)(Ctx *, const void *d_partials, int count);
     // generic tile: device arrays of bucket index (or value when v2i given) / sign / point index into d_table
     int (*tile)(Ctx *, const void *d_table, const int *d_bvals, const unsigned char *d_signs, const uint32_t *d_pidx,
-                size_t m, const int *d_v2i, const int *d_bucket_vals, size_t nbuckets, int d_max, void *d_out_jac);
+                size_t m, const int *d_v2i, const int *d_bucket_vals, size_t nbuckets, int d_max, const int *d_chunk_first, uint32_t vspan,
+                uint32_t nchunks, void *d_out_jac);
     int (*pippenger)(Ctx *, const void *d_points, size_t npoints, const void *d_scalars, int nbits, void *d_out_jac,
                      bool want_affine);
     int (*field_op)(int field, int op, const void *a, const void *b, void *out, size_t n);
@@ -76,6 +79,9 @@ int measure_peaks(double *macs_per_s, double *fp_mul_per_s);
 const GroupOps *group_ops_g1();
 const GroupOps *group_ops_g2();
 
+// chunk_first[c] = first index l >= 1 with values[l] > c * vspan (c = 0..nchunks), values ascending
+std::vector<int> build_chunk_first(const int *values, size_t count, uint32_t vspan, uint32_t *nchunks_out);
+uint32_t pick_vspan_host(size_t max_value, uint32_t nwindows);
 int ctx_fail(Ctx *c, int code, const std::string &msg);
 int ensure(Ctx *c, DevBuf &b, size_t bytes);
 

@@ -40,7 +40,7 @@ static __global__ void peak_fp_mul_kernel(fp_t *out, int iters) {
     fp_set_one(y);
     x.l[0] ^= tid; y.l[1] ^= tid * 2654435761u;
 #pragma unroll 1
-    for (int i = 0; i < iters; i++) { fp_mul(x, x, y); fp_mul(y, y, x); }
+    for (int i = 0; i < iters; i++) { fp_mul_inline(x, x, y); fp_mul_inline(y, y, x); }
     x.l[0] ^= y.l[0];
     out[tid] = x;
 }

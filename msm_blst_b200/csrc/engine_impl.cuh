@@ -17,7 +17,17 @@ struct Layout {
     uint32_t wbits;      // doublings between windows
     const int *bucket_vals;  // device, or nullptr for dense (value = local index)
     int d_max;
+    const int *chunk_first;  // device (sparse only): first local index whose value exceeds c * vspan, c = 0..nchunks
+    uint32_t vspan;          // value span of one reduction chunk (power of two)
+    uint32_t nchunks;        // reduction chunks per window
 };
+
+// value span of a reduction chunk: aim at ~32 K chunks in total, between 8 and 64 values per chunk
+static inline uint32_t pick_vspan(size_t max_value, uint32_t nwindows) {
+    uint32_t v = 64;
+    while (v > 8 && (max_value / v) * nwindows < 32768) v >>= 1;
+    return v;
+}
 
 // sort + accumulate + reduce + finalize over entries already in c->keys / c->vals with histogram in c->count
 // F: field type of the hot kernels (multiplier inlined); FC: same layout, out-of-line multiplier, for the rest
@@ -72,28 +82,27 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     c->launches += 2;
     MSM_CUDA(c, cudaEventRecord(c->ev[3], st));
     // ---- reduce ----
-    uint32_t chunk = 32;
-    // keep at least ~4 warps per SM busy, but never fewer than 8 buckets per chunk
-    while (chunk > 8 && (size_t)L.nwindows * ((L.nbw + chunk - 1) / chunk) < 148 * 128) chunk >>= 1;
-    uint32_t cpw = (L.nbw - 1 + chunk - 1) / chunk;
-    if (cpw == 0) cpw = 1;
+    const uint32_t cpw = L.nchunks;
     size_t nchunks = (size_t)cpw * L.nwindows;
-    if (ensure(c, c->chunk_a, nchunks * sizeof(xyzz_t<F>)) || ensure(c, c->chunk_b, (nchunks / 8 + L.nwindows + 1) * sizeof(xyzz_t<F>)))
+    if (ensure(c, c->chunk_a, 2 * nchunks * sizeof(xyzz_t<F>)) || ensure(c, c->chunk_b, (2 * ((size_t)cpw / 4 + 2) * L.nwindows + 2) * sizeof(xyzz_t<F>)))
         return MSMB200_ECUDA;
     if (L.bucket_vals)
         reduce_chunks_kernel<F, false><<<blocks_for(nchunks, 128), 128, 0, st>>>(
-            (const xyzz_t<F> *)c->partial.p, count, (const uint32_t *)c->item_start.p, L.bucket_vals, L.nbw, L.nwindows, chunk, cpw,
-            L.d_max, (xyzz_t<F> *)c->chunk_a.p);
+            (const xyzz_t<F> *)c->partial.p, count, (const uint32_t *)c->item_start.p, L.bucket_vals, L.chunk_first, L.nbw, L.nwindows,
+            L.vspan, cpw, L.d_max, (xyzz_t<F> *)c->chunk_a.p);
     else
         reduce_chunks_kernel<F, true><<<blocks_for(nchunks, 128), 128, 0, st>>>(
-            (const xyzz_t<F> *)c->partial.p, count, (const uint32_t *)c->item_start.p, nullptr, L.nbw, L.nwindows, chunk, cpw, 1,
+            (const xyzz_t<F> *)c->partial.p, count, (const uint32_t *)c->item_start.p, nullptr, nullptr, L.nbw, L.nwindows, L.vspan, cpw, 1,
             (xyzz_t<F> *)c->chunk_a.p);
     c->launches += 1;
+    // tree of sums over the 2 rows of every window
     xyzz_t<F> *cur = (xyzz_t<F> *)c->chunk_a.p, *nxt = (xyzz_t<F> *)c->chunk_b.p;
     uint32_t per = cpw;
+    const uint32_t nrows = 2 * L.nwindows;
     while (per > 1) {
-        uint32_t groups = (per + 7) / 8;
-        sum_groups_kernel<FC><<<blocks_for((size_t)groups * L.nwindows, 128), 128, 0, st>>>((const xyzz_t<FC> *)cur, per, L.nwindows, 8, groups, (xyzz_t<FC> *)nxt);
+        uint32_t r = per > 4096 ? 8 : 4;
+        uint32_t groups = (per + r - 1) / r;
+        sum_groups_kernel<FC><<<blocks_for((size_t)groups * nrows, 128), 128, 0, st>>>((const xyzz_t<FC> *)cur, per, nrows, r, groups, (xyzz_t<FC> *)nxt);
         c->launches += 1;
         std::swap(cur, nxt);
         per = groups;
@@ -102,7 +111,9 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     // ---- finalize ----
     jac_t<F> *d_jac = d_out_jac ? (jac_t<F> *)d_out_jac : (jac_t<F> *)c->result.p;
     aff_t<F> *d_aff = (aff_t<F> *)((char *)c->result.p + sizeof(jac_t<F>));
-    finalize_kernel<FC><<<1, 32, 0, st>>>((const xyzz_t<FC> *)cur, L.nwindows, L.wbits, (jac_t<FC> *)d_jac, want_affine ? (aff_t<FC> *)d_aff : nullptr);
+    uint32_t vshift = 0;
+    while ((1u << vshift) < L.vspan) vshift++;
+    finalize_kernel<FC><<<1, 32, 0, st>>>((const xyzz_t<FC> *)cur, L.nwindows, L.wbits, vshift, (jac_t<FC> *)d_jac, want_affine ? (aff_t<FC> *)d_aff : nullptr);
     c->launches += 1;
     if (want_affine) MSM_CUDA(c, cudaMemcpyAsync(c->h_result, d_aff, sizeof(aff_t<F>), cudaMemcpyDeviceToHost, st));
     MSM_CUDA(c, cudaEventRecord(c->ev[5], st));
@@ -137,7 +148,8 @@ static int pippenger_impl(Ctx *c, const void *d_points, size_t npoints, const vo
                                                                   (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p);
     c->launches += 1;
     MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
-    Layout L{m, nbw, (uint32_t)tiles, (uint32_t)w, nullptr, 1};
+    uint32_t vs = pick_vspan(nbw - 1, (uint32_t)tiles);
+    Layout L{m, nbw, (uint32_t)tiles, (uint32_t)w, nullptr, 1, nullptr, vs, (nbw - 1 + vs - 1) / vs};
     return run_buckets<F, FC>(c, L, (const aff_t<F> *)d_points, d_out_jac, want_affine);
 }
 
@@ -171,7 +183,7 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
             c->launches += 3;
         }
         MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
-        Layout L{m, (uint32_t)nb, 1, 0, c->d_bucket_vals, cfg.d};
+        Layout L{m, (uint32_t)nb, 1, 0, c->d_bucket_vals, cfg.d, c->d_chunk_first, c->red_vspan, c->red_nchunks};
         return run_buckets<F, FC>(c, L, (const aff_t<F> *)c->d_table_ches, d_out_jac, want_affine);
     }
     if (method == MSMB200_BGMW95) {
@@ -185,7 +197,8 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
                                                                (uint32_t *)c->count.p);
         c->launches += 1;
         MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
-        Layout L{m, nbw, 1, 0, nullptr, 1};
+        uint32_t vs = pick_vspan(nbw - 1, 1);
+        Layout L{m, nbw, 1, 0, nullptr, 1, nullptr, vs, (nbw - 1 + vs - 1) / vs};
         return run_buckets<F, FC>(c, L, (const aff_t<F> *)c->d_table_bgmw, d_out_jac, want_affine);
     }
     return ctx_fail(c, MSMB200_EINVAL, "unknown method");
@@ -195,7 +208,8 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
 // blst_p1_tile_pippenger_d_CHES / _BGMW95 shims
 template <class F, class FC>
 static int tile_impl(Ctx *c, const void *d_table, const int *d_bvals, const unsigned char *d_signs, const uint32_t *d_pidx, size_t m,
-                     const int *d_v2i, const int *d_bucket_vals, size_t nbuckets, int d_max, void *d_out_jac) {
+                     const int *d_v2i, const int *d_bucket_vals, size_t nbuckets, int d_max, const int *d_chunk_first, uint32_t vspan,
+                     uint32_t nchunks, void *d_out_jac) {
     cudaStream_t st = c->stream;
     c->launches = 0;
     MSM_CUDA(c, cudaEventRecord(c->ev[0], st));
@@ -205,7 +219,7 @@ static int tile_impl(Ctx *c, const void *d_table, const int *d_bvals, const unsi
                                                            (uint32_t *)c->count.p);
     c->launches += 1;
     MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
-    Layout L{m, (uint32_t)nbuckets, 1, 0, d_bucket_vals, d_max};
+    Layout L{m, (uint32_t)nbuckets, 1, 0, d_bucket_vals, d_max, d_chunk_first, vspan, nchunks};
     return run_buckets<F, FC>(c, L, (const aff_t<F> *)d_table, d_out_jac, false);
 }
 

@@ -171,7 +171,7 @@ __device__ __forceinline__ void fp_row(uint32_t *ev, uint32_t *od, const uint32_
     fp_row_reduce(ev, od);
 }
 
-__device__ __forceinline__ void fp_mul(fp_t &r, const fp_t &a, const fp_t &b) {
+__device__ __forceinline__ void fp_mul_inline(fp_t &r, const fp_t &a, const fp_t &b) {
     uint32_t A[12], B[12];
     {
         uint32_t b0 = b.l[0];
@@ -197,7 +197,18 @@ __device__ __forceinline__ void fp_mul(fp_t &r, const fp_t &a, const fp_t &b) {
     t[11] = addc(A[11], 0);
     fp_final_sub(r, t);
 }
-__device__ __forceinline__ void fp_sqr(fp_t &r, const fp_t &a) { fp_mul(r, a, a); }
+// ONE out-of-line copy of the multiplier per translation unit, operands and result passed BY VALUE: the CUDA ABI
+// keeps 12-word structs in registers across the call (cuobjdump shows no LDL/STL), so a point addition is ~10
+// CALLs into 5.6 KB of code instead of 60+ KB of straight-line code. ncu on the fully inlined version showed
+// `stalled_no_instruction` as a top stall reason (instruction-cache misses: every multiplication instance was
+// fetched again on every loop iteration).
+static __device__ __noinline__ fp_t fp_mul_fn(fp_t a, fp_t b) {
+    fp_t r;
+    fp_mul_inline(r, a, b);
+    return r;
+}
+__device__ __forceinline__ void fp_mul(fp_t &r, const fp_t &a, const fp_t &b) { r = fp_mul_fn(a, b); }
+__device__ __forceinline__ void fp_sqr(fp_t &r, const fp_t &a) { r = fp_mul_fn(a, a); }
 
 // from Montgomery form: a * 1 * R^-1
 __device__ __forceinline__ void fp_from_mont(fp_t &r, const fp_t &a) {

@@ -27,7 +27,7 @@ __device__ __forceinline__ void f_inv(fp_t &r, const fp_t &a) { fp_inv(r, a); }
 // Kernels off the hot path are instantiated with F = fpc_t so that each translation unit contains ONE copy
 // of the ~350-instruction Montgomery multiplier instead of one per call site (compile time, I-cache).
 struct __align__(16) fpc_t : fp_t {};
-static __device__ __noinline__ void fp_mul_call(fp_t &r, const fp_t &a, const fp_t &b) { fp_mul(r, a, b); }
+__device__ __forceinline__ void fp_mul_call(fp_t &r, const fp_t &a, const fp_t &b) { r = fp_mul_fn(a, b); }
 __device__ __forceinline__ void f_mul(fpc_t &r, const fpc_t &a, const fpc_t &b) { fp_mul_call(r, a, b); }
 __device__ __forceinline__ void f_sqr(fpc_t &r, const fpc_t &a) { fp_mul_call(r, a, a); }
 __device__ __forceinline__ void f_add(fpc_t &r, const fpc_t &a, const fpc_t &b) { fp_add(r, a, b); }

@@ -86,7 +86,7 @@ __global__ void k_fp_mul(fp_t *out, const fp_t *in, int iters, long long *cyc) {
     fp_t x = in[tid & 1023], y = in[(tid + 7) & 1023];
     long long t0 = clock64();
 #pragma unroll 1
-    for (int i = 0; i < iters; i++) { fp_mul(x, x, y); fp_mul(y, y, x); }
+    for (int i = 0; i < iters; i++) { fp_mul_inline(x, x, y); fp_mul_inline(y, y, x); }
     long long t1 = clock64();
     out[tid] = x;
     out[tid].l[0] ^= y.l[0];

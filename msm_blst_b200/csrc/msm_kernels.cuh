@@ -394,13 +394,22 @@ __device__ __forceinline__ void load_xyzz(xyzz_t<F> &p, const xyzz_t<F> *src_) {
 }
 template <class F, bool DENSE>
 static __global__ void __launch_bounds__(128) reduce_chunks_kernel(const xyzz_t<F> *__restrict__ partial, const uint32_t *__restrict__ count,
-                                                            const uint32_t *__restrict__ item_start, const int *__restrict__ bucket_vals,
-                                                            uint32_t nbw, uint32_t nwindows, uint32_t chunk, uint32_t chunks_per_window,
-                                                            int d_max, xyzz_t<F> *__restrict__ out) {
+                                                                   const uint32_t *__restrict__ item_start, const int *__restrict__ bucket_vals,
+                                                                   const int *__restrict__ chunk_first, uint32_t nbw, uint32_t nwindows,
+                                                                   uint32_t vspan, uint32_t chunks_per_window, int d_max,
+                                                                   xyzz_t<F> *__restrict__ out) {
+    // chunk c of window w covers the buckets whose VALUE lies in (c*vspan, (c+1)*vspan]  (vspan a power of two).
+    //   DENSE : value == local index           -> locals [c*vspan + 1, (c+1)*vspan]
+    //   sparse: values = bucket_vals[] (CHES)  -> locals [chunk_first[c], chunk_first[c+1])
+    // out rows per window: row 0 = W_c = sum (val - c*vspan) * S, row 1 = c * T_c  (T_c = sum S); the caller adds
+    // sum(row0) + vspan * sum(row1).
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nwindows * chunks_per_window) return;
     uint32_t w = t / chunks_per_window, c = t % chunks_per_window;
-    uint32_t lo = 1 + c * chunk, hi = min(nbw, lo + chunk);  // locals [lo, hi)
+    uint32_t lo, hi;
+    if (DENSE) { lo = 1 + c * vspan; hi = min(nbw, lo + vspan); }
+    else { lo = (uint32_t)chunk_first[c]; hi = (uint32_t)chunk_first[c + 1]; }
+    const int base = (int)(c * vspan);
     xyzz_t<F> tmp, W;
     xyzz_set_inf(tmp);
     xyzz_set_inf(W);
@@ -408,9 +417,7 @@ static __global__ void __launch_bounds__(128) reduce_chunks_kernel(const xyzz_t<
     if (!DENSE) {
         for (int g = 0; g <= d_max; g++) xyzz_set_inf(tmp_d[g]);
     }
-    int base = 0;
     if (lo < hi) {
-        base = DENSE ? (int)(lo - 1) : bucket_vals[lo - 1];
 #pragma unroll 1
         for (uint32_t l = hi; l-- > lo;) {
             size_t b = (size_t)w * nbw + l;
@@ -422,7 +429,7 @@ static __global__ void __launch_bounds__(128) reduce_chunks_kernel(const xyzz_t<
             if (DENSE) {
                 xyzz_add_cold(W, tmp);
             } else {
-                int gap = bucket_vals[l] - bucket_vals[l - 1];
+                int gap = bucket_vals[l] - (l > lo ? bucket_vals[l - 1] : base);
                 xyzz_add_cold(tmp_d[gap], tmp);
             }
         }
@@ -435,20 +442,21 @@ static __global__ void __launch_bounds__(128) reduce_chunks_kernel(const xyzz_t<
                 xyzz_add_cold(W, acc);
             }
         }
-        // W += base * tmp  (MSB-first double-and-add; base < 2^22)
-        if (base != 0 && !xyzz_is_inf(tmp)) {
-            xyzz_t<F> r;
-            xyzz_set_inf(r);
-            int top = 31 - __clz(base);
+    }
+    // row 1: c * T_c by MSB-first double-and-add (c < 2^17)
+    xyzz_t<F> r;
+    xyzz_set_inf(r);
+    if (c != 0 && !xyzz_is_inf(tmp)) {
+        int top = 31 - __clz((int)c);
 #pragma unroll 1
-            for (int bit = top; bit >= 0; bit--) {
-                if (!xyzz_is_inf(r)) xyzz_double(r, r);
-                if ((base >> bit) & 1) xyzz_add_cold(r, tmp);
-            }
-            xyzz_add_cold(W, r);
+        for (int bit = top; bit >= 0; bit--) {
+            if (!xyzz_is_inf(r)) { xyzz_t<F> a = r; xyzz_double(r, a); }
+            if ((c >> bit) & 1) xyzz_add_cold(r, tmp);
         }
     }
-    out[t] = W;
+    size_t o = (size_t)w * 2 * chunks_per_window + c;
+    out[o] = W;
+    out[o + chunks_per_window] = r;
 }
 // out[w*groups + g] = sum of in[w*per_window + g*r .. +r)
 template <class F>
@@ -474,17 +482,22 @@ static __global__ void __launch_bounds__(128) sum_groups_kernel(const xyzz_t<F> 
 // (src/ec_ops.h:771-777) and, when want_affine, blst_p1_to_affine (src/e1.c:80-92). One thread.
 // ------------------------------------------------------------------------------------------------
 template <class F>
-static __global__ void finalize_kernel(const xyzz_t<F> *__restrict__ window_sums, uint32_t nwindows, uint32_t wbits,
-                                jac_t<F> *__restrict__ out_jac, aff_t<F> *__restrict__ out_aff) {
+static __global__ void finalize_kernel(const xyzz_t<F> *__restrict__ row_sums, uint32_t nwindows, uint32_t wbits, uint32_t vshift,
+                                       jac_t<F> *__restrict__ out_jac, aff_t<F> *__restrict__ out_aff) {
+    // row_sums[2w] = sum of the W rows, row_sums[2w+1] = sum of the c*T rows of window w: window sum = W + 2^vshift * P
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     xyzz_t<F> acc;
     xyzz_set_inf(acc);
     for (int w = (int)nwindows - 1; w >= 0; w--) {
-        xyzz_t<F> s = window_sums[w];
+        xyzz_t<F> s = row_sums[2 * w + 1];
+        for (uint32_t k = 0; k < vshift; k++)
+            if (!xyzz_is_inf(s)) { xyzz_t<F> a = s; xyzz_double(s, a); }
+        xyzz_t<F> wrow = row_sums[2 * w];
+        xyzz_add_cold(s, wrow);
         xyzz_add_cold(acc, s);
         if (w > 0)
             for (uint32_t k = 0; k < wbits; k++)
-                if (!xyzz_is_inf(acc)) xyzz_double(acc, acc);
+                if (!xyzz_is_inf(acc)) { xyzz_t<F> a = acc; xyzz_double(acc, a); }
     }
     jac_t<F> j;
     if (xyzz_is_inf(acc)) jac_set_inf(j);
