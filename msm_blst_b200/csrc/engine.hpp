@@ -47,7 +47,7 @@ struct Ctx {
     // workspace (grow-only)
     DevBuf scalars, keys, vals, sorted, count, packed, scanned, tile_sums, seg_start, item_start, cursor,
         item_begin, item_cnt, order, len_hist, len_start, len_cursor, partial, chunk_a, chunk_b, result,
-        flat, signs, pidx;
+        flat, signs, pidx, heavy;
     void *h_result = nullptr;  // pinned staging for the result
 
     // timing

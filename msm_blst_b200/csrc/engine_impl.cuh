@@ -47,7 +47,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         ensure(c, c->sorted, m * 4) || ensure(c, c->item_begin, max_items * 4) || ensure(c, c->item_cnt, max_items * 4) ||
         ensure(c, c->order, max_items * 4) || ensure(c, c->len_hist, (item_len + 1) * 4) ||
         ensure(c, c->len_start, (item_len + 1) * 4) || ensure(c, c->len_cursor, (item_len + 1) * 4) ||
-        ensure(c, c->partial, max_items * sizeof(xyzz_t<F>)) || ensure(c, c->result, sizeof(jac_t<F>) + sizeof(aff_t<F>)))
+        ensure(c, c->partial, max_items * sizeof(xyzz_t<F>)) || ensure(c, c->heavy, (m / item_len + 2) * 4) || ensure(c, c->result, sizeof(jac_t<F>) + sizeof(aff_t<F>)))
         return MSMB200_ECUDA;
 
     uint32_t *count = (uint32_t *)c->count.p;
@@ -63,9 +63,10 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
                                                        (const uint32_t *)c->seg_start.p, (uint32_t *)c->cursor.p,
                                                        (uint32_t *)c->sorted.p);
     MSM_CUDA(c, cudaMemsetAsync(c->len_hist.p, 0, (item_len + 1) * 4, st));
+    MSM_CUDA(c, cudaMemsetAsync(c->heavy.p, 0, 4, st));
     itemize_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, (const uint32_t *)c->seg_start.p, (const uint32_t *)c->item_start.p,
                                                         nb, item_len, (uint32_t *)c->item_begin.p, (uint32_t *)c->item_cnt.p,
-                                                        (uint32_t *)c->len_hist.p);
+                                                        (uint32_t *)c->len_hist.p, (uint32_t *)c->heavy.p);
     len_scan_kernel<<<1, 32, 0, st>>>((const uint32_t *)c->len_hist.p, (uint32_t *)c->len_start.p, (uint32_t *)c->len_cursor.p, item_len);
     const uint64_t *totals = (const uint64_t *)c->tile_sums.p + ntiles;
     order_items_kernel<<<blocks_for(max_items, 256), 256, 0, st>>>((const uint32_t *)c->item_cnt.p, totals,
@@ -77,8 +78,13 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     accumulate_kernel<F><<<blocks_for(max_items, 128), 128, 0, st>>>(d_table, (const uint32_t *)c->sorted.p,
                                                                      (const uint32_t *)c->item_begin.p, (const uint32_t *)c->item_cnt.p,
                                                                      (const uint32_t *)c->order.p, totals, (xyzz_t<F> *)c->partial.p);
-    combine_items_kernel<FC><<<blocks_for(nb, 128), 128, 0, st>>>(count, (const uint32_t *)c->item_start.p, nb, item_len,
-                                                                  (xyzz_t<FC> *)c->partial.p);
+    {
+        size_t smem = 128 * sizeof(xyzz_t<FC>);
+        MSM_CUDA(c, cudaFuncSetAttribute(combine_heavy_kernel<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        unsigned max_heavy = (unsigned)(m / item_len + 1);
+        combine_heavy_kernel<FC><<<max_heavy, 128, smem, st>>>(count, (const uint32_t *)c->item_start.p, (const uint32_t *)c->heavy.p, item_len,
+                                                              (xyzz_t<FC> *)c->partial.p);
+    }
     c->launches += 2;
     MSM_CUDA(c, cudaEventRecord(c->ev[3], st));
     // ---- reduce ----
@@ -99,13 +105,21 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     xyzz_t<F> *cur = (xyzz_t<F> *)c->chunk_a.p, *nxt = (xyzz_t<F> *)c->chunk_b.p;
     uint32_t per = cpw;
     const uint32_t nrows = 2 * L.nwindows;
-    while (per > 1) {
-        uint32_t r = per > 4096 ? 8 : 4;
+    while (per > 1024) {
+        uint32_t r = 8;
         uint32_t groups = (per + r - 1) / r;
         sum_groups_kernel<FC><<<blocks_for((size_t)groups * nrows, 128), 128, 0, st>>>((const xyzz_t<FC> *)cur, per, nrows, r, groups, (xyzz_t<FC> *)nxt);
         c->launches += 1;
         std::swap(cur, nxt);
         per = groups;
+    }
+    if (per > 1) {
+        size_t smem = 256 * sizeof(xyzz_t<FC>);
+        MSM_CUDA(c, cudaFuncSetAttribute(tree_tail_kernel<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tree_tail_kernel<FC><<<nrows, 256, smem, st>>>((const xyzz_t<FC> *)cur, per, (xyzz_t<FC> *)nxt);
+        c->launches += 1;
+        std::swap(cur, nxt);
+        per = 1;
     }
     MSM_CUDA(c, cudaEventRecord(c->ev[4], st));
     // ---- finalize ----

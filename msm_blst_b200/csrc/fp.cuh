@@ -218,27 +218,85 @@ __device__ __forceinline__ void fp_from_mont(fp_t &r, const fp_t &a) {
     fp_mul(r, a, one);
 }
 
-// a^(p-2) (Fermat), square-and-multiply over the fixed exponent; 0 -> 0 like reference reciprocal_fp
-// (src/recip.c:58-92). Used once per MSM (to_affine) and once per batch in the batch-affine adder.
+// RR = 2^768 mod p (reference src/consts.c:22-26), 32-bit limbs
+__device__ __forceinline__ uint32_t fp_rr_limb(int i) {
+    switch (i) {
+    case 0: return 0x1c341746u; case 1: return 0xf4df1f34u; case 2: return 0x09d104f1u; case 3: return 0x0a76e6a6u;
+    case 4: return 0x4c95b6d5u; case 5: return 0x8de5476cu; case 6: return 0x939d83c0u; case 7: return 0x67eb88a9u;
+    case 8: return 0xb519952du; case 9: return 0x9a793e85u; case 10: return 0x92cae3aau; default: return 0x11988fe5u;
+    }
+}
+// 1/a in Montgomery form, 0 -> 0 like the reference's reciprocal_fp (src/recip.c:58-92). Binary extended GCD
+// on the plain integer A = a*R mod p (not constant time: the MSM path is not, src/ec_ops.h:634): ~760 shift /
+// subtract steps of 12-limb carry chains instead of the ~570 dependent Montgomery multiplications of Fermat's
+// a^(p-2). The result A^-1 is brought back with two multiplications by RR: A^-1 * R^2 = (a^-1) * R.
 static __device__ __noinline__ void fp_inv(fp_t &r, const fp_t &a) {
-    // p - 2, 32-bit limbs
-    const uint32_t e[12] = {FP_P0 - 2u, FP_P1, FP_P2, FP_P3, FP_P4, FP_P5, FP_P6, FP_P7, FP_P8, FP_P9, FP_P10, FP_P11};
-    fp_t acc;
-    fp_set_one(acc);
-    // top limb 0x1a0111ea has 29 significant bits
-#pragma unroll 1
-    for (int i = 380; i >= 0; i--) {
-        bool bit = (e[i >> 5] >> (i & 31)) & 1;
-        // one multiplier instance: pass 0 squares, pass 1 (only when the exponent bit is set) multiplies by a
-#pragma unroll 1
-        for (int pass = 0; pass < (bit ? 2 : 1); pass++) {
-            fp_t y;
+    uint32_t u[12], v[12], b[12], c[12];
+    if (fp_is_zero(a)) { fp_set_zero(r); return; }
 #pragma unroll
-            for (int k = 0; k < 12; k++) y.l[k] = pass ? a.l[k] : acc.l[k];
-            fp_mul(acc, acc, y);
+    for (int i = 0; i < 12; i++) { u[i] = a.l[i]; v[i] = fp_p_limb(i); b[i] = 0; c[i] = 0; }
+    b[0] = 1;
+    auto shr1 = [](uint32_t *x) {
+#pragma unroll
+        for (int i = 0; i < 11; i++) x[i] = __funnelshift_r(x[i], x[i + 1], 1);
+        x[11] >>= 1;
+    };
+    auto add_p = [](uint32_t *x) {
+        x[0] = add_cc(x[0], fp_p_limb(0));
+#pragma unroll
+        for (int i = 1; i < 11; i++) x[i] = addc_cc(x[i], fp_p_limb(i));
+        x[11] = addc(x[11], fp_p_limb(11));
+    };
+    auto is_one = [](const uint32_t *x) {
+        uint32_t acc = x[0] ^ 1u;
+#pragma unroll
+        for (int i = 1; i < 12; i++) acc |= x[i];
+        return acc == 0;
+    };
+    // x -= y, returns borrow mask
+    auto sub = [](uint32_t *x, const uint32_t *y) {
+        x[0] = sub_cc(x[0], y[0]);
+#pragma unroll
+        for (int i = 1; i < 12; i++) x[i] = subc_cc(x[i], y[i]);
+        return subc(0, 0);
+    };
+    auto less = [](const uint32_t *x, const uint32_t *y) {  // x < y
+        uint32_t t = sub_cc(x[0], y[0]);
+#pragma unroll
+        for (int i = 1; i < 12; i++) t = subc_cc(x[i], y[i]);
+        (void)t;
+        return subc(0, 0) != 0;
+    };
+    bool res_is_b;
+#pragma unroll 1
+    for (;;) {
+#pragma unroll 1
+        while (!(u[0] & 1u)) {
+            shr1(u);
+            if (b[0] & 1u) add_p(b);
+            shr1(b);
+        }
+        if (is_one(u)) { res_is_b = true; break; }
+#pragma unroll 1
+        while (!(v[0] & 1u)) {
+            shr1(v);
+            if (c[0] & 1u) add_p(c);
+            shr1(c);
+        }
+        if (is_one(v)) { res_is_b = false; break; }
+        if (!less(u, v)) {
+            sub(u, v);
+            if (sub(b, c)) add_p(b);
+        } else {
+            sub(v, u);
+            if (sub(c, b)) add_p(c);
         }
     }
-    r = acc;
+    fp_t x, rr;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { x.l[i] = res_is_b ? b[i] : c[i]; rr.l[i] = fp_rr_limb(i); }
+    fp_mul(x, x, rr);
+    fp_mul(r, x, rr);
 }
 
 }  // namespace msmb200

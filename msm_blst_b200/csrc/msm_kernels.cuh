@@ -283,11 +283,12 @@ static __global__ void scatter_kernel(const uint32_t *__restrict__ keys, const u
 static __global__ void itemize_kernel(const uint32_t *__restrict__ count, const uint32_t *__restrict__ seg_start,
                                const uint32_t *__restrict__ item_start, size_t nb, uint32_t item_len,
                                uint32_t *__restrict__ item_begin, uint32_t *__restrict__ item_cnt,
-                               uint32_t *__restrict__ len_hist) {
+                               uint32_t *__restrict__ len_hist, uint32_t *__restrict__ heavy /* [0] = count, then bucket ids */) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     uint32_t c = count[b];
     if (c == 0) return;
+    if (c > item_len) heavy[1 + atomicAdd(&heavy[0], 1u)] = (uint32_t)b;
     uint32_t s = seg_start[b], it = item_start[b];
     for (uint32_t off = 0; off < c; off += item_len, it++) {
         uint32_t len = min(item_len, c - off);
@@ -355,21 +356,38 @@ static __global__ void __launch_bounds__(128) accumulate_kernel(const aff_t<F> *
     }
     partial[it] = acc;
 }
-// buckets that were split into several items: fold the partials into the first one
+template <class F> __device__ __noinline__ void xyzz_add_cold(xyzz_t<F> &acc, const xyzz_t<F> &q);
+template <class F> __device__ __forceinline__ void load_xyzz(xyzz_t<F> &p, const xyzz_t<F> *src_);
+// Buckets that were split into several work items ("heavy": more than item_len entries, e.g. the top window of
+// blst's Pippenger or adversarially equal scalars): one BLOCK per heavy bucket folds its partials into the first
+// one with a strided pass and a shared-memory tree, so the dependent chain is items/blockDim + log2(blockDim).
 template <class F>
-static __global__ void __launch_bounds__(128) combine_items_kernel(const uint32_t *__restrict__ count, const uint32_t *__restrict__ item_start,
-                                                            size_t nb, uint32_t item_len, xyzz_t<F> *__restrict__ partial) {
-    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    uint32_t c = count[b];
-    if (c <= item_len) return;
-    uint32_t items = (c + item_len - 1) / item_len, it = item_start[b];
-    xyzz_t<F> acc = partial[it];
-    for (uint32_t k = 1; k < items; k++) {
-        xyzz_t<F> q = partial[it + k];
-        xyzz_add(acc, q);
+static __global__ void __launch_bounds__(128) combine_heavy_kernel(const uint32_t *__restrict__ count, const uint32_t *__restrict__ item_start,
+                                                                   const uint32_t *__restrict__ heavy, uint32_t item_len,
+                                                                   xyzz_t<F> *__restrict__ partial) {
+    extern __shared__ uint4 tree_smem_raw[];
+    xyzz_t<F> *sm = reinterpret_cast<xyzz_t<F> *>(tree_smem_raw);
+    if (blockIdx.x >= heavy[0]) return;
+    const uint32_t b = heavy[1 + blockIdx.x], t = threadIdx.x;
+    const uint32_t c = count[b], items = (c + item_len - 1) / item_len, it = item_start[b];
+    xyzz_t<F> acc;
+    xyzz_set_inf(acc);
+    for (uint32_t k = t; k < items; k += blockDim.x) {
+        xyzz_t<F> q;
+        load_xyzz(q, partial + it + k);
+        xyzz_add_cold(acc, q);
     }
-    partial[it] = acc;
+    sm[t] = acc;
+    __syncthreads();
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (t < s) {
+            xyzz_t<F> a = sm[t], q = sm[t + s];
+            xyzz_add_cold(a, q);
+            sm[t] = a;
+        }
+        __syncthreads();
+    }
+    if (t == 0) partial[it] = sm[0];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -474,6 +492,33 @@ static __global__ void __launch_bounds__(128) sum_groups_kernel(const xyzz_t<F> 
         xyzz_add(acc, q);
     }
     out[t] = acc;
+}
+
+// last levels of the tree in ONE launch: block `row` sums in[row*per .. +per) (per <= a few thousand) with a
+// shared-memory tree: log2(blockDim) dependent additions instead of one kernel launch per level
+template <class F>
+static __global__ void __launch_bounds__(256) tree_tail_kernel(const xyzz_t<F> *__restrict__ in, uint32_t per, xyzz_t<F> *__restrict__ out) {
+    extern __shared__ uint4 tree_smem_raw[];
+    xyzz_t<F> *sm = reinterpret_cast<xyzz_t<F> *>(tree_smem_raw);
+    const uint32_t row = blockIdx.x, t = threadIdx.x;
+    xyzz_t<F> acc;
+    xyzz_set_inf(acc);
+    for (uint32_t k = t; k < per; k += blockDim.x) {
+        xyzz_t<F> q;
+        load_xyzz(q, in + (size_t)row * per + k);
+        xyzz_add_cold(acc, q);
+    }
+    sm[t] = acc;
+    __syncthreads();
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (t < s) {
+            xyzz_t<F> a = sm[t], b = sm[t + s];
+            xyzz_add_cold(a, b);
+            sm[t] = a;
+        }
+        __syncthreads();
+    }
+    if (t == 0) out[row] = sm[0];
 }
 
 // ------------------------------------------------------------------------------------------------
