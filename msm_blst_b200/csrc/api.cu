@@ -43,6 +43,7 @@ std::vector<int> build_chunk_first(const int *values, size_t count, uint32_t vsp
     return cf;
 }
 uint32_t pick_vspan_host(size_t max_value, uint32_t nwindows) {
+    if (const char *e = getenv("MSMB200_VSPAN")) return (uint32_t)atoi(e);
     uint32_t v = 64;
     while (v > 8 && (max_value / v) * nwindows < 32768) v >>= 1;
     return v;

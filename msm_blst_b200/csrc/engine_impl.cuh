@@ -3,6 +3,7 @@
 // groups compile in parallel). All work is enqueued on the context's stream; nothing here computes on the CPU.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include "engine.hpp"
 #include "msm_kernels.cuh"
 
@@ -24,6 +25,7 @@ struct Layout {
 
 // value span of a reduction chunk: aim at ~32 K chunks in total, between 8 and 64 values per chunk
 static inline uint32_t pick_vspan(size_t max_value, uint32_t nwindows) {
+    if (const char *e = getenv("MSMB200_VSPAN")) return (uint32_t)atoi(e);
     uint32_t v = 64;
     while (v > 8 && (max_value / v) * nwindows < 32768) v >>= 1;
     return v;
@@ -81,7 +83,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     {
         size_t smem = 128 * sizeof(xyzz_t<FC>);
         MSM_CUDA(c, cudaFuncSetAttribute(combine_heavy_kernel<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        unsigned max_heavy = (unsigned)(m / item_len + 1);
+        unsigned max_heavy = (unsigned)std::min<size_t>(m / item_len + 1, 592);
         combine_heavy_kernel<FC><<<max_heavy, 128, smem, st>>>(count, (const uint32_t *)c->item_start.p, (const uint32_t *)c->heavy.p, item_len,
                                                               (xyzz_t<FC> *)c->partial.p);
     }
@@ -93,11 +95,11 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     if (ensure(c, c->chunk_a, 2 * nchunks * sizeof(xyzz_t<F>)) || ensure(c, c->chunk_b, (2 * ((size_t)cpw / 4 + 2) * L.nwindows + 2) * sizeof(xyzz_t<F>)))
         return MSMB200_ECUDA;
     if (L.bucket_vals)
-        reduce_chunks_kernel<F, false><<<blocks_for(nchunks, 128), 128, 0, st>>>(
+        reduce_chunks_kernel<F, false><<<blocks_for(nchunks, 64), 64, 0, st>>>(
             (const xyzz_t<F> *)c->partial.p, count, (const uint32_t *)c->item_start.p, L.bucket_vals, L.chunk_first, L.nbw, L.nwindows,
             L.vspan, cpw, L.d_max, (xyzz_t<F> *)c->chunk_a.p);
     else
-        reduce_chunks_kernel<F, true><<<blocks_for(nchunks, 128), 128, 0, st>>>(
+        reduce_chunks_kernel<F, true><<<blocks_for(nchunks, 64), 64, 0, st>>>(
             (const xyzz_t<F> *)c->partial.p, count, (const uint32_t *)c->item_start.p, nullptr, nullptr, L.nbw, L.nwindows, L.vspan, cpw, 1,
             (xyzz_t<F> *)c->chunk_a.p);
     c->launches += 1;

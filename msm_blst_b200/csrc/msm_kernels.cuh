@@ -367,8 +367,8 @@ static __global__ void __launch_bounds__(128) combine_heavy_kernel(const uint32_
                                                                    xyzz_t<F> *__restrict__ partial) {
     extern __shared__ uint4 tree_smem_raw[];
     xyzz_t<F> *sm = reinterpret_cast<xyzz_t<F> *>(tree_smem_raw);
-    if (blockIdx.x >= heavy[0]) return;
-    const uint32_t b = heavy[1 + blockIdx.x], t = threadIdx.x;
+    for (uint32_t hidx = blockIdx.x; hidx < heavy[0]; hidx += gridDim.x) {
+    const uint32_t b = heavy[1 + hidx], t = threadIdx.x;
     const uint32_t c = count[b], items = (c + item_len - 1) / item_len, it = item_start[b];
     xyzz_t<F> acc;
     xyzz_set_inf(acc);
@@ -388,6 +388,8 @@ static __global__ void __launch_bounds__(128) combine_heavy_kernel(const uint32_
         __syncthreads();
     }
     if (t == 0) partial[it] = sm[0];
+    __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -411,7 +413,7 @@ __device__ __forceinline__ void load_xyzz(xyzz_t<F> &p, const xyzz_t<F> *src_) {
     for (int k = 0; k < (int)(sizeof(xyzz_t<F>) / 16); k++) dst[k] = src[k];
 }
 template <class F, bool DENSE>
-static __global__ void __launch_bounds__(128) reduce_chunks_kernel(const xyzz_t<F> *__restrict__ partial, const uint32_t *__restrict__ count,
+static __global__ void __launch_bounds__(64) reduce_chunks_kernel(const xyzz_t<F> *__restrict__ partial, const uint32_t *__restrict__ count,
                                                                    const uint32_t *__restrict__ item_start, const int *__restrict__ bucket_vals,
                                                                    const int *__restrict__ chunk_first, uint32_t nbw, uint32_t nwindows,
                                                                    uint32_t vspan, uint32_t chunks_per_window, int d_max,
