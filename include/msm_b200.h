@@ -75,6 +75,11 @@ const char *msmb200_last_error(const msmb200_ctx *ctx); /* ctx may be NULL: last
 /* Use the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream). */
 int msmb200_set_stream(msmb200_ctx *ctx, void *cuda_stream);
 
+/* Bucket-accumulation algorithm: 0 = library default, 1 = XYZZ mixed additions, one thread per work item (the
+ * reference's xyzz_dadd_affine loop, src/multi_scalar.c:437-461), 2 = batch-affine pairwise rounds sharing one
+ * inversion per batch (the reference's bulk_addition.c:51-143 analogue). Results are identical. */
+int msmb200_set_accumulator(msmb200_ctx *ctx, int mode);
+
 /* FIX_POINTS_LIST (main_p1.cpp:47): upload caller's affine points (host memory, npoints entries). */
 int msmb200_set_points(msmb200_ctx *ctx, const void *points_affine_host);
 /* init_fix_point_list (main_p1.cpp:52-66): P_i = 2^(first+i+1) * G computed on the device. */

@@ -67,6 +67,7 @@ def lib():
         L.msmb200_last_error.restype = C.c_char_p
         L.msmb200_set_stream.argtypes = [vp, vp]
         L.msmb200_set_points.argtypes = [vp, vp]
+        L.msmb200_set_accumulator.argtypes = [vp, ci]
         L.msmb200_generate_fix_points.argtypes = [vp, sz]
         L.msmb200_table_build_ches.argtypes = [vp]
         L.msmb200_table_build_bgmw95.argtypes = [vp]
@@ -206,6 +207,10 @@ class MsmContext:
 
     def set_stream(self, cuda_stream):
         self._ck(lib().msmb200_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_accumulator(self, mode):
+        """0 default, 1 XYZZ work items, 2 batch-affine rounds (identical results)."""
+        self._ck(lib().msmb200_set_accumulator(self._h, int(mode)))
 
     # -- reference driver mirror --
     def init_fix_point_list(self):

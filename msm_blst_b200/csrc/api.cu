@@ -67,7 +67,8 @@ static void ctx_free(Ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->scalars, &c->keys, &c->vals, &c->sorted, &c->count, &c->packed, &c->scanned, &c->tile_sums, &c->seg_start,
                       &c->item_start, &c->cursor, &c->item_begin, &c->item_cnt, &c->order, &c->len_hist, &c->len_start, &c->len_cursor,
-                      &c->partial, &c->chunk_a, &c->chunk_b, &c->result, &c->flat, &c->signs, &c->pidx, &c->heavy};
+                      &c->partial, &c->chunk_a, &c->chunk_b, &c->result, &c->flat, &c->signs, &c->pidx, &c->heavy, &c->bucket_of0, &c->bo_a, &c->bo_b,
+                      &c->pts_a, &c->pts_b, &c->base_a, &c->base_b, &c->tile_sums2, &c->maxcount};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     void *ptrs[] = {c->d_bucket_vals, c->d_v2i, c->d_dtab, c->d_chunk_first, c->d_points, c->d_table_ches, c->d_table_bgmw};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -196,6 +197,11 @@ int msmb200_set_stream(msmb200_ctx *ctx, void *cuda_stream) {
     return MSMB200_OK;
 }
 
+int msmb200_set_accumulator(msmb200_ctx *ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 2) return MSMB200_EINVAL;
+    C(ctx)->accum_mode = mode;
+    return MSMB200_OK;
+}
 int msmb200_set_points(msmb200_ctx *ctx, const void *points_affine_host) {
     if (!ctx || !points_affine_host) return MSMB200_EINVAL;
     Ctx *c = C(ctx);

@@ -11,6 +11,10 @@ namespace msmb200 {
 
 static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
+#ifndef MSMB200_DEFAULT_ACCUM
+#define MSMB200_DEFAULT_ACCUM 1
+#endif
+
 struct Layout {
     size_t m;            // number of (key, val) entries
     uint32_t nbw;        // buckets per window (local index 0 unused)
@@ -46,7 +50,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
 
     if (ensure(c, c->packed, nb * 8) || ensure(c, c->scanned, nb * 8) || ensure(c, c->tile_sums, (ntiles + 1) * 8) ||
         ensure(c, c->seg_start, nb * 4) || ensure(c, c->item_start, nb * 4) || ensure(c, c->cursor, nb * 4) ||
-        ensure(c, c->sorted, m * 4) || ensure(c, c->item_begin, max_items * 4) || ensure(c, c->item_cnt, max_items * 4) ||
+        ensure(c, c->sorted, (m + nb + 2) * 4) || ensure(c, c->maxcount, 16) || ensure(c, c->item_begin, max_items * 4) || ensure(c, c->item_cnt, max_items * 4) ||
         ensure(c, c->order, max_items * 4) || ensure(c, c->len_hist, (item_len + 1) * 4) ||
         ensure(c, c->len_start, (item_len + 1) * 4) || ensure(c, c->len_cursor, (item_len + 1) * 4) ||
         ensure(c, c->partial, max_items * sizeof(xyzz_t<F>)) || ensure(c, c->heavy, (m / item_len + 2) * 4) || ensure(c, c->result, sizeof(jac_t<F>) + sizeof(aff_t<F>)))
@@ -54,7 +58,13 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
 
     uint32_t *count = (uint32_t *)c->count.p;
     // ---- sort by bucket ----
-    prep_counts_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, (uint64_t *)c->packed.p, nb, item_len);
+    int mode = c->accum_mode;
+    if (const char *e = getenv("MSMB200_ACCUM")) mode = atoi(e);
+    if (mode == 0) mode = MSMB200_DEFAULT_ACCUM;
+    const bool batch_affine = mode == 2;
+    if (batch_affine && ensure(c, c->bucket_of0, (m + nb + 2) * 4)) return MSMB200_ECUDA;
+    MSM_CUDA(c, cudaMemsetAsync(c->maxcount.p, 0, 4, st));
+    prep_counts_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, (uint64_t *)c->packed.p, nb, item_len, (uint32_t *)c->maxcount.p);
     scan_tiles_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>((const uint64_t *)c->packed.p, (uint64_t *)c->scanned.p,
                                                                    (uint64_t *)c->tile_sums.p, nb);
     scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>((uint64_t *)c->tile_sums.p, ntiles);
@@ -63,45 +73,95 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
                                                             (uint32_t *)c->cursor.p, nb);
     scatter_kernel<<<blocks_for(m, 256), 256, 0, st>>>((const uint32_t *)c->keys.p, (const uint32_t *)c->vals.p, m,
                                                        (const uint32_t *)c->seg_start.p, (uint32_t *)c->cursor.p,
-                                                       (uint32_t *)c->sorted.p);
-    MSM_CUDA(c, cudaMemsetAsync(c->len_hist.p, 0, (item_len + 1) * 4, st));
-    MSM_CUDA(c, cudaMemsetAsync(c->heavy.p, 0, 4, st));
-    itemize_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, (const uint32_t *)c->seg_start.p, (const uint32_t *)c->item_start.p,
-                                                        nb, item_len, (uint32_t *)c->item_begin.p, (uint32_t *)c->item_cnt.p,
-                                                        (uint32_t *)c->len_hist.p, (uint32_t *)c->heavy.p);
-    len_scan_kernel<<<1, 32, 0, st>>>((const uint32_t *)c->len_hist.p, (uint32_t *)c->len_start.p, (uint32_t *)c->len_cursor.p, item_len);
+                                                       (uint32_t *)c->sorted.p, batch_affine ? (uint32_t *)c->bucket_of0.p : nullptr);
     const uint64_t *totals = (const uint64_t *)c->tile_sums.p + ntiles;
-    order_items_kernel<<<blocks_for(max_items, 256), 256, 0, st>>>((const uint32_t *)c->item_cnt.p, totals,
-                                                                   (const uint32_t *)c->len_start.p, (uint32_t *)c->len_cursor.p,
-                                                                   (uint32_t *)c->order.p);
-    c->launches += 8;
-    MSM_CUDA(c, cudaEventRecord(c->ev[2], st));
-    // ---- accumulate ----
-    accumulate_kernel<F><<<blocks_for(max_items, 128), 128, 0, st>>>(d_table, (const uint32_t *)c->sorted.p,
-                                                                     (const uint32_t *)c->item_begin.p, (const uint32_t *)c->item_cnt.p,
-                                                                     (const uint32_t *)c->order.p, totals, (xyzz_t<F> *)c->partial.p);
-    {
-        size_t smem = 128 * sizeof(xyzz_t<FC>);
-        MSM_CUDA(c, cudaFuncSetAttribute(combine_heavy_kernel<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        unsigned max_heavy = (unsigned)std::min<size_t>(m / item_len + 1, 592);
-        combine_heavy_kernel<FC><<<max_heavy, 128, smem, st>>>(count, (const uint32_t *)c->item_start.p, (const uint32_t *)c->heavy.p, item_len,
-                                                              (xyzz_t<FC> *)c->partial.p);
+    const void *bucket_points = nullptr;      // what the reduction reads: XYZZ partials or affine points
+    const uint32_t *bucket_point_index = nullptr;
+    if (!batch_affine) {
+        MSM_CUDA(c, cudaMemsetAsync(c->len_hist.p, 0, (item_len + 1) * 4, st));
+        MSM_CUDA(c, cudaMemsetAsync(c->heavy.p, 0, 4, st));
+        itemize_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, (const uint32_t *)c->seg_start.p, (const uint32_t *)c->item_start.p,
+                                                            nb, item_len, (uint32_t *)c->item_begin.p, (uint32_t *)c->item_cnt.p,
+                                                            (uint32_t *)c->len_hist.p, (uint32_t *)c->heavy.p);
+        len_scan_kernel<<<1, 32, 0, st>>>((const uint32_t *)c->len_hist.p, (uint32_t *)c->len_start.p, (uint32_t *)c->len_cursor.p, item_len);
+        order_items_kernel<<<blocks_for(max_items, 256), 256, 0, st>>>((const uint32_t *)c->item_cnt.p, totals,
+                                                                       (const uint32_t *)c->len_start.p, (uint32_t *)c->len_cursor.p,
+                                                                       (uint32_t *)c->order.p);
+        c->launches += 8;
+        MSM_CUDA(c, cudaEventRecord(c->ev[2], st));
+        // ---- accumulate: XYZZ mixed additions, one thread per work item ----
+        accumulate_kernel<F><<<blocks_for(max_items, 128), 128, 0, st>>>(d_table, (const uint32_t *)c->sorted.p,
+                                                                         (const uint32_t *)c->item_begin.p, (const uint32_t *)c->item_cnt.p,
+                                                                         (const uint32_t *)c->order.p, totals, (xyzz_t<F> *)c->partial.p);
+        {
+            size_t smem = 128 * sizeof(xyzz_t<FC>);
+            MSM_CUDA(c, cudaFuncSetAttribute(combine_heavy_kernel<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            unsigned max_heavy = (unsigned)std::min<size_t>(m / item_len + 1, 592);
+            combine_heavy_kernel<FC><<<max_heavy, 128, smem, st>>>(count, (const uint32_t *)c->item_start.p, (const uint32_t *)c->heavy.p, item_len,
+                                                                  (xyzz_t<FC> *)c->partial.p);
+        }
+        c->launches += 2;
+        bucket_points = c->partial.p;
+        bucket_point_index = (const uint32_t *)c->item_start.p;
+    } else {
+        c->launches += 5;
+        MSM_CUDA(c, cudaEventRecord(c->ev[2], st));
+        // ---- accumulate: batch-affine pairwise rounds ----
+        uint32_t max_count = 0;
+        MSM_CUDA(c, cudaMemcpyAsync(&max_count, c->maxcount.p, 4, cudaMemcpyDeviceToHost, st));
+        MSM_CUDA(c, cudaStreamSynchronize(st));
+        int rounds = 1;
+        while (((size_t)1 << rounds) < max_count) rounds++;
+        constexpr int BATCH = sizeof(F) > 48 ? 8 : 16;
+        const size_t out_cap = m / 2 + 2 * nb + 4;
+        if (ensure(c, c->pts_a, out_cap * sizeof(aff_t<F>)) || ensure(c, c->pts_b, (out_cap / 2 + 2 * nb + 4) * sizeof(aff_t<F>)) ||
+            ensure(c, c->bo_a, out_cap * 4) || ensure(c, c->bo_b, (out_cap / 2 + 2 * nb + 4) * 4) || ensure(c, c->base_a, nb * 4) ||
+            ensure(c, c->base_b, nb * 4) || ensure(c, c->tile_sums2, (ntiles + 1) * 8))
+            return MSMB200_ECUDA;
+        const aff_t<F> *in_pts = nullptr;
+        const uint32_t *bo_in = (const uint32_t *)c->bucket_of0.p, *base_in = (const uint32_t *)c->seg_start.p;
+        const uint64_t *tot_in = totals;
+        aff_t<F> *pts[2] = {(aff_t<F> *)c->pts_a.p, (aff_t<F> *)c->pts_b.p};
+        uint32_t *bo[2] = {(uint32_t *)c->bo_a.p, (uint32_t *)c->bo_b.p};
+        uint32_t *base[2] = {(uint32_t *)c->base_a.p, (uint32_t *)c->base_b.p};
+        uint64_t *ts[2] = {(uint64_t *)c->tile_sums2.p, (uint64_t *)c->tile_sums.p};
+        size_t bound_in = m + nb + 2;  // upper bound of the padded input length of the round
+        for (int r = 0; r < rounds; r++) {
+            const int o = r & 1;
+            ba_plan_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, (uint64_t *)c->packed.p, nb, r + 1);
+            scan_tiles_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>((const uint64_t *)c->packed.p, (uint64_t *)c->scanned.p, ts[o], nb);
+            scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(ts[o], ntiles);
+            ba_scan_finish_kernel<<<blocks_for(nb, 256), 256, 0, st>>>((const uint64_t *)c->scanned.p, ts[o], base[o], nb);
+            const size_t threads = (bound_in / 2 + BATCH - 1) / BATCH + 1;
+            if (r == 0)
+                ba_round_kernel<F, true, BATCH><<<blocks_for(threads, 128), 128, 0, st>>>(d_table, (const uint32_t *)c->sorted.p, nullptr, bo_in, base_in,
+                                                                                          count, r, tot_in, base[o], pts[o], bo[o]);
+            else
+                ba_round_kernel<F, false, BATCH><<<blocks_for(threads, 128), 128, 0, st>>>(d_table, nullptr, in_pts, bo_in, base_in, count, r, tot_in,
+                                                                                           base[o], pts[o], bo[o]);
+            c->launches += 5;
+            in_pts = pts[o];
+            bo_in = bo[o];
+            base_in = base[o];
+            tot_in = ts[o] + ntiles;
+            bound_in = bound_in / 2 + nb + 2;
+        }
+        bucket_points = in_pts;
+        bucket_point_index = base_in;
     }
-    c->launches += 2;
     MSM_CUDA(c, cudaEventRecord(c->ev[3], st));
     // ---- reduce ----
     const uint32_t cpw = L.nchunks;
     size_t nchunks = (size_t)cpw * L.nwindows;
     if (ensure(c, c->chunk_a, 2 * nchunks * sizeof(xyzz_t<F>)) || ensure(c, c->chunk_b, (2 * ((size_t)cpw / 4 + 2) * L.nwindows + 2) * sizeof(xyzz_t<F>)))
         return MSMB200_ECUDA;
-    if (L.bucket_vals)
-        reduce_chunks_kernel<F, false><<<blocks_for(nchunks, 64), 64, 0, st>>>(
-            (const xyzz_t<F> *)c->partial.p, count, (const uint32_t *)c->item_start.p, L.bucket_vals, L.chunk_first, L.nbw, L.nwindows,
-            L.vspan, cpw, L.d_max, (xyzz_t<F> *)c->chunk_a.p);
-    else
-        reduce_chunks_kernel<F, true><<<blocks_for(nchunks, 64), 64, 0, st>>>(
-            (const xyzz_t<F> *)c->partial.p, count, (const uint32_t *)c->item_start.p, nullptr, nullptr, L.nbw, L.nwindows, L.vspan, cpw, 1,
-            (xyzz_t<F> *)c->chunk_a.p);
+#define MSM_REDUCE_LAUNCH(DENSE_, AFF_)                                                                                             \
+    reduce_chunks_kernel<F, DENSE_, AFF_><<<blocks_for(nchunks, 64), 64, 0, st>>>(                                                  \
+        bucket_points, count, bucket_point_index, L.bucket_vals, L.chunk_first, L.nbw, L.nwindows, L.vspan, cpw, L.bucket_vals ? L.d_max : 1, \
+        (xyzz_t<F> *)c->chunk_a.p)
+    if (L.bucket_vals) { if (batch_affine) MSM_REDUCE_LAUNCH(false, true); else MSM_REDUCE_LAUNCH(false, false); }
+    else { if (batch_affine) MSM_REDUCE_LAUNCH(true, true); else MSM_REDUCE_LAUNCH(true, false); }
+#undef MSM_REDUCE_LAUNCH
     c->launches += 1;
     // tree of sums over the 2 rows of every window
     xyzz_t<F> *cur = (xyzz_t<F> *)c->chunk_a.p, *nxt = (xyzz_t<F> *)c->chunk_b.p;

@@ -200,12 +200,17 @@ constexpr int SCAN_ITEMS = 8;  // per thread
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 // packs (count, nitems) into one u64 so one scan yields segment starts and item starts
-static __global__ void prep_counts_kernel(const uint32_t *__restrict__ count, uint64_t *__restrict__ packed, size_t nb, uint32_t item_len) {
+// Segments are padded to an even length so that the batch-affine rounds can pair elements (2s, 2s+1) without
+// straddling buckets. Also records the largest bucket (number of pairwise rounds needed).
+static __global__ void prep_counts_kernel(const uint32_t *__restrict__ count, uint64_t *__restrict__ packed, size_t nb, uint32_t item_len,
+                                          uint32_t *__restrict__ max_count) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c = b < nb ? count[b] : 0;
+    uint32_t wmax = __reduce_max_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && wmax) atomicMax(max_count, wmax);
     if (b >= nb) return;
-    uint32_t c = count[b];
     uint32_t items = (c + item_len - 1) / item_len;
-    packed[b] = (uint64_t)c | ((uint64_t)items << 32);
+    packed[b] = (uint64_t)(c + (c & 1u)) | ((uint64_t)items << 32);
 }
 __device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t *total) {
     __shared__ uint64_t warp_sums[SCAN_THREADS / 32];
@@ -270,13 +275,14 @@ static __global__ void scan_finish_kernel(const uint64_t *__restrict__ scanned, 
 }
 static __global__ void scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, size_t m,
                                const uint32_t *__restrict__ seg_start, uint32_t *__restrict__ cursor,
-                               uint32_t *__restrict__ sorted) {
+                               uint32_t *__restrict__ sorted, uint32_t *__restrict__ bucket_of /* may be null */) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m) return;
     uint32_t key = keys[k];
     if (key == KEY_SKIP) return;
     uint32_t pos = seg_start[key] + atomicAdd(&cursor[key], 1u);
     sorted[pos] = vals[k];
+    if (bucket_of) bucket_of[pos] = key;
 }
 // One work item = up to item_len consecutive entries of one bucket (a bucket with a huge count is split so
 // that no thread serialises more than item_len additions). Also builds the histogram of item lengths.
@@ -392,6 +398,145 @@ static __global__ void __launch_bounds__(128) combine_heavy_kernel(const uint32_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// [3'] bucket accumulation by BATCH-AFFINE pairwise rounds — the GPU analogue of the reference's
+// POINTonE1s_accumulate / HEAD / TAIL (src/bulk_addition.c:51-143): affine + affine -> affine with the
+// slope denominators of a whole batch inverted together by Montgomery's trick (5M+1S per addition plus the
+// shared inversion, :27), doubling folded into the same batch with denominator 2y (:63-74), P + (-P) and
+// infinity inputs resolved without arithmetic.
+// Round r turns every bucket's list of k = ceil(count / 2^r) points into ceil(k/2) points; lists sit at even
+// offsets (base_in), slot s pairs elements (2s, 2s+1) of one bucket. One thread handles BATCH consecutive slots:
+// forward pass (denominators, running product kept in local memory), ONE field inversion (binary GCD: ALU
+// pipe, not the saturated multiplier pipe), backward pass (slopes, results). Round 0 reads the table through
+// the sorted (index | sign) references, later rounds read the previous round's points.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ba_len(uint32_t count, int r) { return count ? ((count - 1u) >> r) + 1u : 0u; }
+
+static __global__ void ba_plan_kernel(const uint32_t *__restrict__ count, uint64_t *__restrict__ packed, size_t nb, int r_next) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t k = ba_len(count[b], r_next);
+    packed[b] = (uint64_t)(k + (k & 1u));
+}
+static __global__ void ba_scan_finish_kernel(const uint64_t *__restrict__ scanned, const uint64_t *__restrict__ tile_sums,
+                                             uint32_t *__restrict__ base_next, size_t nb) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    base_next[b] = (uint32_t)(scanned[b] + tile_sums[b / SCAN_TILE]);
+}
+enum { BA_NONE = 0, BA_ADD = 1, BA_DBL = 2, BA_COPY_P = 3, BA_COPY_Q = 4, BA_INF = 5 };
+
+template <class F, bool FIRST>
+__device__ __forceinline__ void ba_load(aff_t<F> &p, size_t e, const aff_t<F> *__restrict__ table, const uint32_t *__restrict__ sorted,
+                                        const aff_t<F> *__restrict__ in_pts) {
+    if (FIRST) {
+        uint32_t v = sorted[e];
+        load_affine(p, table, v & 0x7fffffffu);
+        f_cneg(p.y, p.y, (v >> 31) != 0);  // infinity (0,0) stays (0,0)
+    } else {
+        load_affine(p, in_pts, (uint32_t)e);
+    }
+}
+template <class F, bool FIRST, int BATCH>
+static __global__ void __launch_bounds__(128) ba_round_kernel(const aff_t<F> *__restrict__ table, const uint32_t *__restrict__ sorted,
+                                                              const aff_t<F> *__restrict__ in_pts, const uint32_t *__restrict__ bucket_of_in,
+                                                              const uint32_t *__restrict__ base_in, const uint32_t *__restrict__ count, int r,
+                                                              const uint64_t *__restrict__ total_in, const uint32_t *__restrict__ base_out,
+                                                              aff_t<F> *__restrict__ out_pts, uint32_t *__restrict__ bucket_of_out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t s0 = t * BATCH;
+    const size_t nslots = (size_t)((uint32_t)*total_in) >> 1;  // padded total (low half of the packed scan total) is even
+    if (s0 >= nslots) return;
+    F prefix[BATCH];
+    unsigned char tag[BATCH];
+    F run;
+    f_set_one(run);
+    // ---- forward: classify, collect denominators ----
+#pragma unroll 1
+    for (int j = 0; j < BATCH; j++) {
+        const size_t s = s0 + j;
+        unsigned char tg = BA_NONE;
+        if (s < nslots) {
+            const uint32_t b = bucket_of_in[2 * s];
+            const uint32_t i = (uint32_t)(2 * s) - base_in[b];
+            const uint32_t k = ba_len(count[b], r);
+            if (i + 1 < k) {
+                aff_t<F> P, Q;
+                ba_load<F, FIRST>(P, 2 * s, table, sorted, in_pts);
+                ba_load<F, FIRST>(Q, 2 * s + 1, table, sorted, in_pts);
+                F d;
+                if (aff_is_inf(P)) tg = BA_COPY_Q;
+                else if (aff_is_inf(Q)) tg = BA_COPY_P;
+                else {
+                    f_sub(d, Q.x, P.x);
+                    if (!f_is_zero(d)) tg = BA_ADD;
+                    else if (f_eq(P.y, Q.y) && !f_is_zero(P.y)) { tg = BA_DBL; f_dbl(d, P.y); }
+                    else tg = BA_INF;
+                }
+                if (tg == BA_ADD || tg == BA_DBL) {
+                    prefix[j] = run;
+                    f_mul(run, run, d);
+                }
+            } else if (i < k) {
+                tg = BA_COPY_P;
+            }
+        }
+        tag[j] = tg;
+    }
+    F inv;
+    f_inv(inv, run);
+    // ---- backward: slopes and results ----
+#pragma unroll 1
+    for (int j = BATCH - 1; j >= 0; j--) {
+        const unsigned char tg = tag[j];
+        if (tg == BA_NONE) continue;
+        const size_t s = s0 + j;
+        const uint32_t b = bucket_of_in[2 * s];
+        const uint32_t i = (uint32_t)(2 * s) - base_in[b];
+        const uint32_t o = base_out[b] + (i >> 1);
+        aff_t<F> P, R;
+        ba_load<F, FIRST>(P, 2 * s, table, sorted, in_pts);
+        if (tg == BA_COPY_P) {
+            R = P;
+        } else if (tg == BA_INF) {
+            f_set_zero(R.x);
+            f_set_zero(R.y);
+        } else {
+            aff_t<F> Q;
+            ba_load<F, FIRST>(Q, 2 * s + 1, table, sorted, in_pts);
+            if (tg == BA_COPY_Q) {
+                R = Q;
+            } else {
+                F d, dinv, lam, t1;
+                if (tg == BA_ADD) f_sub(d, Q.x, P.x);
+                else f_dbl(d, P.y);
+                f_mul(dinv, inv, prefix[j]);
+                f_mul(inv, inv, d);
+                if (tg == BA_ADD) {
+                    f_sub(t1, Q.y, P.y);
+                    f_mul(lam, t1, dinv);            // lambda = (y2 - y1) / (x2 - x1)
+                    f_sqr(t1, lam);
+                    f_sub(t1, t1, P.x);
+                    f_sub(R.x, t1, Q.x);             // x3 = lambda^2 - x1 - x2
+                } else {
+                    f_sqr(t1, P.x);
+                    f_mul3(t1, t1);
+                    f_mul(lam, t1, dinv);            // lambda = 3 x1^2 / (2 y1)
+                    f_sqr(t1, lam);
+                    f_sub(t1, t1, P.x);
+                    f_sub(R.x, t1, P.x);             // x3 = lambda^2 - 2 x1
+                }
+                f_sub(t1, P.x, R.x);
+                f_mul(t1, t1, lam);
+                f_sub(R.y, t1, P.y);                 // y3 = lambda (x1 - x3) - y1
+            }
+        }
+        out_pts[o] = R;
+        bucket_of_out[o] = b;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // [4] bucket reduction. Replaces POINTonE1_integrate_buckets_accumulation_d_CHES (src/multi_scalar.c:301-321)
 // and POINTonE1_integrate_buckets (:281-297) with the chunked form of SURVEY App. B.6: window `w` has nbw
@@ -412,8 +557,8 @@ __device__ __forceinline__ void load_xyzz(xyzz_t<F> &p, const xyzz_t<F> *src_) {
 #pragma unroll
     for (int k = 0; k < (int)(sizeof(xyzz_t<F>) / 16); k++) dst[k] = src[k];
 }
-template <class F, bool DENSE>
-static __global__ void __launch_bounds__(64) reduce_chunks_kernel(const xyzz_t<F> *__restrict__ partial, const uint32_t *__restrict__ count,
+template <class F, bool DENSE, bool AFFINE_IN>
+static __global__ void __launch_bounds__(64) reduce_chunks_kernel(const void *__restrict__ bucket_points, const uint32_t *__restrict__ count,
                                                                    const uint32_t *__restrict__ item_start, const int *__restrict__ bucket_vals,
                                                                    const int *__restrict__ chunk_first, uint32_t nbw, uint32_t nwindows,
                                                                    uint32_t vspan, uint32_t chunks_per_window, int d_max,
@@ -442,9 +587,16 @@ static __global__ void __launch_bounds__(64) reduce_chunks_kernel(const xyzz_t<F
         for (uint32_t l = hi; l-- > lo;) {
             size_t b = (size_t)w * nbw + l;
             if (count[b] != 0) {
-                xyzz_t<F> s;
-                load_xyzz(s, partial + item_start[b]);
-                xyzz_add(tmp, s);
+                // bucket sum: XYZZ partial of the bucket's first work item, or (batch-affine path) ONE affine point
+                if (AFFINE_IN) {
+                    aff_t<F> a;
+                    load_affine(a, (const aff_t<F> *)bucket_points, item_start[b]);
+                    xyzz_add_affine(tmp, a, false);
+                } else {
+                    xyzz_t<F> s;
+                    load_xyzz(s, (const xyzz_t<F> *)bucket_points + item_start[b]);
+                    xyzz_add(tmp, s);
+                }
             }
             if (DENSE) {
                 xyzz_add_cold(W, tmp);

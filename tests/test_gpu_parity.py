@@ -464,3 +464,51 @@ def test_reference_driver_runs_on_the_cuda_shims(M, group):
         pts.append(tuple(coords[: (2 if group == 1 else 4)]))
     assert pts[0] == pts[1] == pts[2] == pts[3], pts
     assert "0x0000000000000000 0000000000000000 0000000000000000 0000000000000000 0000000000000000 0000000000000000" not in pts[0][0]
+
+
+# ---------------------------------------------------------------- both bucket accumulators
+@pytest.mark.parametrize("group", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_accumulator_modes_agree(M, group, mode):
+    """mode 1 = XYZZ mixed additions per work item (xyzz_dadd_affine loop), mode 2 = batch-affine pairwise rounds
+    with one shared inversion per batch (bulk_addition.c analogue). Same bytes, including the inputs that force
+    P + P, P - P and infinity inside a batch (all-equal scalars, zero scalars, infinity table entries)."""
+    n = 1024
+    ctx = M.MsmContext(group, "10")
+    ctx.set_accumulator(mode)
+    ctx.init_fix_point_list()
+    ctx.init_pippenger_CHES_q_over_5()
+    ctx.init_pippenger_BGMW95()
+    rm1 = [((O.R_ORDER - 1) >> (64 * i)) & (2**64 - 1) for i in range(4)]
+    cases = [O.gen_scalars(50 + mode, n), np.repeat(O.gen_scalars(9, 1), n, axis=0), np.zeros((n, 4), dtype=np.uint64),
+             np.array([rm1] * n, dtype=np.uint64)]
+    mixed = O.gen_scalars(10, n)
+    mixed[::3] = 0
+    cases.append(mixed)
+    for sc in cases:
+        exp, _ = O.closed_form(group, sc)
+        for method in (1, 2, 3, 4):
+            assert (ctx.msm(method, sc) == exp).all(), (mode, method)
+    ctx.close()
+    # unstructured points with an infinity entry in the table
+    import json, os
+    gd = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))["pippenger_unstructured"][str(group)]
+    pts = np.frombuffer(bytes.fromhex(gd["points"]), dtype=np.uint8).copy()
+    sc = np.frombuffer(bytes.fromhex(gd["scalars"]), dtype=np.uint64).reshape(gd["n"], 4).copy()
+    ctx = M.MsmContext(group, "8", npoints=gd["n"])
+    ctx.set_accumulator(mode)
+    ctx.set_points(pts)
+    ctx.init_pippenger_CHES_q_over_5()
+    for method in (1, 4):
+        assert M.affine_serialize(group, ctx.msm(method, sc)).hex() == gd["result"]
+    ctx.close()
+
+
+def test_batch_affine_full_size_known_answer(M, golden):
+    ctx = M.MsmContext(1, "16")
+    ctx.set_accumulator(2)
+    ctx.init_fix_point_list()
+    ctx.init_pippenger_CHES_q_over_5()
+    sc = O.gen_scalars(1, ctx.n)
+    assert M.affine_serialize(1, ctx.msm(1, sc)).hex() == golden["kat_appc"]["g1_n16"]
+    ctx.close()
