@@ -42,9 +42,11 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     cudaStream_t st = c->stream;
     const size_t nb = (size_t)L.nbw * L.nwindows;
     const size_t m = L.m;
-    // work-item length: a few times the mean bucket load, bounded
+    // work-item length: long enough that a typical bucket is one item, short enough that there are at least
+    // ~8 items per resident thread (148 SMs x 384 threads) even when buckets are few and heavy
     size_t avg = std::max<size_t>(1, m / std::max<size_t>(1, nb));
     uint32_t item_len = (uint32_t)std::min<size_t>(1024, std::max<size_t>(128, 8 * avg));
+    if (nb < 148 * 384 * 2) item_len = (uint32_t)std::max<size_t>(32, std::min<size_t>(item_len, m / (148 * 384 * 8)));
     const size_t max_items = std::min(nb, m) + m / item_len + 1;
     const size_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
 
