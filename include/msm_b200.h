@@ -146,7 +146,8 @@ void msmb200_blst_p2_tile_pippenger_BGMW95(void *ret_jacobian, const void *const
 
 /* ---- building blocks exposed for parity tests (each is a batched CUDA kernel launch; host buffers) ---
  * field ops on n elements. field: 1 = Fp (48 B), 2 = Fp2 (96 B).
- * op: 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 5 mul_by_3, 6 inverse        (blst_fp_mul ... bindings/blst.h:108-137) */
+ * op: 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 5 mul_by_3, 6 inverse        (blst_fp_mul ... bindings/blst.h:108-137),
+ *     7 inverse through the warp-level Montgomery trick of the batch-affine accumulator */
 int msmb200_test_field_op(int device, int field, int op, const void *a, const void *b, void *out, size_t n);
 /* point ops on n elements, group 1|2. op: 0 jac add-or-double (blst_p1_add_or_double), 1 jac double,
  * 2 xyzz += affine with sign flags (blst_p1xyzz_dadd_affine), 3 xyzz += xyzz (blst_p1xyzz_dadd),

@@ -44,8 +44,9 @@ std::vector<int> build_chunk_first(const int *values, size_t count, uint32_t vsp
 }
 uint32_t pick_vspan_host(size_t max_value, uint32_t nwindows) {
     if (const char *e = getenv("MSMB200_VSPAN")) return (uint32_t)atoi(e);
-    uint32_t v = 64;
-    while (v > 8 && (max_value / v) * nwindows < 32768) v >>= 1;
+    // ~32 K chunks in total (measured optimum on B200: G1 n=2^21 -> 64, G2 n=2^18 -> 16), 8 <= v <= 64, power of two
+    uint32_t v = 8;
+    while (v < 64 && ((max_value + 1) * nwindows + v - 1) / v > 32768 + 1024) v <<= 1;
     return v;
 }
 
@@ -358,7 +359,7 @@ static int field_fn(const void *a, const void *b, const unsigned char *, void *o
     return group_ops_g1()->field_op(f->field, f->op, a, b, out, f->n);
 }
 int msmb200_test_field_op(int device, int field, int op, const void *a, const void *b, void *out, size_t n) {
-    if ((field != 1 && field != 2) || op < 0 || op > 6 || !a || !out || n == 0) return MSMB200_EINVAL;
+    if ((field != 1 && field != 2) || op < 0 || op > 7 || !a || !out || n == 0) return MSMB200_EINVAL;
     size_t eb = field == 1 ? 48 : 96;
     FieldArg arg{field, op, n};
     return with_device_buffers(device, a, n * eb, b, n * eb, nullptr, 0, out, n * eb, field_fn, &arg);

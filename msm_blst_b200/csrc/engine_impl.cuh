@@ -30,8 +30,9 @@ struct Layout {
 // value span of a reduction chunk: aim at ~32 K chunks in total, between 8 and 64 values per chunk
 static inline uint32_t pick_vspan(size_t max_value, uint32_t nwindows) {
     if (const char *e = getenv("MSMB200_VSPAN")) return (uint32_t)atoi(e);
-    uint32_t v = 64;
-    while (v > 8 && (max_value / v) * nwindows < 32768) v >>= 1;
+    // ~32 K chunks in total (measured optimum on B200: G1 n=2^21 -> 64, G2 n=2^18 -> 16), 8 <= v <= 64, power of two
+    uint32_t v = 8;
+    while (v < 64 && ((max_value + 1) * nwindows + v - 1) / v > 32768 + 1024) v <<= 1;
     return v;
 }
 
@@ -114,7 +115,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         MSM_CUDA(c, cudaStreamSynchronize(st));
         int rounds = 1;
         while (((size_t)1 << rounds) < max_count) rounds++;
-        constexpr int BATCH = sizeof(F) > 48 ? 8 : 16;
+        constexpr int BATCH = sizeof(F) > 48 ? 8 : 32;
         const size_t out_cap = m / 2 + 2 * nb + 4;
         if (ensure(c, c->pts_a, out_cap * sizeof(aff_t<F>)) || ensure(c, c->pts_b, (out_cap / 2 + 2 * nb + 4) * sizeof(aff_t<F>)) ||
             ensure(c, c->bo_a, out_cap * 4) || ensure(c, c->bo_b, (out_cap / 2 + 2 * nb + 4) * 4) || ensure(c, c->base_a, nb * 4) ||
@@ -137,10 +138,10 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
             const size_t threads = (bound_in / 2 + BATCH - 1) / BATCH + 1;
             if (r == 0)
                 ba_round_kernel<F, true, BATCH><<<blocks_for(threads, 128), 128, 0, st>>>(d_table, (const uint32_t *)c->sorted.p, nullptr, bo_in, base_in,
-                                                                                          count, r, tot_in, base[o], pts[o], bo[o]);
+                                                                                          count, r, tot_in, base[o], pts[o], bo[o], getenv("MSMB200_BA_LANEINV") ? 1 : 0);
             else
                 ba_round_kernel<F, false, BATCH><<<blocks_for(threads, 128), 128, 0, st>>>(d_table, nullptr, in_pts, bo_in, base_in, count, r, tot_in,
-                                                                                           base[o], pts[o], bo[o]);
+                                                                                           base[o], pts[o], bo[o], getenv("MSMB200_BA_LANEINV") ? 1 : 0);
             c->launches += 5;
             in_pts = pts[o];
             bo_in = bo[o];
@@ -223,7 +224,7 @@ static int pippenger_impl(Ctx *c, const void *d_points, size_t npoints, const vo
     int rc = prepare_entries(c, m, nb);
     if (rc) return rc;
     digits_booth_kernel<<<blocks_for(npoints, 256), 256, 0, st>>>((const uint32_t *)d_scalars, npoints, nbits, w, tiles,
-                                                                  (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p);
+                                                                  (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p, 1);
     c->launches += 1;
     MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
     uint32_t vs = pick_vspan(nbw - 1, (uint32_t)tiles);
@@ -248,7 +249,7 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
         if (rc) return rc;
         if (method == MSMB200_CHES) {
             digits_ches_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab,
-                                                                   (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p);
+                                                                   (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p, 1);
             c->launches += 1;
         } else {
             if (ensure(c, c->flat, (m + 2) * 4) || ensure(c, c->signs, m) || ensure(c, c->pidx, m * 4)) return MSMB200_ECUDA;
@@ -272,7 +273,7 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
         if (rc) return rc;
         digits_bgmw_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h_bgmw, cfg.e_bgmw,
                                                                bgmw_trick(cfg) ? 1 : 0, (uint32_t *)c->keys.p, (uint32_t *)c->vals.p,
-                                                               (uint32_t *)c->count.p);
+                                                               (uint32_t *)c->count.p, 1);
         c->launches += 1;
         MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
         uint32_t vs = pick_vspan(nbw - 1, 1);
@@ -384,11 +385,11 @@ template <class F> static int digits_impl(Ctx *c, int kind, const void *d_scalar
     if (ensure(c, c->count, nb * 4)) return MSMB200_ECUDA;
     MSM_CUDA(c, cudaMemsetAsync(c->count.p, 0, nb * 4, st));
     if (kind == 0)
-        digits_ches_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab, d_keys, d_vals, (uint32_t *)c->count.p);
+        digits_ches_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab, d_keys, d_vals, (uint32_t *)c->count.p, 0);
     else if (kind == 1)
-        digits_bgmw_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h_bgmw, cfg.e_bgmw, bgmw_trick(cfg) ? 1 : 0, d_keys, d_vals, (uint32_t *)c->count.p);
+        digits_bgmw_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h_bgmw, cfg.e_bgmw, bgmw_trick(cfg) ? 1 : 0, d_keys, d_vals, (uint32_t *)c->count.p, 0);
     else
-        digits_booth_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, 255, c->pip_window, c->pip_tiles, d_keys, d_vals, (uint32_t *)c->count.p);
+        digits_booth_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, 255, c->pip_window, c->pip_tiles, d_keys, d_vals, (uint32_t *)c->count.p, 0);
     MSM_CUDA(c, cudaGetLastError());
     MSM_CUDA(c, cudaStreamSynchronize(st));
     return MSMB200_OK;

@@ -45,7 +45,7 @@ __device__ __forceinline__ void load_scalar(uint32_t s[8], const uint32_t *scala
 // is 0 are skipped like `if(booth_idx)` in src/multi_scalar.c:445,:457.
 static __global__ void digits_ches_kernel(const uint32_t *__restrict__ scalars, size_t n, int h, int e,
                                    const uint32_t *__restrict__ dtab, uint32_t *__restrict__ keys,
-                                   uint32_t *__restrict__ vals, uint32_t *__restrict__ count) {
+                                   uint32_t *__restrict__ vals, uint32_t *__restrict__ count, int digit_major) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -64,8 +64,10 @@ static __global__ void digits_ches_kernel(const uint32_t *__restrict__ scalars, 
             key = idx;
             atomicAdd(&count[idx], 1u);
         }
-        keys[slot] = key;
-        vals[slot] = (uint32_t)(3 * slot + m1) | (alpha << 31);
+        // digit-major placement (j*n + i) makes the warp's stores contiguous; the table index keeps the reference's i*h + j
+        const size_t at = digit_major ? (size_t)j * n + i : slot;
+        keys[at] = key;
+        vals[at] = (uint32_t)(3 * slot + m1) | (alpha << 31);
     }
 }
 
@@ -119,7 +121,7 @@ static __global__ void tile_lookup_kernel(const int *__restrict__ bvals, const u
 // front end of pippenger_variant_BGMW95 (main_p1.cpp:311-375) including the r - a switch for the
 // configurations with e'*h' == 255 (`trick`). r = group order (auxiliaryfunc.h:5-7).
 static __global__ void digits_bgmw_kernel(const uint32_t *__restrict__ scalars, size_t n, int h, int e, int trick,
-                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count) {
+                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count, int digit_major) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -155,8 +157,9 @@ static __global__ void digits_bgmw_kernel(const uint32_t *__restrict__ scalars, 
             key = (uint32_t)mag;
             atomicAdd(&count[mag], 1u);
         }
-        keys[slot] = key;
-        vals[slot] = (uint32_t)slot | ((sign ^ flip) << 31);
+        const size_t at = digit_major ? (size_t)j * n + i : slot;
+        keys[at] = key;
+        vals[at] = (uint32_t)slot | ((sign ^ flip) << 31);
     }
 }
 
@@ -165,7 +168,7 @@ static __global__ void digits_bgmw_kernel(const uint32_t *__restrict__ scalars, 
 // [t*w, t*w + wb) plus the bit below it; the top tile has wb = nbits % w (possibly 0) and is unsigned.
 // key = t * (2^(w-1) + 1) + |digit|; all tiles are emitted at once (ntiles entries per scalar).
 static __global__ void digits_booth_kernel(const uint32_t *__restrict__ scalars, size_t n, int nbits, int w, int ntiles,
-                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count) {
+                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count, int digit_major) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -187,8 +190,9 @@ static __global__ void digits_booth_kernel(const uint32_t *__restrict__ scalars,
             key = (uint32_t)t * nbw + (uint32_t)mag;
             atomicAdd(&count[key], 1u);
         }
-        keys[slot] = key;
-        vals[slot] = (uint32_t)i | (sign << 31);
+        const size_t at = digit_major ? (size_t)t * n + i : slot;
+        keys[at] = key;
+        vals[at] = (uint32_t)i | (sign << 31);
     }
 }
 
@@ -427,6 +431,56 @@ static __global__ void ba_scan_finish_kernel(const uint64_t *__restrict__ scanne
 }
 enum { BA_NONE = 0, BA_ADD = 1, BA_DBL = 2, BA_COPY_P = 3, BA_COPY_Q = 4, BA_INF = 5 };
 
+// warp shuffles of whole field elements (12 / 24 words)
+__device__ __forceinline__ void f_shfl_up(fp_t &r, const fp_t &a, int o) {
+#pragma unroll
+    for (int k = 0; k < 12; k++) r.l[k] = __shfl_up_sync(0xffffffffu, a.l[k], o);
+}
+__device__ __forceinline__ void f_shfl_down(fp_t &r, const fp_t &a, int o) {
+#pragma unroll
+    for (int k = 0; k < 12; k++) r.l[k] = __shfl_down_sync(0xffffffffu, a.l[k], o);
+}
+__device__ __forceinline__ void f_shfl_idx(fp_t &r, const fp_t &a, int src) {
+#pragma unroll
+    for (int k = 0; k < 12; k++) r.l[k] = __shfl_sync(0xffffffffu, a.l[k], src);
+}
+__device__ __forceinline__ void f_shfl_up(fp2_t &r, const fp2_t &a, int o) { f_shfl_up(r.c0, a.c0, o); f_shfl_up(r.c1, a.c1, o); }
+__device__ __forceinline__ void f_shfl_down(fp2_t &r, const fp2_t &a, int o) { f_shfl_down(r.c0, a.c0, o); f_shfl_down(r.c1, a.c1, o); }
+__device__ __forceinline__ void f_shfl_idx(fp2_t &r, const fp2_t &a, int src) { f_shfl_idx(r.c0, a.c0, src); f_shfl_idx(r.c1, a.c1, src); }
+__device__ __forceinline__ void f_shfl_up(fpc_t &r, const fpc_t &a, int o) { f_shfl_up((fp_t &)r, (const fp_t &)a, o); }
+__device__ __forceinline__ void f_shfl_down(fpc_t &r, const fpc_t &a, int o) { f_shfl_down((fp_t &)r, (const fp_t &)a, o); }
+__device__ __forceinline__ void f_shfl_idx(fpc_t &r, const fpc_t &a, int src) { f_shfl_idx((fp_t &)r, (const fp_t &)a, src); }
+
+// Montgomery's trick ACROSS the warp: every lane holds a non-zero `run`; returns 1/run in every lane with ONE field
+// inversion per warp (all lanes invert the same total, so the data-dependent GCD loop does not diverge):
+// prefix and suffix products by shuffles (5 + 5 multiplications), 1/run = 1/total * prefix_excl * suffix_excl.
+template <class F> __device__ __noinline__ void warp_batch_invert(F &inv, const F &run) {
+    // control flow is kept warp-uniform (lanes that have nothing to fold multiply by one): no divergent calls between shuffles
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    F pre = run, suf = run, other, one;
+    f_set_one(one);
+#pragma unroll 1
+    for (int o = 1; o < 32; o <<= 1) {
+        f_shfl_up(other, pre, o);
+        if (lane < o) other = one;
+        f_mul(pre, pre, other);
+        f_shfl_down(other, suf, o);
+        if (lane + o >= 32) other = one;
+        f_mul(suf, suf, other);
+    }
+    F total, tinv, pre_ex, suf_ex;
+    f_shfl_idx(total, pre, 31);
+    f_inv(tinv, total);
+    f_shfl_up(pre_ex, pre, 1);
+    f_shfl_down(suf_ex, suf, 1);
+    if (lane == 0) pre_ex = one;
+    if (lane == 31) suf_ex = one;
+    f_mul(tinv, tinv, pre_ex);
+    f_mul(tinv, tinv, suf_ex);
+    inv = tinv;
+    __syncwarp();
+}
 template <class F, bool FIRST>
 __device__ __forceinline__ void ba_load(aff_t<F> &p, size_t e, const aff_t<F> *__restrict__ table, const uint32_t *__restrict__ sorted,
                                         const aff_t<F> *__restrict__ in_pts) {
@@ -443,11 +497,11 @@ static __global__ void __launch_bounds__(128) ba_round_kernel(const aff_t<F> *__
                                                               const aff_t<F> *__restrict__ in_pts, const uint32_t *__restrict__ bucket_of_in,
                                                               const uint32_t *__restrict__ base_in, const uint32_t *__restrict__ count, int r,
                                                               const uint64_t *__restrict__ total_in, const uint32_t *__restrict__ base_out,
-                                                              aff_t<F> *__restrict__ out_pts, uint32_t *__restrict__ bucket_of_out) {
+                                                              aff_t<F> *__restrict__ out_pts, uint32_t *__restrict__ bucket_of_out, int lane_inversion) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t s0 = t * BATCH;
     const size_t nslots = (size_t)((uint32_t)*total_in) >> 1;  // padded total (low half of the packed scan total) is even
-    if (s0 >= nslots) return;
+    if (__all_sync(0xffffffffu, s0 >= nslots)) return;  // whole warp idle; otherwise every lane takes part in the shuffles
     F prefix[BATCH];
     unsigned char tag[BATCH];
     F run;
@@ -485,7 +539,8 @@ static __global__ void __launch_bounds__(128) ba_round_kernel(const aff_t<F> *__
         tag[j] = tg;
     }
     F inv;
-    f_inv(inv, run);
+    if (lane_inversion) f_inv(inv, run);  // one GCD per lane (diverges); kept as a fallback knob
+    else warp_batch_invert(inv, run);    // one GCD per warp
     // ---- backward: slopes and results ----
 #pragma unroll 1
     for (int j = BATCH - 1; j >= 0; j--) {
@@ -831,6 +886,14 @@ static __global__ void __launch_bounds__(128) fix_points_kernel(const jac_t<F> *
 template <class F>
 static __global__ void field_op_kernel(int op, const F *__restrict__ a, const F *__restrict__ b, F *__restrict__ out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (op == 7) {  // warp-level Montgomery trick (warp_batch_invert): every lane participates, idle lanes hold one
+        F x, r;
+        if (i < n) x = a[i]; else f_set_one(x);
+        if (f_is_zero(x)) f_set_one(x);
+        warp_batch_invert(r, x);
+        if (i < n) out[i] = r;
+        return;
+    }
     if (i >= n) return;
     F x = a[i], y, r;
     if (b) y = b[i]; else f_set_zero(y);

@@ -512,3 +512,22 @@ def test_batch_affine_full_size_known_answer(M, golden):
     sc = O.gen_scalars(1, ctx.n)
     assert M.affine_serialize(1, ctx.msm(1, sc)).hex() == golden["kat_appc"]["g1_n16"]
     ctx.close()
+
+
+@pytest.mark.parametrize("field", [1, 2])
+def test_warp_batch_inversion_vs_plain_inverse(M, field):
+    """Montgomery's trick across the warp (one inversion per 32 lanes, used by the batch-affine rounds) returns the
+    same bytes as the per-element inverse (reference reciprocal_fp / reciprocal_fp2, src/recip.c:58-114)."""
+    rng = np.random.default_rng(3)
+    n = 3000 + 37
+    a = rng.integers(0, 2**64, size=(n, 6 * field), dtype=np.uint64)
+    a[:, 5::6] &= np.uint64(0x0FFFFFFFFFFFFFFF)
+    one = np.frombuffer(bytes.fromhex("fdff02000000097602000cc40b00f4ebba58c7535798485f455752705358ce776dec56a2971a075c93e480fac35ef615"), dtype=np.uint64)
+    idx = rng.integers(0, n, size=n // 3)
+    a[idx, :6] = one
+    if field == 2:
+        a[idx, 6:] = 0
+    exp = np.empty_like(a)
+    (O.oracle().oracle_fp_op if field == 1 else O.oracle().oracle_fp2_op)(6, O.ptr(a), None, O.ptr(exp), n)
+    assert (M.test_field_op(field, 7, a) == exp).all()
+    assert (M.test_field_op(field, 6, a) == exp).all()
