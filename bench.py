@@ -425,8 +425,10 @@ def main():
                 "bound": "imad", "kernel": "accumulate_kernel (bucket accumulation, xyzz += affine)",
                 "achieved": achieved, "peak": peak_mac / 1e12, "unit": "TMAC/s (32x32+64-bit)", "frac": achieved / (peak_mac / 1e12),
                 "traffic": None,
-                "note": "achieved = ALGORITHMIC MACs (n*h adds x 10 Fp-mul x 300 MAC, reference formulas SURVEY §8d) / CUDA-event time of the "
-                        "accumulate phase; peak = IMAD.WIDE.U32 microbenchmark measured in this run (MEASURED_PEAKS.json has no integer figure)",
+                "note": "achieved = ALGORITHMIC MACs (n*h adds x C_add Fp-mul x 300 MAC, reference formulas SURVEY §8d) / CUDA-event time of the "
+                        "accumulate phase; peak = IMAD.WIDE.U32 register-only microbenchmark measured in this run (MEASURED_PEAKS.json has no "
+                        "integer figure). That microbenchmark reuses its multiplicands; with distinct operands the heavy FMA pipe issues one "
+                        "IMAD.WIDE per 4 cycles (32 MAC/clk/SM = %.2f TMAC/s at %.0f MHz), see profiles/" % (32 * 148 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12, clocks["sm_mhz"] or 1965.0),
             }
             line["roofline_path"] = {"bound": "imad", "achieved": cm["w_mac"] / (ms_step * 1e-3) / 1e12, "peak": peak_mac / 1e12,
                                      "unit": "TMAC/s", "frac": cm["w_mac"] / (ms_step * 1e-3) / peak_mac, "note": "whole MSM, W_MAC = 300*W_Fp"}

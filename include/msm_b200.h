@@ -144,6 +144,11 @@ void msmb200_blst_p2_tile_pippenger_BGMW95(void *ret_jacobian, const void *const
                                            const int scalars[], const unsigned char booth_signs[], void *buckets,
                                            size_t q_exponent);
 
+/* blst_p1s_add / blst_p2s_add (bindings/blst.h:224,:364; src/bulk_addition.c:145-164): Jacobian sum of npoints affine
+ * points (pointer-array convention as above). SURVEY §8f rank 1: the library's other consumer of bulk addition. */
+void msmb200_blst_p1s_add(void *ret_jacobian, const void *const points[], size_t npoints);
+void msmb200_blst_p2s_add(void *ret_jacobian, const void *const points[], size_t npoints);
+
 /* ---- building blocks exposed for parity tests (each is a batched CUDA kernel launch; host buffers) ---
  * field ops on n elements. field: 1 = Fp (48 B), 2 = Fp2 (96 B).
  * op: 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 5 mul_by_3, 6 inverse        (blst_fp_mul ... bindings/blst.h:108-137),

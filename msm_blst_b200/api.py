@@ -93,6 +93,9 @@ def lib():
             f = getattr(L, "msmb200_blst_p%ds_mult_pippenger" % g)
             f.argtypes = [vp, vp, sz, vp, sz, vp]
             f.restype = None
+            f = getattr(L, "msmb200_blst_p%ds_add" % g)
+            f.argtypes = [vp, vp, sz]
+            f.restype = None
             f = getattr(L, "msmb200_blst_p%d_tile_pippenger_d_CHES" % g)
             f.argtypes = [vp, vp, sz, vp, vp, vp, vp, vp, sz, ci]
             f.restype = None

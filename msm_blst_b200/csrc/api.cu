@@ -472,6 +472,34 @@ static void shim_tile(int group, void *ret, const void *const points[], size_t n
     cudaFree(dp); cudaFree(dsc); cudaFree(dsg); cudaFree(dpi); cudaFree(dj); cudaFree(dbs); cudaFree(dv); cudaFree(dcf);
 }
 
+// blst_pNs_add (src/bulk_addition.c:145-164): sum of npoints affine points. One bucket holding every point, so the
+// work is exactly the bucket-accumulation stage (batch-affine rounds or XYZZ work items + block combine).
+static void shim_points_add(int group, void *ret, const void *const points[], size_t npoints) {
+    Ctx *c = shim_ctx(group);
+    size_t ab = c->ops->aff_bytes, jb = c->ops->jac_bytes;
+    if (npoints == 0) { memset(ret, 0, jb); return; }
+    cudaSetDevice(c->device);
+    std::vector<unsigned char> hp;
+    gather_ptr_array(hp, points, npoints, ab, ab);
+    std::vector<int> ones(npoints, 1);
+    std::vector<uint32_t> pidx(npoints);
+    for (size_t k = 0; k < npoints; k++) pidx[k] = (uint32_t)k;
+    void *dp = nullptr, *dsc = nullptr, *dsg = nullptr, *dpi = nullptr, *dj = nullptr;
+    if (cudaMalloc(&dp, hp.size()) != cudaSuccess || cudaMalloc(&dsc, npoints * 4) != cudaSuccess || cudaMalloc(&dsg, npoints) != cudaSuccess ||
+        cudaMalloc(&dpi, npoints * 4) != cudaSuccess || cudaMalloc(&dj, jb) != cudaSuccess) { c->err = "cudaMalloc"; shim_fail(c, "blst_pNs_add"); }
+    cudaMemcpyAsync(dp, hp.data(), hp.size(), cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(dsc, ones.data(), npoints * 4, cudaMemcpyHostToDevice, c->stream);
+    cudaMemsetAsync(dsg, 0, npoints, c->stream);
+    cudaMemcpyAsync(dpi, pidx.data(), npoints * 4, cudaMemcpyHostToDevice, c->stream);
+    if (c->ops->tile(c, dp, (const int *)dsc, (const unsigned char *)dsg, (const uint32_t *)dpi, npoints, nullptr, nullptr, 2, 1, nullptr, 8, 1, dj))
+        shim_fail(c, "blst_pNs_add");
+    cudaMemcpyAsync(ret, dj, jb, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pNs_add"); }
+    cudaFree(dp); cudaFree(dsc); cudaFree(dsg); cudaFree(dpi); cudaFree(dj);
+}
+void msmb200_blst_p1s_add(void *ret, const void *const points[], size_t npoints) { shim_points_add(1, ret, points, npoints); }
+void msmb200_blst_p2s_add(void *ret, const void *const points[], size_t npoints) { shim_points_add(2, ret, points, npoints); }
+
 size_t msmb200_blst_p1s_mult_pippenger_scratch_sizeof(size_t npoints) { return (size_t)192 << (pippenger_window_size(npoints) - 1); }
 size_t msmb200_blst_p2s_mult_pippenger_scratch_sizeof(size_t npoints) { return (size_t)384 << (pippenger_window_size(npoints) - 1); }
 void msmb200_blst_p1s_mult_pippenger(void *ret, const void *const points[], size_t npoints, const unsigned char *const scalars[], size_t nbits, void *) {

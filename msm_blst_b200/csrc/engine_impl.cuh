@@ -97,11 +97,9 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
                                                                          (const uint32_t *)c->item_begin.p, (const uint32_t *)c->item_cnt.p,
                                                                          (const uint32_t *)c->order.p, totals, (xyzz_t<F> *)c->partial.p);
         {
-            size_t smem = 128 * sizeof(xyzz_t<FC>);
-            MSM_CUDA(c, cudaFuncSetAttribute(combine_heavy_kernel<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             unsigned max_heavy = (unsigned)std::min<size_t>(m / item_len + 1, 592);
-            combine_heavy_kernel<FC><<<max_heavy, 128, smem, st>>>(count, (const uint32_t *)c->item_start.p, (const uint32_t *)c->heavy.p, item_len,
-                                                                  (xyzz_t<FC> *)c->partial.p);
+            combine_heavy_kernel<FC><<<max_heavy, 128, 0, st>>>(count, (const uint32_t *)c->item_start.p, (const uint32_t *)c->heavy.p, item_len,
+                                                               (xyzz_t<FC> *)c->partial.p);
         }
         c->launches += 2;
         bucket_points = c->partial.p;
@@ -179,9 +177,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         per = groups;
     }
     if (per > 1) {
-        size_t smem = 256 * sizeof(xyzz_t<FC>);
-        MSM_CUDA(c, cudaFuncSetAttribute(tree_tail_kernel<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tree_tail_kernel<FC><<<nrows, 256, smem, st>>>((const xyzz_t<FC> *)cur, per, (xyzz_t<FC> *)nxt);
+        tree_tail_kernel<FC><<<nrows, 256, 0, st>>>((xyzz_t<FC> *)cur, per, (xyzz_t<FC> *)nxt);
         c->launches += 1;
         std::swap(cur, nxt);
         per = 1;

@@ -374,34 +374,40 @@ template <class F> __device__ __forceinline__ void load_xyzz(xyzz_t<F> &p, const
 template <class F>
 static __global__ void __launch_bounds__(128) combine_heavy_kernel(const uint32_t *__restrict__ count, const uint32_t *__restrict__ item_start,
                                                                    const uint32_t *__restrict__ heavy, uint32_t item_len,
-                                                                   xyzz_t<F> *__restrict__ partial) {
-    extern __shared__ uint4 tree_smem_raw[];
-    xyzz_t<F> *sm = reinterpret_cast<xyzz_t<F> *>(tree_smem_raw);
-    for (uint32_t hidx = blockIdx.x; hidx < heavy[0]; hidx += gridDim.x) {
-    const uint32_t b = heavy[1 + hidx], t = threadIdx.x;
-    const uint32_t c = count[b], items = (c + item_len - 1) / item_len, it = item_start[b];
-    xyzz_t<F> acc;
-    xyzz_set_inf(acc);
-    for (uint32_t k = t; k < items; k += blockDim.x) {
-        xyzz_t<F> q;
-        load_xyzz(q, partial + it + k);
-        xyzz_add_cold(acc, q);
-    }
-    sm[t] = acc;
-    __syncthreads();
-    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
-        if (t < s) {
-            xyzz_t<F> a = sm[t], q = sm[t + s];
-            xyzz_add_cold(a, q);
-            sm[t] = a;
+                                                                   xyzz_t<F> *partial) {
+    // tree in place in global memory (no shared memory: a different carve-out than the neighbouring kernels costs
+    // an SM reconfiguration per launch, measured ~0.3 ms even when there is nothing to combine)
+    const uint32_t nheavy = heavy[0];
+    for (uint32_t hidx = blockIdx.x; hidx < nheavy; hidx += gridDim.x) {
+        const uint32_t b = heavy[1 + hidx], t = threadIdx.x;
+        const uint32_t c = count[b], items = (c + item_len - 1) / item_len, it = item_start[b];
+        // strided pass: thread t folds items t, t+128, ... into slot t
+        if (t < items) {
+            xyzz_t<F> acc;
+            load_xyzz(acc, partial + it + t);
+            for (uint32_t k = t + blockDim.x; k < items; k += blockDim.x) {
+                xyzz_t<F> q;
+                load_xyzz(q, partial + it + k);
+                xyzz_add_cold(acc, q);
+            }
+            partial[it + t] = acc;
         }
+        __threadfence_block();
         __syncthreads();
-    }
-    if (t == 0) partial[it] = sm[0];
-    __syncthreads();
+        const uint32_t live = min(items, (uint32_t)blockDim.x);
+        for (uint32_t s = 64; s > 0; s >>= 1) {
+            if (t < s && t + s < live) {
+                xyzz_t<F> a, q;
+                load_xyzz(a, partial + it + t);
+                load_xyzz(q, partial + it + t + s);
+                xyzz_add_cold(a, q);
+                partial[it + t] = a;
+            }
+            __threadfence_block();
+            __syncthreads();
+        }
     }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // [3'] bucket accumulation by BATCH-AFFINE pairwise rounds — the GPU analogue of the reference's
@@ -706,28 +712,35 @@ static __global__ void __launch_bounds__(128) sum_groups_kernel(const xyzz_t<F> 
 // last levels of the tree in ONE launch: block `row` sums in[row*per .. +per) (per <= a few thousand) with a
 // shared-memory tree: log2(blockDim) dependent additions instead of one kernel launch per level
 template <class F>
-static __global__ void __launch_bounds__(256) tree_tail_kernel(const xyzz_t<F> *__restrict__ in, uint32_t per, xyzz_t<F> *__restrict__ out) {
-    extern __shared__ uint4 tree_smem_raw[];
-    xyzz_t<F> *sm = reinterpret_cast<xyzz_t<F> *>(tree_smem_raw);
+static __global__ void __launch_bounds__(256) tree_tail_kernel(xyzz_t<F> *in, uint32_t per, xyzz_t<F> *__restrict__ out) {
+    // block `row` sums in[row*per .. +per) in place (global memory tree, see combine_heavy_kernel for why not shared memory)
     const uint32_t row = blockIdx.x, t = threadIdx.x;
-    xyzz_t<F> acc;
-    xyzz_set_inf(acc);
-    for (uint32_t k = t; k < per; k += blockDim.x) {
-        xyzz_t<F> q;
-        load_xyzz(q, in + (size_t)row * per + k);
-        xyzz_add_cold(acc, q);
-    }
-    sm[t] = acc;
-    __syncthreads();
-    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
-        if (t < s) {
-            xyzz_t<F> a = sm[t], b = sm[t + s];
-            xyzz_add_cold(a, b);
-            sm[t] = a;
+    xyzz_t<F> *base = in + (size_t)row * per;
+    if (t < per) {
+        xyzz_t<F> acc;
+        load_xyzz(acc, base + t);
+        for (uint32_t k = t + blockDim.x; k < per; k += blockDim.x) {
+            xyzz_t<F> q;
+            load_xyzz(q, base + k);
+            xyzz_add_cold(acc, q);
         }
+        base[t] = acc;
+    }
+    __threadfence_block();
+    __syncthreads();
+    const uint32_t live = min(per, (uint32_t)blockDim.x);
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (t < s && t + s < live) {
+            xyzz_t<F> a, q;
+            load_xyzz(a, base + t);
+            load_xyzz(q, base + t + s);
+            xyzz_add_cold(a, q);
+            base[t] = a;
+        }
+        __threadfence_block();
         __syncthreads();
     }
-    if (t == 0) out[row] = sm[0];
+    if (t == 0) out[row] = base[0];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -531,3 +531,35 @@ def test_warp_batch_inversion_vs_plain_inverse(M, field):
     (O.oracle().oracle_fp_op if field == 1 else O.oracle().oracle_fp2_op)(6, O.ptr(a), None, O.ptr(exp), n)
     assert (M.test_field_op(field, 7, a) == exp).all()
     assert (M.test_field_op(field, 6, a) == exp).all()
+
+
+@pytest.mark.parametrize("group", [1, 2])
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_blst_points_add_shim_vs_compiled_reference(M, golden, group, mode, monkeypatch):
+    """msmb200_blst_pNs_add (sum of affine points; the reference's bulk_addition.c consumer) against the
+    compiled reference's blst_pNs_add when oracle/_ref is present, else against the oracle; both accumulators."""
+    monkeypatch.setenv("MSMB200_ACCUM", mode)
+    gd = golden["pippenger_unstructured"][str(group)]
+    n = gd["n"]
+    ab, jb = O.AFF_BYTES[group], O.JAC_BYTES[group]
+    pts = np.frombuffer(bytes.fromhex(gd["points"]), dtype=np.uint8).copy()
+    # duplicate a few points so that P + P shows up in the tree, and add P, -P neighbours
+    pts2 = np.concatenate([pts, pts[: 10 * ab], pts[20 * ab: 21 * ab]])
+    n2 = n + 11
+    pp = (C.c_void_p * 2)(pts2.ctypes.data, None)
+    ret = np.zeros(jb, dtype=np.uint8)
+    getattr(M.lib(), "msmb200_blst_p%ds_add" % group)(O.ptr(ret), pp, n2)
+    got = M.test_point_op(group, 5, ret)
+    # expected: sum with all-one scalars through the oracle (naive double-and-add MSM)
+    ones = np.zeros((n2, 4), dtype=np.uint64)
+    ones[:, 0] = 1
+    exp = np.zeros(ab, dtype=np.uint8)
+    O.oracle().oracle_naive_msm(group, O.ptr(pts2), O.ptr(ones), n2, O.ptr(exp))
+    assert (got == exp).all()
+    if O.has_ref():
+        b = O.blst_ref()
+        rj = np.zeros(jb, dtype=np.uint8)
+        getattr(b, "blst_p%ds_add" % group)(O.ptr(rj), pp, C.c_size_t(n2))
+        ra = np.zeros(ab, dtype=np.uint8)
+        getattr(b, "blst_p%d_to_affine" % group)(O.ptr(ra), O.ptr(rj))
+        assert (got == ra).all()
