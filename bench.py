@@ -287,6 +287,8 @@ def main():
     ap.add_argument("--method", type=int, default=1, choices=[1, 2, 3, 4])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard-config", default="auto", help="reference config used per shard when --gpus > 1 (auto: tuned for n/G)")
+    ap.add_argument("--shard", default="buckets", choices=["buckets", "points"],
+                    help="multi-GPU decomposition: bucket ranges with replicated tables (default) or point shards")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -314,9 +316,12 @@ def main():
     full_cfg = M.config_lookup(cfgname)
     n = 1 << full_cfg.n_exp
     method = args.method
-    lo, hi = D.shard_range(n, rank, N)
-    shard_cfgname = cfgname if N == 1 else (D.shard_config_name(hi - lo) if args.shard_config == "auto" else args.shard_config)
+    by_buckets = N > 1 and args.shard == "buckets"
+    lo, hi = (0, n) if (by_buckets or N == 1) else D.shard_range(n, rank, N)
+    shard_cfgname = cfgname if (N == 1 or by_buckets) else (D.shard_config_name(hi - lo) if args.shard_config == "auto" else args.shard_config)
     ctx = M.MsmContext(group, shard_cfgname, npoints=hi - lo, device=local_rank, first=lo)
+    if by_buckets:
+        ctx.set_bucket_shard(rank, N)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     t0 = time.time()
@@ -330,8 +335,15 @@ def main():
     # several scalar sets, rotated so that no step re-reads the previous step's inputs
     nsets = 3
     sets = [gen_scalars(1 + s, n) for s in range(nsets)]
-    host_sets = [torch.from_numpy(s[lo:hi].view(np.uint8).copy()).pin_memory() for s in sets]
-    dev_sets = [h.cuda(non_blocking=True) for h in host_sets]
+    # host side always holds this rank's 1/N of the scalars; with bucket sharding the device needs all of them
+    # (device-resident for `value`; for `e2e` the shards are uploaded and all-gathered over NVLink inside the timed region)
+    slo, shi = D.shard_range(n, rank, N)
+    host_sets = [torch.from_numpy(s[slo:shi].view(np.uint8).copy()).pin_memory() for s in sets]
+    if by_buckets:
+        dev_sets = [torch.from_numpy(s.view(np.uint8).copy()).cuda() for s in sets]
+        dev_shards = [torch.empty((shi - slo) * 32, dtype=torch.uint8, device="cuda") for _ in sets]
+    else:
+        dev_sets = [h.cuda(non_blocking=True) for h in host_sets]
     jb = M.api.JAC_BYTES[group]
     partial = torch.zeros(jb, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
@@ -345,7 +357,12 @@ def main():
         if N == 1:
             return ctx.msm(method, host_sets[i % nsets].numpy())
         d = dev_sets[i % nsets]
-        d.copy_(host_sets[i % nsets], non_blocking=True)
+        if by_buckets:
+            sh = dev_shards[i % nsets]
+            sh.copy_(host_sets[i % nsets].view(-1), non_blocking=True)
+            D.all_gather_scalars(sh, d.view(-1))
+        else:
+            d.copy_(host_sets[i % nsets], non_blocking=True)
         return D.msm_sharded(ctx, method, d, partial)
 
     def timed(fn, steps, sampler=None):
@@ -406,11 +423,11 @@ def main():
             "value": ms_step, "unit": "ms", "n_gpus": N, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32x12 (384-bit Montgomery integers)", "data": "synthetic: P_i=2^(i+1)G, seeded splitmix64 scalars < r (SURVEY App. C)",
-            "config": {"workload": desc, "method": METHOD_NAMES[method], "n": n, "shard_config": shard_cfgname, "parallelism": "points sharded x%d" % N,
+            "config": {"workload": desc, "method": METHOD_NAMES[method], "n": n, "shard_config": shard_cfgname, "parallelism": ("bucket ranges x%d, tables replicated" % N) if by_buckets else ("points sharded x%d" % N),
                        "l2_policy": "inputs larger than L2: %.2f GB precomputation table gathered at random per step, %d rotating scalar sets" % (
                            (3 * n * full_cfg.h if method in (1, 2) else n * full_cfg.h_bgmw if method == 3 else n) * (96 if group == 1 else 192) / 1e9, nsets),
                        "table_setup_s": t_setup},
-            "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": int((hi - lo) * 32) * N, "d2h_bytes_per_step": (96 if group == 1 else 192)},
+            "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": int(n * 32), "d2h_bytes_per_step": (96 if group == 1 else 192)},
             "gpu_launches": launches,
             "result_hex": result_hex, "result_consistent": consistent, "last_scalar_seed": 1 + last_set,
             "clocks": clocks,

@@ -75,6 +75,12 @@ const char *msmb200_last_error(const msmb200_ctx *ctx); /* ctx may be NULL: last
 /* Use the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream). */
 int msmb200_set_stream(msmb200_ctx *ctx, void *cuda_stream);
 
+/* Multi-GPU by BUCKET RANGE (the alternative of SURVEY §8e): every context holds all points and tables; context
+ * `rank` of `world` accumulates and reduces only its 1/world slice of the bucket-reduction chunks, so both hot
+ * loops scale 1/world; the per-context results are Jacobian partials that sum to the full MSM (same gather as the
+ * point-sharded mode). Default rank 0 of 1. */
+int msmb200_set_bucket_shard(msmb200_ctx *ctx, int rank, int world);
+
 /* Bucket-accumulation algorithm: 0 = library default, 1 = XYZZ mixed additions, one thread per work item (the
  * reference's xyzz_dadd_affine loop, src/multi_scalar.c:437-461), 2 = batch-affine pairwise rounds sharing one
  * inversion per batch (the reference's bulk_addition.c:51-143 analogue). Results are identical. */

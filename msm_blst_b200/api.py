@@ -68,6 +68,7 @@ def lib():
         L.msmb200_set_stream.argtypes = [vp, vp]
         L.msmb200_set_points.argtypes = [vp, vp]
         L.msmb200_set_accumulator.argtypes = [vp, ci]
+        L.msmb200_set_bucket_shard.argtypes = [vp, ci, ci]
         L.msmb200_generate_fix_points.argtypes = [vp, sz]
         L.msmb200_table_build_ches.argtypes = [vp]
         L.msmb200_table_build_bgmw95.argtypes = [vp]
@@ -214,6 +215,10 @@ class MsmContext:
     def set_accumulator(self, mode):
         """0 default, 1 XYZZ work items, 2 batch-affine rounds (identical results)."""
         self._ck(lib().msmb200_set_accumulator(self._h, int(mode)))
+
+    def set_bucket_shard(self, rank, world):
+        """Bucket-range sharding: this context (holding ALL points) handles slice `rank` of `world` of the buckets."""
+        self._ck(lib().msmb200_set_bucket_shard(self._h, int(rank), int(world)))
 
     # -- reference driver mirror --
     def init_fix_point_list(self):

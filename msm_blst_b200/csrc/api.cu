@@ -170,6 +170,7 @@ int msmb200_ctx_create(msmb200_ctx **out, int group, const msmb200_config *cfg, 
     CREATE_CUDA(cudaMalloc(&c->d_dtab, dtab.size() * sizeof(uint32_t)));
     c->red_vspan = pick_vspan_host((size_t)c->bucket_set.back(), 1);
     std::vector<int> cf = build_chunk_first(c->bucket_set.data(), c->bucket_set.size(), c->red_vspan, &c->red_nchunks);
+    c->h_chunk_first = cf;
     CREATE_CUDA(cudaMalloc(&c->d_chunk_first, cf.size() * sizeof(int)));
     CREATE_CUDA(cudaMemcpy(c->d_chunk_first, cf.data(), cf.size() * sizeof(int), cudaMemcpyHostToDevice));
     CREATE_CUDA(cudaMalloc(&c->d_points, npoints * c->ops->aff_bytes));
@@ -198,6 +199,12 @@ int msmb200_set_stream(msmb200_ctx *ctx, void *cuda_stream) {
     return MSMB200_OK;
 }
 
+int msmb200_set_bucket_shard(msmb200_ctx *ctx, int rank, int world) {
+    if (!ctx || world < 1 || rank < 0 || rank >= world) return MSMB200_EINVAL;
+    C(ctx)->shard_rank = rank;
+    C(ctx)->shard_world = world;
+    return MSMB200_OK;
+}
 int msmb200_set_accumulator(msmb200_ctx *ctx, int mode) {
     if (!ctx || mode < 0 || mode > 2) return MSMB200_EINVAL;
     C(ctx)->accum_mode = mode;

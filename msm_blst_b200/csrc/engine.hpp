@@ -48,6 +48,8 @@ struct Ctx {
     DevBuf scalars, keys, vals, sorted, count, packed, scanned, tile_sums, seg_start, item_start, cursor,
         item_begin, item_cnt, order, len_hist, len_start, len_cursor, partial, chunk_a, chunk_b, result,
         flat, signs, pidx, heavy, bucket_of0, bo_a, bo_b, pts_a, pts_b, base_a, base_b, tile_sums2, maxcount;
+    std::vector<int> h_chunk_first;   // host copy of d_chunk_first
+    int shard_rank = 0, shard_world = 1;  // bucket-range sharding: this context owns 1/world of the reduction chunks
     int accum_mode = 0;  // 0 = default, 1 = XYZZ work items, 2 = batch-affine rounds
     void *h_result = nullptr;  // pinned staging for the result
 

@@ -24,8 +24,17 @@ struct Layout {
     int d_max;
     const int *chunk_first;  // device (sparse only): first local index whose value exceeds c * vspan, c = 0..nchunks
     uint32_t vspan;          // value span of one reduction chunk (power of two)
-    uint32_t nchunks;        // reduction chunks per window
+    uint32_t nchunks;        // reduction chunks per window (all of them)
+    uint32_t chunk_lo = 0, chunk_cnt = 0;  // the slice this context reduces (bucket-range sharding); cnt 0 = all
 };
+
+// slice of the reduction chunks owned by this context and the matching local bucket-index range [lo, hi)
+static inline void shard_slice(const Ctx *c, uint32_t nchunks, uint32_t *chunk_lo, uint32_t *chunk_cnt) {
+    uint32_t lo = (uint32_t)((uint64_t)nchunks * c->shard_rank / c->shard_world);
+    uint32_t hi = (uint32_t)((uint64_t)nchunks * (c->shard_rank + 1) / c->shard_world);
+    *chunk_lo = lo;
+    *chunk_cnt = hi - lo;
+}
 
 // value span of a reduction chunk: aim at ~32 K chunks in total, between 8 and 64 values per chunk
 static inline uint32_t pick_vspan(size_t max_value, uint32_t nwindows) {
@@ -152,13 +161,13 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     }
     MSM_CUDA(c, cudaEventRecord(c->ev[3], st));
     // ---- reduce ----
-    const uint32_t cpw = L.nchunks;
+    const uint32_t cpw = L.chunk_cnt ? L.chunk_cnt : L.nchunks;
     size_t nchunks = (size_t)cpw * L.nwindows;
     if (ensure(c, c->chunk_a, 2 * nchunks * sizeof(xyzz_t<F>)) || ensure(c, c->chunk_b, (2 * ((size_t)cpw / 4 + 2) * L.nwindows + 2) * sizeof(xyzz_t<F>)))
         return MSMB200_ECUDA;
 #define MSM_REDUCE_LAUNCH(DENSE_, AFF_)                                                                                             \
     reduce_chunks_kernel<F, DENSE_, AFF_><<<blocks_for(nchunks, 64), 64, 0, st>>>(                                                  \
-        bucket_points, count, bucket_point_index, L.bucket_vals, L.chunk_first, L.nbw, L.nwindows, L.vspan, cpw, L.bucket_vals ? L.d_max : 1, \
+        bucket_points, count, bucket_point_index, L.bucket_vals, L.chunk_first, L.nbw, L.nwindows, L.vspan, cpw, L.chunk_lo, L.bucket_vals ? L.d_max : 1, \
         (xyzz_t<F> *)c->chunk_a.p)
     if (L.bucket_vals) { if (batch_affine) MSM_REDUCE_LAUNCH(false, true); else MSM_REDUCE_LAUNCH(false, false); }
     else { if (batch_affine) MSM_REDUCE_LAUNCH(true, true); else MSM_REDUCE_LAUNCH(true, false); }
@@ -219,12 +228,16 @@ static int pippenger_impl(Ctx *c, const void *d_points, size_t npoints, const vo
     size_t m = npoints * (size_t)tiles, nb = (size_t)nbw * tiles;
     int rc = prepare_entries(c, m, nb);
     if (rc) return rc;
+    const uint32_t vs = pick_vspan(nbw - 1, (uint32_t)tiles), nch = (nbw - 1 + vs - 1) / vs;
+    uint32_t clo, ccnt;
+    shard_slice(c, nch, &clo, &ccnt);
+    const uint32_t blo = 1 + clo * vs, bhi = std::min<uint32_t>(nbw, 1 + (clo + ccnt) * vs);
     digits_booth_kernel<<<blocks_for(npoints, 256), 256, 0, st>>>((const uint32_t *)d_scalars, npoints, nbits, w, tiles,
-                                                                  (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p, 1);
+                                                                  (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p, 1, blo, bhi);
     c->launches += 1;
     MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
-    uint32_t vs = pick_vspan(nbw - 1, (uint32_t)tiles);
-    Layout L{m, nbw, (uint32_t)tiles, (uint32_t)w, nullptr, 1, nullptr, vs, (nbw - 1 + vs - 1) / vs};
+    Layout L{m, nbw, (uint32_t)tiles, (uint32_t)w, nullptr, 1, nullptr, vs, nch};
+    L.chunk_lo = clo; L.chunk_cnt = ccnt;
     return run_buckets<F, FC>(c, L, (const aff_t<F> *)d_points, d_out_jac, want_affine);
 }
 
@@ -243,9 +256,12 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
         size_t m = n * (size_t)cfg.h, nb = c->bucket_set.size();
         int rc = prepare_entries(c, m, nb);
         if (rc) return rc;
+        uint32_t clo, ccnt;
+        shard_slice(c, c->red_nchunks, &clo, &ccnt);
+        const uint32_t blo = (uint32_t)c->h_chunk_first[clo], bhi = (uint32_t)c->h_chunk_first[clo + ccnt];
         if (method == MSMB200_CHES) {
             digits_ches_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab,
-                                                                   (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p, 1);
+                                                                   (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p, 1, blo, bhi);
             c->launches += 1;
         } else {
             if (ensure(c, c->flat, (m + 2) * 4) || ensure(c, c->signs, m) || ensure(c, c->pidx, m * 4)) return MSMB200_ECUDA;
@@ -254,11 +270,12 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
                                                                     n, cfg.h, c->d_dtab, c->d_bucket_vals);
             tile_lookup_kernel<<<blocks_for(m, 256), 256, 0, st>>>((const int *)c->flat.p, (const unsigned char *)c->signs.p,
                                                                    (const uint32_t *)c->pidx.p, m, c->d_v2i, (uint32_t *)c->keys.p,
-                                                                   (uint32_t *)c->vals.p, (uint32_t *)c->count.p);
+                                                                   (uint32_t *)c->vals.p, (uint32_t *)c->count.p, blo, bhi);
             c->launches += 3;
         }
         MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
         Layout L{m, (uint32_t)nb, 1, 0, c->d_bucket_vals, cfg.d, c->d_chunk_first, c->red_vspan, c->red_nchunks};
+        L.chunk_lo = clo; L.chunk_cnt = ccnt;
         return run_buckets<F, FC>(c, L, (const aff_t<F> *)c->d_table_ches, d_out_jac, want_affine);
     }
     if (method == MSMB200_BGMW95) {
@@ -267,13 +284,17 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
         uint32_t nbw = (1u << (cfg.e_bgmw - 1)) + 1u;
         int rc = prepare_entries(c, m, nbw);
         if (rc) return rc;
+        const uint32_t vs = pick_vspan(nbw - 1, 1), nch = (nbw - 1 + vs - 1) / vs;
+        uint32_t clo, ccnt;
+        shard_slice(c, nch, &clo, &ccnt);
+        const uint32_t blo = 1 + clo * vs, bhi = std::min<uint32_t>(nbw, 1 + (clo + ccnt) * vs);
         digits_bgmw_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h_bgmw, cfg.e_bgmw,
                                                                bgmw_trick(cfg) ? 1 : 0, (uint32_t *)c->keys.p, (uint32_t *)c->vals.p,
-                                                               (uint32_t *)c->count.p, 1);
+                                                               (uint32_t *)c->count.p, 1, blo, bhi);
         c->launches += 1;
         MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
-        uint32_t vs = pick_vspan(nbw - 1, 1);
-        Layout L{m, nbw, 1, 0, nullptr, 1, nullptr, vs, (nbw - 1 + vs - 1) / vs};
+        Layout L{m, nbw, 1, 0, nullptr, 1, nullptr, vs, nch};
+        L.chunk_lo = clo; L.chunk_cnt = ccnt;
         return run_buckets<F, FC>(c, L, (const aff_t<F> *)c->d_table_bgmw, d_out_jac, want_affine);
     }
     return ctx_fail(c, MSMB200_EINVAL, "unknown method");
@@ -291,7 +312,7 @@ static int tile_impl(Ctx *c, const void *d_table, const int *d_bvals, const unsi
     int rc = prepare_entries(c, m, nbuckets);
     if (rc) return rc;
     tile_lookup_kernel<<<blocks_for(m, 256), 256, 0, st>>>(d_bvals, d_signs, d_pidx, m, d_v2i, (uint32_t *)c->keys.p, (uint32_t *)c->vals.p,
-                                                           (uint32_t *)c->count.p);
+                                                           (uint32_t *)c->count.p, 0u, 0xffffffffu);
     c->launches += 1;
     MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
     Layout L{m, (uint32_t)nbuckets, 1, 0, d_bucket_vals, d_max, d_chunk_first, vspan, nchunks};
@@ -381,11 +402,11 @@ template <class F> static int digits_impl(Ctx *c, int kind, const void *d_scalar
     if (ensure(c, c->count, nb * 4)) return MSMB200_ECUDA;
     MSM_CUDA(c, cudaMemsetAsync(c->count.p, 0, nb * 4, st));
     if (kind == 0)
-        digits_ches_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab, d_keys, d_vals, (uint32_t *)c->count.p, 0);
+        digits_ches_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab, d_keys, d_vals, (uint32_t *)c->count.p, 0, 0u, 0xffffffffu);
     else if (kind == 1)
-        digits_bgmw_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h_bgmw, cfg.e_bgmw, bgmw_trick(cfg) ? 1 : 0, d_keys, d_vals, (uint32_t *)c->count.p, 0);
+        digits_bgmw_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h_bgmw, cfg.e_bgmw, bgmw_trick(cfg) ? 1 : 0, d_keys, d_vals, (uint32_t *)c->count.p, 0, 0u, 0xffffffffu);
     else
-        digits_booth_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, 255, c->pip_window, c->pip_tiles, d_keys, d_vals, (uint32_t *)c->count.p, 0);
+        digits_booth_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, 255, c->pip_window, c->pip_tiles, d_keys, d_vals, (uint32_t *)c->count.p, 0, 0u, 0xffffffffu);
     MSM_CUDA(c, cudaGetLastError());
     MSM_CUDA(c, cudaStreamSynchronize(st));
     return MSMB200_OK;

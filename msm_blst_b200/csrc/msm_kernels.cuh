@@ -45,7 +45,8 @@ __device__ __forceinline__ void load_scalar(uint32_t s[8], const uint32_t *scala
 // is 0 are skipped like `if(booth_idx)` in src/multi_scalar.c:445,:457.
 static __global__ void digits_ches_kernel(const uint32_t *__restrict__ scalars, size_t n, int h, int e,
                                    const uint32_t *__restrict__ dtab, uint32_t *__restrict__ keys,
-                                   uint32_t *__restrict__ vals, uint32_t *__restrict__ count, int digit_major) {
+                                   uint32_t *__restrict__ vals, uint32_t *__restrict__ count, int digit_major, uint32_t lo, uint32_t hi) {
+    // [lo, hi): bucket-index range owned by this context (bucket-range sharding over GPUs); others are skipped
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -60,7 +61,7 @@ static __global__ void digits_ches_kernel(const uint32_t *__restrict__ scalars, 
         carry = alpha;
         size_t slot = i * h + j;
         uint32_t key = KEY_SKIP;
-        if (idx != 0) {
+        if (idx != 0 && idx >= lo && idx < hi) {
             key = idx;
             atomicAdd(&count[idx], 1u);
         }
@@ -104,12 +105,12 @@ static __global__ void construct_nh_kernel(int *__restrict__ flat, unsigned char
 // bucket_value_to_its_index[scalars[k]], skip when 0. Also serves the literal blst-named shim.
 static __global__ void tile_lookup_kernel(const int *__restrict__ bvals, const unsigned char *__restrict__ signs,
                                    const uint32_t *__restrict__ pidx, size_t m, const int *__restrict__ v2i,
-                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count) {
+                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count, uint32_t lo, uint32_t hi) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m) return;
     int idx = v2i ? v2i[bvals[k]] : bvals[k];
     uint32_t key = KEY_SKIP;
-    if (idx != 0) {
+    if (idx != 0 && (uint32_t)idx >= lo && (uint32_t)idx < hi) {
         key = (uint32_t)idx;
         atomicAdd(&count[idx], 1u);
     }
@@ -121,7 +122,7 @@ static __global__ void tile_lookup_kernel(const int *__restrict__ bvals, const u
 // front end of pippenger_variant_BGMW95 (main_p1.cpp:311-375) including the r - a switch for the
 // configurations with e'*h' == 255 (`trick`). r = group order (auxiliaryfunc.h:5-7).
 static __global__ void digits_bgmw_kernel(const uint32_t *__restrict__ scalars, size_t n, int h, int e, int trick,
-                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count, int digit_major) {
+                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count, int digit_major, uint32_t lo, uint32_t hi) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -153,7 +154,7 @@ static __global__ void digits_bgmw_kernel(const uint32_t *__restrict__ scalars, 
         if (mag > qhalf) mag = qhalf;  // unreachable for scalars < r except with prob 2^-62; clamp
         size_t slot = i * h + j;
         uint32_t key = KEY_SKIP;
-        if (mag != 0) {
+        if (mag != 0 && (uint32_t)mag >= lo && (uint32_t)mag < hi) {
             key = (uint32_t)mag;
             atomicAdd(&count[mag], 1u);
         }
@@ -168,7 +169,7 @@ static __global__ void digits_bgmw_kernel(const uint32_t *__restrict__ scalars, 
 // [t*w, t*w + wb) plus the bit below it; the top tile has wb = nbits % w (possibly 0) and is unsigned.
 // key = t * (2^(w-1) + 1) + |digit|; all tiles are emitted at once (ntiles entries per scalar).
 static __global__ void digits_booth_kernel(const uint32_t *__restrict__ scalars, size_t n, int nbits, int w, int ntiles,
-                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count, int digit_major) {
+                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count, int digit_major, uint32_t lo, uint32_t hi) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -186,7 +187,7 @@ static __global__ void digits_booth_kernel(const uint32_t *__restrict__ scalars,
         int mag = d < 0 ? -d : d;
         size_t slot = i * ntiles + t;
         uint32_t key = KEY_SKIP;
-        if (mag != 0) {
+        if (mag != 0 && (uint32_t)mag >= lo && (uint32_t)mag < hi) {
             key = (uint32_t)t * nbw + (uint32_t)mag;
             atomicAdd(&count[key], 1u);
         }
@@ -622,7 +623,7 @@ template <class F, bool DENSE, bool AFFINE_IN>
 static __global__ void __launch_bounds__(64) reduce_chunks_kernel(const void *__restrict__ bucket_points, const uint32_t *__restrict__ count,
                                                                    const uint32_t *__restrict__ item_start, const int *__restrict__ bucket_vals,
                                                                    const int *__restrict__ chunk_first, uint32_t nbw, uint32_t nwindows,
-                                                                   uint32_t vspan, uint32_t chunks_per_window, int d_max,
+                                                                   uint32_t vspan, uint32_t chunks_per_window, uint32_t chunk_lo, int d_max,
                                                                    xyzz_t<F> *__restrict__ out) {
     // chunk c of window w covers the buckets whose VALUE lies in (c*vspan, (c+1)*vspan]  (vspan a power of two).
     //   DENSE : value == local index           -> locals [c*vspan + 1, (c+1)*vspan]
@@ -631,7 +632,8 @@ static __global__ void __launch_bounds__(64) reduce_chunks_kernel(const void *__
     // sum(row0) + vspan * sum(row1).
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nwindows * chunks_per_window) return;
-    uint32_t w = t / chunks_per_window, c = t % chunks_per_window;
+    // this context owns chunks [chunk_lo, chunk_lo + chunks_per_window) of every window (all of them unless bucket-range sharded)
+    uint32_t w = t / chunks_per_window, cl = t % chunks_per_window, c = chunk_lo + cl;
     uint32_t lo, hi;
     if (DENSE) { lo = 1 + c * vspan; hi = min(nbw, lo + vspan); }
     else { lo = (uint32_t)chunk_first[c]; hi = (uint32_t)chunk_first[c + 1]; }
@@ -687,7 +689,7 @@ static __global__ void __launch_bounds__(64) reduce_chunks_kernel(const void *__
             if ((c >> bit) & 1) xyzz_add_cold(r, tmp);
         }
     }
-    size_t o = (size_t)w * 2 * chunks_per_window + c;
+    size_t o = (size_t)w * 2 * chunks_per_window + cl;
     out[o] = W;
     out[o + chunks_per_window] = r;
 }

@@ -1,4 +1,11 @@
-"""Multi-GPU plumbing: one process per GPU, contiguous point shards, one all-gather of partial points.
+"""Multi-GPU plumbing: one process per GPU, one all-gather of partial points.
+
+Two decompositions, both ending in the same gather + sum of G Jacobian partials:
+  * "points"  - rank g owns a contiguous shard of the points and its own table shard (memory / G); the bucket
+                reduction is repeated on every rank, so latency stops scaling once it dominates;
+  * "buckets" - every rank holds all points and tables and handles 1/G of the bucket-reduction chunks
+                (MsmContext.set_bucket_shard): accumulation AND reduction scale 1/G; the scalars are all-gathered
+                over NVLink when they arrive sharded from the host.
 
 MSM is a sum over points, so rank g owns points [g*n/G, (g+1)*n/G), builds its own table shard from its own
 P_i (no communication), reduces its scalars to ONE partial Jacobian point (144 B G1 / 288 B G2) on its GPU, and
@@ -33,6 +40,12 @@ def all_gather_partials(partial, world=None):
         dist.all_gather(parts, partial)
         out = torch.stack(parts)
     return out
+
+
+def all_gather_scalars(shard, full):
+    """NCCL all-gather of the per-rank scalar shards (uint8 CUDA tensors) into `full` (world * len(shard) bytes)."""
+    dist.all_gather_into_tensor(full, shard)
+    return full
 
 
 def msm_sharded(ctx, method, scalars_dev, partial_buf):
