@@ -287,8 +287,8 @@ def main():
     ap.add_argument("--method", type=int, default=1, choices=[1, 2, 3, 4])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard-config", default="auto", help="reference config used per shard when --gpus > 1 (auto: tuned for n/G)")
-    ap.add_argument("--shard", default="buckets", choices=["buckets", "points"],
-                    help="multi-GPU decomposition: bucket ranges with replicated tables (default) or point shards")
+    ap.add_argument("--shard", default="points", choices=["buckets", "points"],
+                    help="multi-GPU decomposition: point shards (default, faster at N<=8) or bucket ranges with replicated tables")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
