@@ -125,3 +125,38 @@ def test_g1_n21_sharded_over_8_contexts_with_shard_configs(M, golden):
     got = last.sum_partials_device(partials.data_ptr(), world)
     assert M.affine_serialize(1, got).hex() == golden["kat_appc"]["g1_n21"]
     last.close()
+
+
+ALL_CONFIGS = ["8", "9", "10", "11", "12", "13", "14", "15", "16", "16_beta", "17", "17_beta", "18", "19", "20", "20_beta", "21"]
+
+
+@pytest.mark.parametrize("cfgname", ALL_CONFIGS)
+def test_g1_size_sweep_all_reference_configs(M, cfgname):
+    """BASELINE configs[4]: every ches_config_files/config_file_n_exp_*.h row (n = 2^8 .. 2^21 incl. the _beta rows),
+    G1, CHES and its integral-scalar-conversion variant, plus BGMW95 (r - a trick rows included) up to n = 2^19;
+    checked against the closed form of the synthetic points."""
+    ctx = M.MsmContext(1, cfgname)
+    ctx.init_fix_point_list()
+    ctx.init_pippenger_CHES_q_over_5()
+    sc = O.gen_scalars(100 + len(cfgname) + ctx.cfg.n_exp, ctx.n)
+    exp, _ = O.closed_form(1, sc)
+    assert (ctx.msm(1, sc) == exp).all()
+    assert (ctx.msm(2, sc) == exp).all()
+    if ctx.cfg.n_exp <= 19:
+        ctx.init_pippenger_BGMW95()
+        assert (ctx.msm(3, sc) == exp).all()
+        assert (ctx.msm(4, sc) == exp).all()
+    ctx.close()
+
+
+@pytest.mark.parametrize("cfgname", ["8", "11", "13", "15", "16", "16_beta", "17"])
+def test_g2_size_sweep(M, cfgname):
+    ctx = M.MsmContext(2, cfgname)
+    ctx.init_fix_point_list()
+    ctx.init_pippenger_CHES_q_over_5()
+    ctx.init_pippenger_BGMW95()
+    sc = O.gen_scalars(200 + ctx.cfg.n_exp, ctx.n)
+    exp, _ = O.closed_form(2, sc)
+    for m in (1, 2, 3, 4):
+        assert (ctx.msm(m, sc) == exp).all(), m
+    ctx.close()
