@@ -86,6 +86,12 @@ int msmb200_set_bucket_shard(msmb200_ctx *ctx, int rank, int world);
  * inversion per batch (the reference's bulk_addition.c:51-143 analogue). Results are identical. */
 int msmb200_set_accumulator(msmb200_ctx *ctx, int mode);
 
+/* Bucket-reduction algorithm (replaces integrate_buckets_accumulation_d_CHES / integrate_buckets,
+ * src/multi_scalar.c:281-321): 0 = library default, 1 = chunked running sums with the reference's gap
+ * accumulators tmp_d[], 2 = digit splitting (bucket value = lo + 2^c * hi: two additions per bucket into
+ * per-digit lists, then per-bit lists and one Horner pass; no long dependent chain). Results are identical. */
+int msmb200_set_reducer(msmb200_ctx *ctx, int mode);
+
 /* FIX_POINTS_LIST (main_p1.cpp:47): upload caller's affine points (host memory, npoints entries). */
 int msmb200_set_points(msmb200_ctx *ctx, const void *points_affine_host);
 /* init_fix_point_list (main_p1.cpp:52-66): P_i = 2^(first+i+1) * G computed on the device. */
@@ -162,7 +168,8 @@ void msmb200_blst_p2s_add(void *ret_jacobian, const void *const points[], size_t
 int msmb200_test_field_op(int device, int field, int op, const void *a, const void *b, void *out, size_t n);
 /* point ops on n elements, group 1|2. op: 0 jac add-or-double (blst_p1_add_or_double), 1 jac double,
  * 2 xyzz += affine with sign flags (blst_p1xyzz_dadd_affine), 3 xyzz += xyzz (blst_p1xyzz_dadd),
- * 4 xyzz -> jacobian, 5 jacobian -> affine (blst_p1_to_affine) */
+ * 4 xyzz -> jacobian, 5 jacobian -> affine (blst_p1_to_affine), 6 / 7 quad-cooperative xyzz += xyzz / xyzz doubling
+ * (csrc/coop.cuh: four lanes per point), 8 one-thread xyzz doubling */
 int msmb200_test_point_op(int device, int group, int op, const void *a, const void *b, const unsigned char *flags,
                           void *out, size_t n);
 /* digit decomposition of the context's configuration for n scalars (host). kind 0: CHES -> out_key = bucket

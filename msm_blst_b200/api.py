@@ -68,6 +68,7 @@ def lib():
         L.msmb200_set_stream.argtypes = [vp, vp]
         L.msmb200_set_points.argtypes = [vp, vp]
         L.msmb200_set_accumulator.argtypes = [vp, ci]
+        L.msmb200_set_reducer.argtypes = [vp, ci]
         L.msmb200_set_bucket_shard.argtypes = [vp, ci, ci]
         L.msmb200_generate_fix_points.argtypes = [vp, sz]
         L.msmb200_table_build_ches.argtypes = [vp]
@@ -165,8 +166,8 @@ def test_field_op(field, op, a, b=None, device=0):
 
 def test_point_op(group, op, a, b=None, flags=None, device=0):
     A, J, X = AFF_BYTES[group], JAC_BYTES[group], XYZZ_BYTES[group]
-    in_b = [J, J, X, X, X, J][op]
-    out_b = [J, J, X, X, J, A][op]
+    in_b = [J, J, X, X, X, J, X, X, X][op]
+    out_b = [J, J, X, X, J, A, X, X, X][op]
     a = np.ascontiguousarray(a, dtype=np.uint8)
     n = a.nbytes // in_b
     out = np.empty(n * out_b, dtype=np.uint8)
@@ -215,6 +216,10 @@ class MsmContext:
     def set_accumulator(self, mode):
         """0 default, 1 XYZZ work items, 2 batch-affine rounds (identical results)."""
         self._ck(lib().msmb200_set_accumulator(self._h, int(mode)))
+
+    def set_reducer(self, mode):
+        """0 default, 1 chunked running sums (reference's tmp_d[] form), 2 digit splitting (identical results)."""
+        self._ck(lib().msmb200_set_reducer(self._h, int(mode)))
 
     def set_bucket_shard(self, rank, world):
         """Bucket-range sharding: this context (holding ALL points) handles slice `rank` of `world` of the buckets."""

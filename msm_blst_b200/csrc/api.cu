@@ -3,6 +3,7 @@
 // every computation is a CUDA kernel in msm_kernels.cuh. No CPU fallback exists: CUDA errors are returned.
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include "engine.hpp"
@@ -50,6 +51,115 @@ uint32_t pick_vspan_host(size_t max_value, uint32_t nwindows) {
     return v;
 }
 
+// ---- digit-splitting reduction plan (see list_sum_kernel) ----
+// Quads per list for the cooperative list sums: a single warp per SM sub-partition runs at about half the pipe rate,
+// so up to 2 warps per sub-partition are free; beyond that the time grows with the number of warps.
+static uint32_t pick_quads(size_t total_lists, double avg_len, int subparts) {
+    uint32_t best = 8;
+    double best_cost = 1e300;
+    for (uint32_t tq = 8; tq >= 1; tq >>= 1) {
+        double warps = std::ceil((double)total_lists * tq / 8.0);
+        double load = std::max(2.0, std::ceil(warps / (double)subparts));
+        double chain = std::max(1.0, std::ceil(avg_len / tq) - 1.0 + std::log2((double)tq));
+        double cost = load * chain;
+        if (cost < best_cost) { best_cost = cost; best = tq; }
+    }
+    return best;
+}
+static int upload_list_plan(Ctx *c, ListPlan &lp, const std::vector<uint32_t> &start, const std::vector<uint32_t> &idx) {
+    lp.nlists = (uint32_t)start.size() - 1;
+    lp.members = idx.size();
+    if (ensure(c, lp.start, start.size() * 4) || ensure(c, lp.idx, (idx.size() + 1) * 4)) return MSMB200_ECUDA;
+    MSM_CUDA(c, cudaMemcpy(lp.start.p, start.data(), start.size() * 4, cudaMemcpyHostToDevice));
+    if (!idx.empty()) MSM_CUDA(c, cudaMemcpy(lp.idx.p, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice));
+    return MSMB200_OK;
+}
+void free_reduce_plan(ReducePlan &plan) {
+    for (ListPlan *lp : {&plan.s1, &plan.s1b, &plan.s2a, &plan.s2b})
+        for (DevBuf *b : {&lp->start, &lp->idx})
+            if (b->p) { cudaFree(b->p); b->p = nullptr; b->bytes = 0; }
+    plan.valid = false;
+}
+// Cuts every list of (start, idx) into slices of at most `slice` members. Returns the sliced lists (same idx order) in
+// (start_s) and, per original list, the contiguous run of its slices as a second-level plan (start_g, idx_g).
+static void slice_lists(const std::vector<uint32_t> &start, uint32_t slice, std::vector<uint32_t> &start_s, std::vector<uint32_t> &start_g,
+                        std::vector<uint32_t> &idx_g) {
+    start_s.assign(1, 0);
+    start_g.assign(1, 0);
+    idx_g.clear();
+    for (size_t i = 0; i + 1 < start.size(); i++) {
+        for (uint32_t e = start[i]; e < start[i + 1]; e += slice) {
+            idx_g.push_back((uint32_t)start_s.size() - 1);
+            start_s.push_back(std::min(start[i + 1], e + slice));
+        }
+        start_g.push_back((uint32_t)idx_g.size());
+    }
+}
+int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, uint32_t nwindows) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const int subparts = 4 * sms;
+    const uint32_t maxv = nbw > 1 ? (values ? (uint32_t)values[nbw - 1] : (uint32_t)(nbw - 1)) : 1u;
+    uint32_t V = 0;
+    while (V < 32 && (maxv >> V) != 0) V++;
+    const uint32_t c_lo = std::max<uint32_t>(1, (V + 1) / 2);
+    const uint32_t nlo = (1u << c_lo) - 1, nhi = maxv >> c_lo;
+    uint32_t chi = 0;
+    while ((nhi >> chi) != 0) chi++;
+    // digit lists: list (lo digit d) = d - 1, list (hi digit d) = nlo + d - 1; members are local bucket indices
+    const uint32_t nl1 = nlo + nhi;
+    std::vector<uint32_t> start(nl1 + 1, 0), idx;
+    for (size_t l = 1; l < nbw; l++) {
+        uint32_t v = values ? (uint32_t)values[l] : (uint32_t)l;
+        if (v & nlo) start[(v & nlo) - 1 + 1]++;
+        if (v >> c_lo) start[nlo + (v >> c_lo) - 1 + 1]++;
+    }
+    for (uint32_t i = 0; i < nl1; i++) start[i + 1] += start[i];
+    idx.resize(start[nl1]);
+    {
+        std::vector<uint32_t> cur(start.begin(), start.end() - 1);
+        for (size_t l = 1; l < nbw; l++) {
+            uint32_t v = values ? (uint32_t)values[l] : (uint32_t)l;
+            if (v & nlo) idx[cur[(v & nlo) - 1]++] = (uint32_t)l;
+            if (v >> c_lo) idx[cur[nlo + (v >> c_lo) - 1]++] = (uint32_t)l;
+        }
+    }
+    // stage 1: one LANE per slice of a digit list, slices sized so that ~3 warps per SM sub-partition have equal work
+    // (perfect balance whatever the list lengths); stage 1b: the slices of each digit list, summed by quads
+    uint32_t slice1 = (uint32_t)std::min<size_t>(32, std::max<size_t>(2, idx.size() * nwindows / ((size_t)3 * subparts * 32)));
+    if (const char *e = getenv("MSMB200_SLICE1")) slice1 = (uint32_t)std::max(1, atoi(e));
+    std::vector<uint32_t> start_s, start_g, idx_g;
+    slice_lists(start, slice1, start_s, start_g, idx_g);
+    int rc = upload_list_plan(c, plan.s1, start_s, idx);
+    if (rc) return rc;
+    plan.s1.tl = 1;
+    rc = upload_list_plan(c, plan.s1b, start_g, idx_g);
+    if (rc) return rc;
+    plan.s1b.tl = pick_quads((size_t)nl1 * nwindows, nl1 ? (double)idx_g.size() / nl1 : 1.0, subparts);
+    // stage 2a: bit k of the lo (k < c_lo) or hi (k >= c_lo) digit value, cut into slices of SLICE members; 2b: bit lists
+    const uint32_t SLICE = 32, nbits = c_lo + chi;
+    std::vector<uint32_t> start_a(1, 0), idx_a, start_as, start_b, idx_b;
+    for (uint32_t k = 0; k < nbits; k++) {
+        const bool hi = k >= c_lo;
+        const uint32_t bit = hi ? k - c_lo : k, vmax = hi ? nhi : nlo, base = hi ? nlo : 0;
+        for (uint32_t v = 1; v <= vmax; v++)
+            if ((v >> bit) & 1) idx_a.push_back(base + v - 1);
+        start_a.push_back((uint32_t)idx_a.size());
+    }
+    slice_lists(start_a, SLICE, start_as, start_b, idx_b);
+    rc = upload_list_plan(c, plan.s2a, start_as, idx_a);
+    if (rc) return rc;
+    plan.s2a.tl = pick_quads((size_t)plan.s2a.nlists * nwindows, plan.s2a.nlists ? (double)idx_a.size() / plan.s2a.nlists : 1.0, subparts);
+    rc = upload_list_plan(c, plan.s2b, start_b, idx_b);
+    if (rc) return rc;
+    plan.s2b.tl = pick_quads((size_t)nbits * nwindows, nbits ? (double)idx_b.size() / nbits : 1.0, subparts);
+    plan.c_lo = c_lo;
+    plan.nbits_w = nbits;
+    plan.key_nbw = nbw;
+    plan.valid = true;
+    return MSMB200_OK;
+}
+
 static int ctx_init_common(Ctx *c, int group, int device) {
     c->group = group;
     c->device = device;
@@ -69,8 +179,9 @@ static void ctx_free(Ctx *c) {
     DevBuf *bufs[] = {&c->scalars, &c->keys, &c->vals, &c->sorted, &c->count, &c->packed, &c->scanned, &c->tile_sums, &c->seg_start,
                       &c->item_start, &c->cursor, &c->item_begin, &c->item_cnt, &c->order, &c->len_hist, &c->len_start, &c->len_cursor,
                       &c->partial, &c->chunk_a, &c->chunk_b, &c->result, &c->flat, &c->signs, &c->pidx, &c->heavy, &c->bucket_of0, &c->bo_a, &c->bo_b,
-                      &c->pts_a, &c->pts_b, &c->base_a, &c->base_b, &c->tile_sums2, &c->maxcount};
+                      &c->pts_a, &c->pts_b, &c->base_a, &c->base_b, &c->tile_sums2, &c->maxcount, &c->red_a, &c->red_b, &c->red_c, &c->red_d};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    free_reduce_plan(c->plan_ches); free_reduce_plan(c->plan_bgmw); free_reduce_plan(c->plan_pip);
     void *ptrs[] = {c->d_bucket_vals, c->d_v2i, c->d_dtab, c->d_chunk_first, c->d_points, c->d_table_ches, c->d_table_bgmw};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_result) cudaFreeHost(c->h_result);
@@ -178,6 +289,8 @@ int msmb200_ctx_create(msmb200_ctx **out, int group, const msmb200_config *cfg, 
     CREATE_CUDA(cudaMemcpy(c->d_v2i, v2i.data(), v2i.size() * sizeof(int), cudaMemcpyHostToDevice));
     CREATE_CUDA(cudaMemcpy(c->d_dtab, dtab.data(), dtab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 #undef CREATE_CUDA
+    rc = build_reduce_plan(c, c->plan_ches, c->bucket_set.data(), c->bucket_set.size(), 1);
+    if (rc) { g_create_err = c->err; ctx_free(c); return rc; }
     *out = x;
     return MSMB200_OK;
 }
@@ -208,6 +321,11 @@ int msmb200_set_bucket_shard(msmb200_ctx *ctx, int rank, int world) {
 int msmb200_set_accumulator(msmb200_ctx *ctx, int mode) {
     if (!ctx || mode < 0 || mode > 2) return MSMB200_EINVAL;
     C(ctx)->accum_mode = mode;
+    return MSMB200_OK;
+}
+int msmb200_set_reducer(msmb200_ctx *ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 2) return MSMB200_EINVAL;
+    C(ctx)->reduce_mode = mode;
     return MSMB200_OK;
 }
 int msmb200_set_points(msmb200_ctx *ctx, const void *points_affine_host) {
@@ -378,10 +496,10 @@ static int point_fn(const void *a, const void *b, const unsigned char *flags, vo
     return ops->point_op(p->op, a, b, flags, out, p->n);
 }
 int msmb200_test_point_op(int device, int group, int op, const void *a, const void *b, const unsigned char *flags, void *out, size_t n) {
-    if ((group != 1 && group != 2) || op < 0 || op > 5 || !a || !out || n == 0) return MSMB200_EINVAL;
+    if ((group != 1 && group != 2) || op < 0 || op > 8 || !a || !out || n == 0) return MSMB200_EINVAL;
     const GroupOps *ops = group == 1 ? group_ops_g1() : group_ops_g2();
     size_t A = ops->aff_bytes, J = ops->jac_bytes, X = ops->xyzz_bytes;
-    size_t ab[6] = {J, J, X, X, X, J}, bb[6] = {J, 0, A, X, 0, 0}, ob[6] = {J, J, X, X, J, A};
+    size_t ab[9] = {J, J, X, X, X, J, X, X, X}, bb[9] = {J, 0, A, X, 0, 0, X, 0, 0}, ob[9] = {J, J, X, X, J, A, X, X, X};
     if (bb[op] && !b) return MSMB200_EINVAL;
     PointArg arg{group, op, n};
     return with_device_buffers(device, a, n * ab[op], bb[op] ? b : nullptr, n * bb[op], flags, n, out, n * ob[op], point_fn, &arg);
@@ -471,12 +589,15 @@ static void shim_tile(int group, void *ret, const void *const points[], size_t n
         cudaMemcpyAsync(dv, v2i, v2i_len * 4, cudaMemcpyHostToDevice, c->stream);
         cudaMemcpyAsync(dcf, cf.data(), cf.size() * 4, cudaMemcpyHostToDevice, c->stream);
     }
+    ReducePlan plan;  // rebuilt per call: the shim is a compatibility path, the context API caches its plans
+    if (build_reduce_plan(c, plan, bucket_set_ascend, nbuckets, 1)) shim_fail(c, "blst_pN_tile_pippenger");
     if (c->ops->tile(c, dp, (const int *)dsc, (const unsigned char *)dsg, (const uint32_t *)dpi, npoints, (const int *)dv, (const int *)dbs, nbuckets,
-                     d_max, (const int *)dcf, vspan, nchunks, dj))
+                     d_max, (const int *)dcf, vspan, nchunks, &plan, dj))
         shim_fail(c, "blst_pN_tile_pippenger");
     cudaMemcpyAsync(ret, dj, jb, cudaMemcpyDeviceToHost, c->stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pN_tile_pippenger"); }
     cudaFree(dp); cudaFree(dsc); cudaFree(dsg); cudaFree(dpi); cudaFree(dj); cudaFree(dbs); cudaFree(dv); cudaFree(dcf);
+    free_reduce_plan(plan);
 }
 
 // blst_pNs_add (src/bulk_addition.c:145-164): sum of npoints affine points. One bucket holding every point, so the
@@ -498,7 +619,7 @@ static void shim_points_add(int group, void *ret, const void *const points[], si
     cudaMemcpyAsync(dsc, ones.data(), npoints * 4, cudaMemcpyHostToDevice, c->stream);
     cudaMemsetAsync(dsg, 0, npoints, c->stream);
     cudaMemcpyAsync(dpi, pidx.data(), npoints * 4, cudaMemcpyHostToDevice, c->stream);
-    if (c->ops->tile(c, dp, (const int *)dsc, (const unsigned char *)dsg, (const uint32_t *)dpi, npoints, nullptr, nullptr, 2, 1, nullptr, 8, 1, dj))
+    if (c->ops->tile(c, dp, (const int *)dsc, (const unsigned char *)dsg, (const uint32_t *)dpi, npoints, nullptr, nullptr, 2, 1, nullptr, 8, 1, nullptr, dj))
         shim_fail(c, "blst_pNs_add");
     cudaMemcpyAsync(ret, dj, jb, cudaMemcpyDeviceToHost, c->stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pNs_add"); }

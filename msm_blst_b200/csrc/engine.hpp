@@ -19,6 +19,24 @@ struct DevBuf {
 
 struct GroupOps;
 
+// Static plan of the digit-splitting bucket reduction (list_sum_kernel in msm_kernels.cuh). Built once on the host
+// from the bucket values of one window; identical for every window of a layout.
+struct ListPlan {
+    DevBuf start, idx;      // start[nlists + 1], idx[members]: members of list i are idx[start[i] .. start[i+1])
+    uint32_t nlists = 0;
+    uint32_t tl = 1;        // team per list: lanes (list_sum_kernel) or quads (list_sum_coop_kernel), a power of two
+    size_t members = 0;
+};
+struct ReducePlan {
+    bool valid = false;
+    size_t key_nbw = 0;     // cache key: number of buckets per window and largest value (dense plans)
+    uint32_t c_lo = 0;      // value = lo + 2^c_lo * hi
+    uint32_t nbits_w = 0;   // bit positions per window after stage 2
+    // stage 1: slices of the (digit, value) lists over buckets, one lane each; 1b: slices -> digit lists;
+    // 2a: (bit, slice) lists over the digit sums; 2b: slices -> bit lists
+    ListPlan s1, s1b, s2a, s2b;
+};
+
 struct Ctx {
     int group = 0;
     msmb200_config cfg{};
@@ -48,6 +66,10 @@ struct Ctx {
     DevBuf scalars, keys, vals, sorted, count, packed, scanned, tile_sums, seg_start, item_start, cursor,
         item_begin, item_cnt, order, len_hist, len_start, len_cursor, partial, chunk_a, chunk_b, result,
         flat, signs, pidx, heavy, bucket_of0, bo_a, bo_b, pts_a, pts_b, base_a, base_b, tile_sums2, maxcount;
+    ReducePlan plan_ches, plan_bgmw, plan_pip;  // digit-splitting reduction plans (sparse CHES set / dense windows)
+    uint32_t plan_bgmw_windows = 0, plan_pip_windows = 0;
+    DevBuf red_a, red_b, red_c, red_d;          // outputs of the list-sum stages
+    int reduce_mode = 0;                        // 0 = default (digit splitting), 1 = chunked running sums
     std::vector<int> h_chunk_first;   // host copy of d_chunk_first
     int shard_rank = 0, shard_world = 1;  // bucket-range sharding: this context owns 1/world of the reduction chunks
     int accum_mode = 0;  // 0 = default, 1 = XYZZ work items, 2 = batch-affine rounds
@@ -70,7 +92,7 @@ struct GroupOps {
     // generic tile: device arrays of bucket index (or value when v2i given) / sign / point index into d_table
     int (*tile)(Ctx *, const void *d_table, const int *d_bvals, const unsigned char *d_signs, const uint32_t *d_pidx,
                 size_t m, const int *d_v2i, const int *d_bucket_vals, size_t nbuckets, int d_max, const int *d_chunk_first, uint32_t vspan,
-                uint32_t nchunks, void *d_out_jac);
+                uint32_t nchunks, const ReducePlan *plan, void *d_out_jac);
     int (*pippenger)(Ctx *, const void *d_points, size_t npoints, const void *d_scalars, int nbits, void *d_out_jac,
                      bool want_affine);
     int (*field_op)(int field, int op, const void *a, const void *b, void *out, size_t n);
@@ -85,6 +107,9 @@ const GroupOps *group_ops_g2();
 // chunk_first[c] = first index l >= 1 with values[l] > c * vspan (c = 0..nchunks), values ascending
 std::vector<int> build_chunk_first(const int *values, size_t count, uint32_t vspan, uint32_t *nchunks_out);
 uint32_t pick_vspan_host(size_t max_value, uint32_t nwindows);
+// values: ascending bucket values of one window (values[0] = 0 unused) or nullptr for dense (value == index)
+int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, uint32_t nwindows);
+void free_reduce_plan(ReducePlan &plan);
 int ctx_fail(Ctx *c, int code, const std::string &msg);
 int ensure(Ctx *c, DevBuf &b, size_t bytes);
 

@@ -26,7 +26,22 @@ struct Layout {
     uint32_t vspan;          // value span of one reduction chunk (power of two)
     uint32_t nchunks;        // reduction chunks per window (all of them)
     uint32_t chunk_lo = 0, chunk_cnt = 0;  // the slice this context reduces (bucket-range sharding); cnt 0 = all
+    const ReducePlan *plan = nullptr;      // digit-splitting reduction plan (nullptr: chunked running sums only)
 };
+
+static inline bool use_split_reduce(const Ctx *c, const Layout &L) {
+    int mode = c->reduce_mode;
+    if (const char *e = getenv("MSMB200_REDUCE")) mode = atoi(e);
+    return L.plan && L.plan->valid && mode != 1 && (L.nwindows == 1 || L.plan->nbits_w <= L.wbits);
+}
+// dense plans (value == local index) are built on first use and cached per (buckets per window, windows)
+static inline const ReducePlan *dense_plan(Ctx *c, ReducePlan &slot, size_t nbw, uint32_t nwindows, uint32_t *key_windows) {
+    if (!slot.valid || slot.key_nbw != nbw || *key_windows != nwindows) {
+        if (build_reduce_plan(c, slot, nullptr, nbw, nwindows) != MSMB200_OK) return nullptr;
+        *key_windows = nwindows;
+    }
+    return &slot;
+}
 
 // slice of the reduction chunks owned by this context and the matching local bucket-index range [lo, hi)
 static inline void shard_slice(const Ctx *c, uint32_t nchunks, uint32_t *chunk_lo, uint32_t *chunk_cnt) {
@@ -161,6 +176,47 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     }
     MSM_CUDA(c, cudaEventRecord(c->ev[3], st));
     // ---- reduce ----
+    if (use_split_reduce(c, L)) {
+        const ReducePlan &P = *L.plan;
+        const uint32_t nw = L.nwindows;
+        if (ensure(c, c->red_a, (size_t)nw * P.s1.nlists * sizeof(xyzz_t<F>) + 64) || ensure(c, c->red_b, (size_t)nw * P.s1b.nlists * sizeof(xyzz_t<F>) + 64) ||
+            ensure(c, c->red_c, (size_t)nw * P.s2a.nlists * sizeof(xyzz_t<F>) + 64) || ensure(c, c->red_d, (size_t)nw * P.s2b.nlists * sizeof(xyzz_t<F>) + 64))
+            return MSMB200_ECUDA;
+        // stage 1: one lane per slice of a digit list, gathering the bucket sums
+        if (P.s1.nlists) {
+            const unsigned g1 = blocks_for((size_t)nw * P.s1.nlists, 128);
+            if (batch_affine)
+                list_sum_kernel<F, 1><<<g1, 128, 0, st>>>(bucket_points, count, bucket_point_index, L.nbw, (const uint32_t *)P.s1.start.p,
+                                                          (const uint32_t *)P.s1.idx.p, P.s1.nlists, nw, 1, (xyzz_t<F> *)c->red_a.p);
+            else
+                list_sum_kernel<F, 0><<<g1, 128, 0, st>>>(bucket_points, count, bucket_point_index, L.nbw, (const uint32_t *)P.s1.start.p,
+                                                          (const uint32_t *)P.s1.idx.p, P.s1.nlists, nw, 1, (xyzz_t<F> *)c->red_a.p);
+        }
+        // stages 1b, 2a, 2b: quad-cooperative list sums over dense arrays
+        auto coop = [&](const ListPlan &lp, const void *src, uint32_t in_stride, void *dst) {
+            list_sum_coop_kernel<FC><<<blocks_for((size_t)nw * lp.nlists * lp.tl * 4, 128), 128, 0, st>>>(
+                (const xyzz_t<FC> *)src, in_stride, (const uint32_t *)lp.start.p, (const uint32_t *)lp.idx.p, lp.nlists, nw, lp.tl, (xyzz_t<FC> *)dst);
+        };
+        coop(P.s1b, c->red_a.p, P.s1.nlists, c->red_b.p);
+        coop(P.s2a, c->red_b.p, P.s1b.nlists, c->red_c.p);
+        coop(P.s2b, c->red_c.p, P.s2a.nlists, c->red_d.p);
+        c->launches += 4;
+        MSM_CUDA(c, cudaEventRecord(c->ev[4], st));
+        jac_t<F> *d_jac = d_out_jac ? (jac_t<F> *)d_out_jac : (jac_t<F> *)c->result.p;
+        aff_t<F> *d_aff = (aff_t<F> *)((char *)c->result.p + sizeof(jac_t<F>));
+        if (getenv("MSMB200_SERIAL_FINALIZE"))
+            bits_finalize_kernel<FC><<<1, 32, 0, st>>>((const xyzz_t<FC> *)c->red_d.p, nw, P.nbits_w, L.wbits, (jac_t<FC> *)d_jac,
+                                                       want_affine ? (aff_t<FC> *)d_aff : nullptr);
+        else
+            bits_finalize_coop_kernel<FC><<<1, 32, 0, st>>>((const xyzz_t<FC> *)c->red_d.p, nw, P.nbits_w, L.wbits, (jac_t<FC> *)d_jac,
+                                                            want_affine ? (aff_t<FC> *)d_aff : nullptr);
+        c->launches += 1;
+        if (want_affine) MSM_CUDA(c, cudaMemcpyAsync(c->h_result, d_aff, sizeof(aff_t<F>), cudaMemcpyDeviceToHost, st));
+        MSM_CUDA(c, cudaEventRecord(c->ev[5], st));
+        MSM_CUDA(c, cudaGetLastError());
+        if (want_affine) MSM_CUDA(c, cudaStreamSynchronize(st));
+        return MSMB200_OK;
+    }
     const uint32_t cpw = L.chunk_cnt ? L.chunk_cnt : L.nchunks;
     size_t nchunks = (size_t)cpw * L.nwindows;
     if (ensure(c, c->chunk_a, 2 * nchunks * sizeof(xyzz_t<F>)) || ensure(c, c->chunk_b, (2 * ((size_t)cpw / 4 + 2) * L.nwindows + 2) * sizeof(xyzz_t<F>)))
@@ -238,6 +294,7 @@ static int pippenger_impl(Ctx *c, const void *d_points, size_t npoints, const vo
     MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
     Layout L{m, nbw, (uint32_t)tiles, (uint32_t)w, nullptr, 1, nullptr, vs, nch};
     L.chunk_lo = clo; L.chunk_cnt = ccnt;
+    L.plan = dense_plan(c, c->plan_pip, nbw, (uint32_t)tiles, &c->plan_pip_windows);
     return run_buckets<F, FC>(c, L, (const aff_t<F> *)d_points, d_out_jac, want_affine);
 }
 
@@ -276,6 +333,7 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
         MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
         Layout L{m, (uint32_t)nb, 1, 0, c->d_bucket_vals, cfg.d, c->d_chunk_first, c->red_vspan, c->red_nchunks};
         L.chunk_lo = clo; L.chunk_cnt = ccnt;
+        L.plan = &c->plan_ches;
         return run_buckets<F, FC>(c, L, (const aff_t<F> *)c->d_table_ches, d_out_jac, want_affine);
     }
     if (method == MSMB200_BGMW95) {
@@ -295,6 +353,7 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
         MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
         Layout L{m, nbw, 1, 0, nullptr, 1, nullptr, vs, nch};
         L.chunk_lo = clo; L.chunk_cnt = ccnt;
+        L.plan = dense_plan(c, c->plan_bgmw, nbw, 1, &c->plan_bgmw_windows);
         return run_buckets<F, FC>(c, L, (const aff_t<F> *)c->d_table_bgmw, d_out_jac, want_affine);
     }
     return ctx_fail(c, MSMB200_EINVAL, "unknown method");
@@ -305,7 +364,7 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
 template <class F, class FC>
 static int tile_impl(Ctx *c, const void *d_table, const int *d_bvals, const unsigned char *d_signs, const uint32_t *d_pidx, size_t m,
                      const int *d_v2i, const int *d_bucket_vals, size_t nbuckets, int d_max, const int *d_chunk_first, uint32_t vspan,
-                     uint32_t nchunks, void *d_out_jac) {
+                     uint32_t nchunks, const ReducePlan *plan, void *d_out_jac) {
     cudaStream_t st = c->stream;
     c->launches = 0;
     MSM_CUDA(c, cudaEventRecord(c->ev[0], st));
@@ -316,6 +375,7 @@ static int tile_impl(Ctx *c, const void *d_table, const int *d_bvals, const unsi
     c->launches += 1;
     MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
     Layout L{m, (uint32_t)nbuckets, 1, 0, d_bucket_vals, d_max, d_chunk_first, vspan, nchunks};
+    L.plan = plan;
     return run_buckets<F, FC>(c, L, (const aff_t<F> *)d_table, d_out_jac, false);
 }
 
@@ -414,6 +474,7 @@ template <class F> static int digits_impl(Ctx *c, int kind, const void *d_scalar
 
 template <class F, class FC> static int point_op_impl(int op, const void *a, const void *b, const unsigned char *flags, void *out, size_t n) {
     if (op == 2 || op == 3) point_op_xyzz_kernel<F><<<blocks_for(n, 128), 128>>>(op, a, b, flags, out, n);
+    else if (op == 6 || op == 7) point_op_coop_kernel<FC><<<blocks_for(4 * n, 128), 128>>>(op, a, b, out, n);
     else point_op_misc_kernel<FC><<<blocks_for(n, 128), 128>>>(op, a, b, out, n);
     return cudaGetLastError() == cudaSuccess ? 0 : MSMB200_ECUDA;
 }

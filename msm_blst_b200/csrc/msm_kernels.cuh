@@ -10,6 +10,7 @@
 #pragma once
 #include <cstdint>
 #include "ec.cuh"
+#include "coop.cuh"
 
 namespace msmb200 {
 
@@ -746,6 +747,216 @@ static __global__ void __launch_bounds__(256) tree_tail_kernel(xyzz_t<F> *in, ui
 }
 
 // ------------------------------------------------------------------------------------------------
+// [4'] bucket reduction by DIGIT SPLITTING (default). Computes the same sum as the reference's
+// POINTonE1_integrate_buckets_accumulation_d_CHES (src/multi_scalar.c:301-321) / integrate_buckets (:281-297),
+// i.e. sum_l val(l) * S_l per window, but without any long running-sum chain:
+//   stage 1   val = lo + 2^c_lo * hi: every bucket sum is added to the list of its lo digit and to the list of
+//             its hi digit (2 additions per bucket, the reference's count) -> two dense arrays of <= 2^11 sums;
+//   stage 2   every dense entry v is added to the list of each set bit of v (sliced, then the slices summed);
+//   final     Horner over the bit positions (bits_finalize_kernel).
+// All three stages are the SAME kernel: a static plan (built once on the host from the bucket values, ReducePlan in
+// engine.hpp) names the members of every list; a team of `tl` lanes strides over one list and folds its partial
+// sums with a shuffle tree. Lists have near-equal lengths, so all lanes of the machine are busy.
+//   MODE 0: members are buckets, sums are XYZZ partials at src[item_start[b]] (skipped when count[b] == 0)
+//   MODE 1: same, but the sums are affine points (batch-affine accumulation)
+//   MODE 2: members index a dense XYZZ array (output of the previous stage)
+// ------------------------------------------------------------------------------------------------
+template <class F> __device__ __forceinline__ void xyzz_shfl_down(xyzz_t<F> &r, const xyzz_t<F> &a, int o) {
+    f_shfl_down(r.x, a.x, o);
+    f_shfl_down(r.y, a.y, o);
+    f_shfl_down(r.zzz, a.zzz, o);
+    f_shfl_down(r.zz, a.zz, o);
+}
+template <class F, int MODE>
+static __global__ void __launch_bounds__(128) list_sum_kernel(const void *__restrict__ src, const uint32_t *__restrict__ count,
+                                                              const uint32_t *__restrict__ item_start, uint32_t in_stride,
+                                                              const uint32_t *__restrict__ start, const uint32_t *__restrict__ idx,
+                                                              uint32_t nlists, uint32_t nwindows, uint32_t tl, xyzz_t<F> *__restrict__ out) {
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gl = gt / tl, sl = gt % tl;  // tl is a power of two <= 32: teams never straddle a warp
+    const uint32_t total = nlists * nwindows;
+    xyzz_t<F> acc;
+    xyzz_set_inf(acc);
+    if (gl < total) {
+        const uint32_t w = gl / nlists, li = gl % nlists;
+        const uint32_t e1 = start[li + 1];
+#pragma unroll 1
+        for (uint32_t e = start[li] + sl; e < e1; e += tl) {
+            const size_t b = (size_t)w * in_stride + idx[e];
+            if (MODE == 2) {
+                xyzz_t<F> s;
+                load_xyzz(s, (const xyzz_t<F> *)src + b);
+                xyzz_add(acc, s);
+            } else if (count[b] != 0) {
+                if (MODE == 1) {
+                    aff_t<F> a;
+                    load_affine(a, (const aff_t<F> *)src, item_start[b]);
+                    xyzz_add_affine(acc, a, false);
+                } else {
+                    xyzz_t<F> s;
+                    load_xyzz(s, (const xyzz_t<F> *)src + item_start[b]);
+                    xyzz_add(acc, s);
+                }
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t o = tl >> 1; o > 0; o >>= 1) {
+        xyzz_t<F> other;
+        xyzz_shfl_down(other, acc, (int)o);
+        if (sl + o >= tl) xyzz_set_inf(other);  // partner belongs to another team (or wrapped): add nothing
+        xyzz_add_cold(acc, other);
+        __syncwarp();
+    }
+    if (gl < total && sl == 0) out[gl] = acc;
+}
+
+// Horner over bit positions: L[w * nbits_w + k] is the sum of everything whose value has bit k set in window w, i.e.
+// the result is sum_w sum_k 2^(w * wbits + k) L[w][k]. Replaces the tail of integrate_buckets and the outer loop of
+// POINTonE1s_mult_pippenger (src/multi_scalar.c:565-575), xyzz_to_Jacobian and (want_affine) blst_p1_to_affine.
+template <class F>
+static __global__ void bits_finalize_kernel(const xyzz_t<F> *__restrict__ L, uint32_t nwindows, uint32_t nbits_w, uint32_t wbits,
+                                            jac_t<F> *__restrict__ out_jac, aff_t<F> *__restrict__ out_aff) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    xyzz_t<F> acc;
+    xyzz_set_inf(acc);
+    uint32_t pos_prev = 0;
+    bool first = true;
+#pragma unroll 1
+    for (int w = (int)nwindows - 1; w >= 0; w--) {
+#pragma unroll 1
+        for (int k = (int)nbits_w - 1; k >= 0; k--) {
+            const uint32_t pos = (uint32_t)w * wbits + (uint32_t)k;
+            if (!first && !xyzz_is_inf(acc)) {
+#pragma unroll 1
+                for (uint32_t d = pos; d < pos_prev; d++) { xyzz_t<F> a = acc; xyzz_double(acc, a); }
+            }
+            first = false;
+            pos_prev = pos;
+            xyzz_t<F> s;
+            load_xyzz(s, L + (size_t)w * nbits_w + k);
+            xyzz_add_cold(acc, s);
+        }
+    }
+    jac_t<F> j;
+    if (xyzz_is_inf(acc)) jac_set_inf(j);
+    else xyzz_to_jac(j, acc);
+    if (out_jac) *out_jac = j;
+    if (out_aff) {
+        aff_t<F> a;
+        jac_to_affine(a, j);
+        *out_aff = a;
+    }
+}
+
+// Quad-cooperative variants for the small stages (coop.cuh): list sums over a dense XYZZ array with one QUAD per team
+// slot (tq quads per list, tq a power of two <= 8), and the Horner pass with the bit positions spread over the 8
+// quads of one warp. Control flow is warp-uniform; trip counts are the warp maximum and idle quads add infinity.
+template <class F>
+static __global__ void __launch_bounds__(128) list_sum_coop_kernel(const xyzz_t<F> *__restrict__ src, uint32_t in_stride,
+                                                                   const uint32_t *__restrict__ start, const uint32_t *__restrict__ idx,
+                                                                   uint32_t nlists, uint32_t nwindows, uint32_t tq, xyzz_t<F> *__restrict__ out) {
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gq = gt >> 2, gl = gq / tq, sq = gq % tq;
+    const uint32_t total = nlists * nwindows;
+    const bool live = gl < total;
+    uint32_t e0 = 0, e1 = 0;
+    size_t base = 0;
+    if (live) {
+        const uint32_t w = gl / nlists, li = gl % nlists;
+        e0 = start[li] + sq;
+        e1 = start[li + 1];
+        base = (size_t)w * in_stride;
+    }
+    const uint32_t my_iters = e1 > e0 ? (e1 - e0 + tq - 1) / tq : 0u;
+    const uint32_t iters = __reduce_max_sync(0xffffffffu, my_iters);
+    xyzz_t<F> acc;
+    xyzz_set_inf(acc);
+#pragma unroll 1
+    for (uint32_t it = 0; it < iters; it++) {
+        xyzz_t<F> s;
+        xyzz_set_inf(s);
+        const uint32_t e = e0 + it * tq;
+        if (e < e1) load_xyzz(s, src + base + idx[e]);
+        if (it == 0) acc = s;
+        else quad_xyzz_add(acc, s);
+    }
+#pragma unroll 1
+    for (uint32_t o = tq >> 1; o > 0; o >>= 1) {
+        xyzz_t<F> other;
+        xyzz_shfl_down_any(other, acc, (int)(4 * o));
+        if (sq + o >= tq) xyzz_set_inf(other);
+        quad_xyzz_add(acc, other);
+    }
+    if (live && sq == 0 && (threadIdx.x & 3) == 0) out[gl] = acc;
+}
+
+template <class F> __device__ __forceinline__ void quad_xyzz_shift(xyzz_t<F> &acc, uint32_t my_doublings) {
+    const uint32_t maxd = __reduce_max_sync(0xffffffffu, my_doublings);
+#pragma unroll 1
+    for (uint32_t i = 0; i < maxd; i++) {
+        xyzz_t<F> d;
+        quad_xyzz_double(d, acc);
+        if (i < my_doublings) acc = d;
+    }
+}
+// One warp. Entries in descending bit position: t = 0..G-1 <-> (w = nwindows-1 - t / nbits_w, k = nbits_w-1 - t % nbits_w),
+// position w * wbits + k. Quad j runs Horner over entries [j*len, (j+1)*len); the 8 partial results are combined by a
+// tree in which the quad holding the higher positions is doubled down to its partner's lowest position.
+template <class F>
+static __global__ void __launch_bounds__(32) bits_finalize_coop_kernel(const xyzz_t<F> *__restrict__ L, uint32_t nwindows, uint32_t nbits_w,
+                                                                      uint32_t wbits, jac_t<F> *__restrict__ out_jac, aff_t<F> *__restrict__ out_aff) {
+    const uint32_t G = nwindows * nbits_w, j = threadIdx.x >> 2;
+    const uint32_t len = (G + 7) / 8;
+    const uint32_t t0 = min(G, j * len), t1 = min(G, t0 + len);
+    auto pos_of = [&](uint32_t t) { return (nwindows - 1 - t / nbits_w) * wbits + (nbits_w - 1 - t % nbits_w); };
+    xyzz_t<F> acc;
+    xyzz_set_inf(acc);
+    uint32_t low = 0;  // lowest position folded into acc so far (0 for an empty quad)
+#pragma unroll 1
+    for (uint32_t s = 0; s < len; s++) {
+        const uint32_t t = t0 + s;
+        const bool have = t < t1;
+        xyzz_t<F> e;
+        xyzz_set_inf(e);
+        uint32_t dbl = 0;
+        if (have) {
+            load_xyzz(e, L + (size_t)(nwindows - 1 - t / nbits_w) * nbits_w + (nbits_w - 1 - t % nbits_w));
+            const uint32_t p = pos_of(t);
+            if (s > 0) dbl = low - p;
+            low = p;
+        }
+        if (s == 0) { acc = e; continue; }  // warp-uniform
+        quad_xyzz_shift(acc, dbl);
+        quad_xyzz_add(acc, e);
+    }
+    if (t0 >= t1) low = 0;
+#pragma unroll 1
+    for (uint32_t o = 1; o < 8; o <<= 1) {
+        xyzz_t<F> other;
+        xyzz_shfl_down_any(other, acc, (int)(4 * o));
+        const uint32_t low_other = __shfl_down_sync(0xffffffffu, low, 4 * o);
+        const bool recv = (j % (2 * o)) == 0;
+        if (!recv) xyzz_set_inf(other);
+        quad_xyzz_shift(acc, recv ? low - low_other : 0u);
+        quad_xyzz_add(acc, other);
+        if (recv) low = low_other;
+    }
+    quad_xyzz_shift(acc, j == 0 ? low : 0u);
+    if (threadIdx.x != 0) return;
+    jac_t<F> jj;
+    if (xyzz_is_inf(acc)) jac_set_inf(jj);
+    else xyzz_to_jac(jj, acc);
+    if (out_jac) *out_jac = jj;
+    if (out_aff) {
+        aff_t<F> a;
+        jac_to_affine(a, jj);
+        *out_aff = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // [5] window combination + output. Replaces the outer loop of POINTonE1s_mult_pippenger
 // (src/multi_scalar.c:565-575: ret = (ret + tile) * 2^window, top tile first), xyzz_to_Jacobian
 // (src/ec_ops.h:771-777) and, when want_affine, blst_p1_to_affine (src/e1.c:80-92). One thread.
@@ -941,6 +1152,22 @@ static __global__ void __launch_bounds__(128) point_op_xyzz_kernel(int op, const
         ((xyzz_t<F> *)out)[i] = x;
     }
 }
+// ops 6,7: the quad-cooperative XYZZ addition / doubling (coop.cuh), one quad per element
+template <class F>
+static __global__ void __launch_bounds__(128) point_op_coop_kernel(int op, const void *__restrict__ a, const void *__restrict__ b,
+                                                                   void *__restrict__ out, size_t n) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    xyzz_t<F> x, y;
+    xyzz_set_inf(x);
+    xyzz_set_inf(y);
+    if (i < n) {
+        x = ((const xyzz_t<F> *)a)[i];
+        if (op == 6) y = ((const xyzz_t<F> *)b)[i];
+    }
+    if (op == 6) quad_xyzz_add(x, y);
+    else { xyzz_t<F> d; quad_xyzz_double(d, x); x = d; }
+    if (i < n && (threadIdx.x & 3) == 0) ((xyzz_t<F> *)out)[i] = x;
+}
 template <class F>
 static __global__ void __launch_bounds__(128) point_op_misc_kernel(int op, const void *__restrict__ a, const void *__restrict__ b,
                                                                    void *__restrict__ out, size_t n) {
@@ -951,6 +1178,7 @@ static __global__ void __launch_bounds__(128) point_op_misc_kernel(int op, const
     case 1: { jac_t<F> x = ((const jac_t<F> *)a)[i], r; jac_double(r, x); ((jac_t<F> *)out)[i] = r; break; }
     case 4: { xyzz_t<F> x = ((const xyzz_t<F> *)a)[i]; jac_t<F> r; if (xyzz_is_inf(x)) jac_set_inf(r); else xyzz_to_jac(r, x); ((jac_t<F> *)out)[i] = r; break; }
     case 5: { jac_t<F> x = ((const jac_t<F> *)a)[i]; aff_t<F> r; jac_to_affine(r, x); ((aff_t<F> *)out)[i] = r; break; }
+    case 8: { xyzz_t<F> x = ((const xyzz_t<F> *)a)[i], r; xyzz_double(r, x); ((xyzz_t<F> *)out)[i] = r; break; }
     }
 }
 

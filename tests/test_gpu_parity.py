@@ -124,6 +124,23 @@ def test_point_ops_vs_oracle_with_special_cases(M, group):
     got = M.test_point_op(group, 3, lhs, rhs).reshape(n, xb)
     finite = exp[:, half:].any(axis=1)
     assert (got[:, half:] == exp[:, half:]).all() and (got[finite] == exp[finite]).all()
+    # quad-cooperative addition / doubling (coop.cuh): same formulas spread over 4 lanes, so the same bytes as the
+    # one-thread versions, including infinity operands on either side, doubling and cancellation
+    rhs2 = rhs.copy()
+    rhs2[16:24] = 0                      # infinity addend
+    lhs2 = lhs.copy()
+    lhs2[24:32] = 0                      # infinity accumulator
+    exp2 = np.zeros_like(lhs2)
+    o.oracle_point_op(group, 3, O.ptr(lhs2), O.ptr(rhs2), None, O.ptr(exp2), n)
+    got2 = M.test_point_op(group, 6, lhs2, rhs2).reshape(n, xb)
+    fin2 = exp2[:, half:].any(axis=1)
+    assert (got2[:, half:] == exp2[:, half:]).all() and (got2[fin2] == exp2[fin2]).all()
+    expd = M.test_point_op(group, 8, lhs2).reshape(n, xb)
+    eo = np.zeros_like(lhs2)
+    o.oracle_point_op(group, 3, O.ptr(lhs2), O.ptr(lhs2), None, O.ptr(eo), n)  # P + P through the oracle's dadd
+    gotd = M.test_point_op(group, 7, lhs2).reshape(n, xb)
+    find = eo[:, half:].any(axis=1)
+    assert (expd[find] == eo[find]).all() and (gotd[find] == eo[find]).all() and not gotd[~find][:, half:].any()
     # xyzz -> jacobian -> affine, jacobian add / double
     jac = M.test_point_op(group, 4, lhs).reshape(n, jb)
     ej = np.zeros_like(jac)
@@ -502,6 +519,34 @@ def test_accumulator_modes_agree(M, group, mode):
     for method in (1, 4):
         assert M.affine_serialize(group, ctx.msm(method, sc)).hex() == gd["result"]
     ctx.close()
+
+
+@pytest.mark.parametrize("group", [1, 2])
+@pytest.mark.parametrize("reducer", [1, 2])
+@pytest.mark.parametrize("accum", [1, 2])
+def test_reducer_modes_agree(M, group, reducer, accum):
+    """Both bucket reductions (1 = chunked running sums with the reference's tmp_d[] gap accumulators, 2 = digit
+    splitting into per-digit / per-bit lists) under both accumulators, all four methods, on inputs that leave most
+    buckets empty (zero / equal scalars) as well as on dense ones; config 13 has the r - a trick in BGMW95."""
+    for cfgname in ("10", "13"):
+        ctx = M.MsmContext(group, cfgname)
+        ctx.set_reducer(reducer)
+        ctx.set_accumulator(accum)
+        ctx.init_fix_point_list()
+        ctx.init_pippenger_CHES_q_over_5()
+        ctx.init_pippenger_BGMW95()
+        n = ctx.n
+        rm1 = [((O.R_ORDER - 1) >> (64 * i)) & (2**64 - 1) for i in range(4)]
+        cases = [O.gen_scalars(70 + reducer, n), np.repeat(O.gen_scalars(9, 1), n, axis=0), np.zeros((n, 4), dtype=np.uint64),
+                 np.array([rm1] * n, dtype=np.uint64)]
+        one = np.zeros((n, 4), dtype=np.uint64)
+        one[n // 2, 0] = 1  # a single non-empty bucket
+        cases.append(one)
+        for sc in cases:
+            exp, _ = O.closed_form(group, sc)
+            for method in (1, 2, 3, 4):
+                assert (ctx.msm(method, sc) == exp).all(), (cfgname, reducer, accum, method)
+        ctx.close()
 
 
 def test_batch_affine_full_size_known_answer(M, golden):
