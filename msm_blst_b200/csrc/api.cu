@@ -126,7 +126,9 @@ int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, u
     }
     // stage 1: one LANE per slice of a digit list, slices sized so that ~3 warps per SM sub-partition have equal work
     // (perfect balance whatever the list lengths); stage 1b: the slices of each digit list, summed by quads
-    uint32_t slice1 = (uint32_t)std::min<size_t>(32, std::max<size_t>(2, idx.size() * nwindows / ((size_t)3 * subparts * 32)));
+    plan.s1_coop = getenv("MSMB200_S1COOP") && atoi(getenv("MSMB200_S1COOP")) != 0;
+    const size_t per_warp = plan.s1_coop ? 8 : 32;  // slices handled by one warp
+    uint32_t slice1 = (uint32_t)std::min<size_t>(plan.s1_coop ? 128 : 32, std::max<size_t>(2, idx.size() * nwindows / ((size_t)3 * subparts * per_warp)));
     if (const char *e = getenv("MSMB200_SLICE1")) slice1 = (uint32_t)std::max(1, atoi(e));
     std::vector<uint32_t> start_s, start_g, idx_g;
     slice_lists(start, slice1, start_s, start_g, idx_g);
@@ -178,7 +180,7 @@ static void ctx_free(Ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->scalars, &c->keys, &c->vals, &c->sorted, &c->count, &c->packed, &c->scanned, &c->tile_sums, &c->seg_start,
                       &c->item_start, &c->cursor, &c->item_begin, &c->item_cnt, &c->order, &c->len_hist, &c->len_start, &c->len_cursor,
-                      &c->partial, &c->chunk_a, &c->chunk_b, &c->result, &c->flat, &c->signs, &c->pidx, &c->heavy, &c->bucket_of0, &c->bo_a, &c->bo_b,
+                      &c->partial, &c->chunk_a, &c->chunk_b, &c->result, &c->flat, &c->signs, &c->pidx, &c->heavy, &c->light, &c->bucket_of0, &c->bo_a, &c->bo_b,
                       &c->pts_a, &c->pts_b, &c->base_a, &c->base_b, &c->tile_sums2, &c->maxcount, &c->red_a, &c->red_b, &c->red_c, &c->red_d};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     free_reduce_plan(c->plan_ches); free_reduce_plan(c->plan_bgmw); free_reduce_plan(c->plan_pip);

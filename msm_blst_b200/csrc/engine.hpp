@@ -32,6 +32,7 @@ struct ReducePlan {
     size_t key_nbw = 0;     // cache key: number of buckets per window and largest value (dense plans)
     uint32_t c_lo = 0;      // value = lo + 2^c_lo * hi
     uint32_t nbits_w = 0;   // bit positions per window after stage 2
+    bool s1_coop = false;   // stage 1 by quads (list_sum_coop_kernel MODE 0) instead of one lane per slice
     // stage 1: slices of the (digit, value) lists over buckets, one lane each; 1b: slices -> digit lists;
     // 2a: (bit, slice) lists over the digit sums; 2b: slices -> bit lists
     ListPlan s1, s1b, s2a, s2b;
@@ -65,7 +66,7 @@ struct Ctx {
     // workspace (grow-only)
     DevBuf scalars, keys, vals, sorted, count, packed, scanned, tile_sums, seg_start, item_start, cursor,
         item_begin, item_cnt, order, len_hist, len_start, len_cursor, partial, chunk_a, chunk_b, result,
-        flat, signs, pidx, heavy, bucket_of0, bo_a, bo_b, pts_a, pts_b, base_a, base_b, tile_sums2, maxcount;
+        flat, signs, pidx, heavy, light, bucket_of0, bo_a, bo_b, pts_a, pts_b, base_a, base_b, tile_sums2, maxcount;
     ReducePlan plan_ches, plan_bgmw, plan_pip;  // digit-splitting reduction plans (sparse CHES set / dense windows)
     uint32_t plan_bgmw_windows = 0, plan_pip_windows = 0;
     DevBuf red_a, red_b, red_c, red_d;          // outputs of the list-sum stages

@@ -72,6 +72,15 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     size_t avg = std::max<size_t>(1, m / std::max<size_t>(1, nb));
     uint32_t item_len = (uint32_t)std::min<size_t>(1024, std::max<size_t>(128, 8 * avg));
     if (nb < 148 * 384 * 2) item_len = (uint32_t)std::max<size_t>(32, std::min<size_t>(item_len, m / (148 * 384 * 8)));
+    // Small problems use short work items (>= ~3 warps per SM sub-partition of equal-length chains); the partials of a
+    // split bucket are folded by one quad (combine_light_kernel) or, beyond heavy_items partials, by one block.
+    const bool split_reduce = use_split_reduce(c, L);
+    uint32_t heavy_items = 8;  // buckets with 2..8 work items: one quad each (combine_light_kernel); more: one block each
+    if (split_reduce) {
+        const size_t want_items = (size_t)3 * 592 * 32;
+        if (nb < want_items) item_len = (uint32_t)std::max<size_t>(8, std::min<size_t>(item_len, m / want_items));
+    }
+    if (const char *e = getenv("MSMB200_ITEM_LEN")) item_len = (uint32_t)std::max(1, atoi(e));
     const size_t max_items = std::min(nb, m) + m / item_len + 1;
     const size_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
 
@@ -107,9 +116,11 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     if (!batch_affine) {
         MSM_CUDA(c, cudaMemsetAsync(c->len_hist.p, 0, (item_len + 1) * 4, st));
         MSM_CUDA(c, cudaMemsetAsync(c->heavy.p, 0, 4, st));
+        if (ensure(c, c->light, (std::min(nb, m / item_len + 1) + 2) * 4)) return MSMB200_ECUDA;
+        MSM_CUDA(c, cudaMemsetAsync(c->light.p, 0, 4, st));
         itemize_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, (const uint32_t *)c->seg_start.p, (const uint32_t *)c->item_start.p,
                                                             nb, item_len, (uint32_t *)c->item_begin.p, (uint32_t *)c->item_cnt.p,
-                                                            (uint32_t *)c->len_hist.p, (uint32_t *)c->heavy.p);
+                                                            (uint32_t *)c->len_hist.p, (uint32_t *)c->heavy.p, heavy_items, (uint32_t *)c->light.p);
         len_scan_kernel<<<1, 32, 0, st>>>((const uint32_t *)c->len_hist.p, (uint32_t *)c->len_start.p, (uint32_t *)c->len_cursor.p, item_len);
         order_items_kernel<<<blocks_for(max_items, 256), 256, 0, st>>>((const uint32_t *)c->item_cnt.p, totals,
                                                                        (const uint32_t *)c->len_start.p, (uint32_t *)c->len_cursor.p,
@@ -124,6 +135,13 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
             unsigned max_heavy = (unsigned)std::min<size_t>(m / item_len + 1, 592);
             combine_heavy_kernel<FC><<<max_heavy, 128, 0, st>>>(count, (const uint32_t *)c->item_start.p, (const uint32_t *)c->heavy.p, item_len,
                                                                (xyzz_t<FC> *)c->partial.p);
+        }
+        if (heavy_items > 1) {
+            // at most min(nb, m / item_len) buckets have more than one work item; grid sized for that bound, idle warps exit
+            const size_t max_light = std::min(nb, m / item_len + 1);
+            combine_light_kernel<FC><<<blocks_for(max_light * 4, 128), 128, 0, st>>>(count, (const uint32_t *)c->item_start.p,
+                                                                                    (const uint32_t *)c->light.p, item_len, (xyzz_t<FC> *)c->partial.p);
+            c->launches += 1;
         }
         c->launches += 2;
         bucket_points = c->partial.p;
@@ -176,7 +194,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     }
     MSM_CUDA(c, cudaEventRecord(c->ev[3], st));
     // ---- reduce ----
-    if (use_split_reduce(c, L)) {
+    if (split_reduce) {
         const ReducePlan &P = *L.plan;
         const uint32_t nw = L.nwindows;
         if (ensure(c, c->red_a, (size_t)nw * P.s1.nlists * sizeof(xyzz_t<F>) + 64) || ensure(c, c->red_b, (size_t)nw * P.s1b.nlists * sizeof(xyzz_t<F>) + 64) ||
@@ -186,16 +204,23 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         if (P.s1.nlists) {
             const unsigned g1 = blocks_for((size_t)nw * P.s1.nlists, 128);
             if (batch_affine)
-                list_sum_kernel<F, 1><<<g1, 128, 0, st>>>(bucket_points, count, bucket_point_index, L.nbw, (const uint32_t *)P.s1.start.p,
-                                                          (const uint32_t *)P.s1.idx.p, P.s1.nlists, nw, 1, (xyzz_t<F> *)c->red_a.p);
+                list_sum_kernel<F, 1><<<g1, 128, 0, st>>>(bucket_points, count, bucket_point_index, L.nbw,
+                                                          (const uint32_t *)P.s1.start.p, (const uint32_t *)P.s1.idx.p, P.s1.nlists, nw, 1,
+                                                          (xyzz_t<F> *)c->red_a.p);
+            else if (P.s1_coop)
+                list_sum_coop_kernel<FC, 0><<<blocks_for((size_t)nw * P.s1.nlists * 4, 128), 128, 0, st>>>(
+                    (const xyzz_t<FC> *)bucket_points, count, bucket_point_index, L.nbw, (const uint32_t *)P.s1.start.p,
+                    (const uint32_t *)P.s1.idx.p, P.s1.nlists, nw, 1, (xyzz_t<FC> *)c->red_a.p);
             else
-                list_sum_kernel<F, 0><<<g1, 128, 0, st>>>(bucket_points, count, bucket_point_index, L.nbw, (const uint32_t *)P.s1.start.p,
-                                                          (const uint32_t *)P.s1.idx.p, P.s1.nlists, nw, 1, (xyzz_t<F> *)c->red_a.p);
+                list_sum_kernel<F, 0><<<g1, 128, 0, st>>>(bucket_points, count, bucket_point_index, L.nbw,
+                                                          (const uint32_t *)P.s1.start.p, (const uint32_t *)P.s1.idx.p, P.s1.nlists, nw, 1,
+                                                          (xyzz_t<F> *)c->red_a.p);
         }
         // stages 1b, 2a, 2b: quad-cooperative list sums over dense arrays
         auto coop = [&](const ListPlan &lp, const void *src, uint32_t in_stride, void *dst) {
-            list_sum_coop_kernel<FC><<<blocks_for((size_t)nw * lp.nlists * lp.tl * 4, 128), 128, 0, st>>>(
-                (const xyzz_t<FC> *)src, in_stride, (const uint32_t *)lp.start.p, (const uint32_t *)lp.idx.p, lp.nlists, nw, lp.tl, (xyzz_t<FC> *)dst);
+            list_sum_coop_kernel<FC, 2><<<blocks_for((size_t)nw * lp.nlists * lp.tl * 4, 128), 128, 0, st>>>(
+                (const xyzz_t<FC> *)src, nullptr, nullptr, in_stride, (const uint32_t *)lp.start.p, (const uint32_t *)lp.idx.p, lp.nlists, nw,
+                lp.tl, (xyzz_t<FC> *)dst);
         };
         coop(P.s1b, c->red_a.p, P.s1.nlists, c->red_b.p);
         coop(P.s2a, c->red_b.p, P.s1b.nlists, c->red_c.p);
@@ -208,8 +233,8 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
             bits_finalize_kernel<FC><<<1, 32, 0, st>>>((const xyzz_t<FC> *)c->red_d.p, nw, P.nbits_w, L.wbits, (jac_t<FC> *)d_jac,
                                                        want_affine ? (aff_t<FC> *)d_aff : nullptr);
         else
-            bits_finalize_coop_kernel<FC><<<1, 32, 0, st>>>((const xyzz_t<FC> *)c->red_d.p, nw, P.nbits_w, L.wbits, (jac_t<FC> *)d_jac,
-                                                            want_affine ? (aff_t<FC> *)d_aff : nullptr);
+            bits_finalize_coop_kernel<FC><<<1, 32, 0, st>>>((const xyzz_t<FC> *)c->red_d.p, nw, P.nbits_w, L.wbits, (xyzz_t<FC> *)c->red_c.p,
+                                                            (jac_t<FC> *)d_jac, want_affine ? (aff_t<FC> *)d_aff : nullptr);
         c->launches += 1;
         if (want_affine) MSM_CUDA(c, cudaMemcpyAsync(c->h_result, d_aff, sizeof(aff_t<F>), cudaMemcpyDeviceToHost, st));
         MSM_CUDA(c, cudaEventRecord(c->ev[5], st));

@@ -295,12 +295,16 @@ static __global__ void scatter_kernel(const uint32_t *__restrict__ keys, const u
 static __global__ void itemize_kernel(const uint32_t *__restrict__ count, const uint32_t *__restrict__ seg_start,
                                const uint32_t *__restrict__ item_start, size_t nb, uint32_t item_len,
                                uint32_t *__restrict__ item_begin, uint32_t *__restrict__ item_cnt,
-                               uint32_t *__restrict__ len_hist, uint32_t *__restrict__ heavy /* [0] = count, then bucket ids */) {
+                               uint32_t *__restrict__ len_hist, uint32_t *__restrict__ heavy /* [0] = count, then bucket ids */,
+                               uint32_t heavy_items, uint32_t *__restrict__ light /* [0] = count, then bucket ids; may be null */) {
+    // buckets with more than heavy_items work items are combined by a block each (combine_heavy_kernel), buckets with
+    // 2..heavy_items work items by a quad each (combine_light_kernel)
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     uint32_t c = count[b];
     if (c == 0) return;
-    if (c > item_len) heavy[1 + atomicAdd(&heavy[0], 1u)] = (uint32_t)b;
+    if (c > item_len * heavy_items) heavy[1 + atomicAdd(&heavy[0], 1u)] = (uint32_t)b;
+    else if (c > item_len) light[1 + atomicAdd(&light[0], 1u)] = (uint32_t)b;
     uint32_t s = seg_start[b], it = item_start[b];
     for (uint32_t off = 0; off < c; off += item_len, it++) {
         uint32_t len = min(item_len, c - off);
@@ -850,11 +854,14 @@ static __global__ void bits_finalize_kernel(const xyzz_t<F> *__restrict__ L, uin
     }
 }
 
-// Quad-cooperative variants for the small stages (coop.cuh): list sums over a dense XYZZ array with one QUAD per team
-// slot (tq quads per list, tq a power of two <= 8), and the Horner pass with the bit positions spread over the 8
-// quads of one warp. Control flow is warp-uniform; trip counts are the warp maximum and idle quads add infinity.
-template <class F>
-static __global__ void __launch_bounds__(128) list_sum_coop_kernel(const xyzz_t<F> *__restrict__ src, uint32_t in_stride,
+// Quad-cooperative variants (coop.cuh: a point is distributed over 4 lanes): list sums with one QUAD per team slot
+// (tq quads per list, tq a power of two <= 8), and the Horner pass with the bit positions spread over the 8 quads of
+// one warp. Control flow is warp-uniform; trip counts are the warp maximum and idle quads add infinity.
+//   MODE 0: members are buckets; their sums are the XYZZ partials src[item_start[b]] (skipped when count[b] == 0)
+//   MODE 2: members index a dense XYZZ array
+template <class F, int MODE>
+static __global__ void __launch_bounds__(128) list_sum_coop_kernel(const xyzz_t<F> *__restrict__ src, const uint32_t *__restrict__ count,
+                                                                   const uint32_t *__restrict__ item_start, uint32_t in_stride,
                                                                    const uint32_t *__restrict__ start, const uint32_t *__restrict__ idx,
                                                                    uint32_t nlists, uint32_t nwindows, uint32_t tq, xyzz_t<F> *__restrict__ out) {
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -871,33 +878,71 @@ static __global__ void __launch_bounds__(128) list_sum_coop_kernel(const xyzz_t<
     }
     const uint32_t my_iters = e1 > e0 ? (e1 - e0 + tq - 1) / tq : 0u;
     const uint32_t iters = __reduce_max_sync(0xffffffffu, my_iters);
-    xyzz_t<F> acc;
-    xyzz_set_inf(acc);
+    F acc;
+    f_set_zero(acc);
 #pragma unroll 1
     for (uint32_t it = 0; it < iters; it++) {
-        xyzz_t<F> s;
-        xyzz_set_inf(s);
         const uint32_t e = e0 + it * tq;
-        if (e < e1) load_xyzz(s, src + base + idx[e]);
-        if (it == 0) acc = s;
-        else quad_xyzz_add(acc, s);
+        const bool have = e < e1;
+        if (MODE == 2) {
+            F s;
+            f_set_zero(s);
+            if (have) dq_load(s, src + base + idx[e]);
+            if (it == 0) acc = s;
+            else dq_add(acc, s);
+        } else {
+            F s;
+            f_set_zero(s);
+            if (have) {
+                const size_t b = base + idx[e];
+                if (count[b] != 0) dq_load(s, src + item_start[b]);
+            }
+            dq_add(acc, s);
+        }
     }
 #pragma unroll 1
     for (uint32_t o = tq >> 1; o > 0; o >>= 1) {
-        xyzz_t<F> other;
-        xyzz_shfl_down_any(other, acc, (int)(4 * o));
-        if (sq + o >= tq) xyzz_set_inf(other);
-        quad_xyzz_add(acc, other);
+        F other;
+        dq_shfl_down(other, acc, (int)(4 * o));
+        if (sq + o >= tq) f_set_zero(other);
+        dq_add(acc, other);
     }
-    if (live && sq == 0 && (threadIdx.x & 3) == 0) out[gl] = acc;
+    if (live && sq == 0) dq_store(out + gl, acc);
 }
 
-template <class F> __device__ __forceinline__ void quad_xyzz_shift(xyzz_t<F> &acc, uint32_t my_doublings) {
+// Buckets split into 2..heavy_items work items: one quad per bucket folds the partials into the first one.
+template <class F>
+static __global__ void __launch_bounds__(128) combine_light_kernel(const uint32_t *__restrict__ count, const uint32_t *__restrict__ item_start,
+                                                                   const uint32_t *__restrict__ light, uint32_t item_len, xyzz_t<F> *partial) {
+    const uint32_t nlight = light[0];
+    const uint32_t gq = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (__all_sync(0xffffffffu, gq >= nlight)) return;
+    uint32_t first = 0, nitems = 0;
+    if (gq < nlight) {
+        const uint32_t b = light[1 + gq];
+        first = item_start[b];
+        nitems = (count[b] + item_len - 1) / item_len;
+    }
+    const uint32_t maxitems = __reduce_max_sync(0xffffffffu, nitems);
+    F acc;
+    f_set_zero(acc);
+#pragma unroll 1
+    for (uint32_t k = 0; k < maxitems; k++) {
+        F s;
+        f_set_zero(s);
+        if (k < nitems) dq_load(s, partial + first + k);
+        if (k == 0) acc = s;
+        else dq_add(acc, s);
+    }
+    if (nitems) dq_store(partial + first, acc);
+}
+
+template <class F> __device__ __forceinline__ void dq_shift(F &acc, uint32_t my_doublings) {
     const uint32_t maxd = __reduce_max_sync(0xffffffffu, my_doublings);
 #pragma unroll 1
     for (uint32_t i = 0; i < maxd; i++) {
-        xyzz_t<F> d;
-        quad_xyzz_double(d, acc);
+        F d;
+        dq_double(d, acc);
         if (i < my_doublings) acc = d;
     }
 }
@@ -906,48 +951,53 @@ template <class F> __device__ __forceinline__ void quad_xyzz_shift(xyzz_t<F> &ac
 // tree in which the quad holding the higher positions is doubled down to its partner's lowest position.
 template <class F>
 static __global__ void __launch_bounds__(32) bits_finalize_coop_kernel(const xyzz_t<F> *__restrict__ L, uint32_t nwindows, uint32_t nbits_w,
-                                                                      uint32_t wbits, jac_t<F> *__restrict__ out_jac, aff_t<F> *__restrict__ out_aff) {
+                                                                      uint32_t wbits, xyzz_t<F> *__restrict__ scratch,
+                                                                      jac_t<F> *__restrict__ out_jac, aff_t<F> *__restrict__ out_aff) {
     const uint32_t G = nwindows * nbits_w, j = threadIdx.x >> 2;
     const uint32_t len = (G + 7) / 8;
     const uint32_t t0 = min(G, j * len), t1 = min(G, t0 + len);
-    auto pos_of = [&](uint32_t t) { return (nwindows - 1 - t / nbits_w) * wbits + (nbits_w - 1 - t % nbits_w); };
-    xyzz_t<F> acc;
-    xyzz_set_inf(acc);
+    F acc;
+    f_set_zero(acc);
     uint32_t low = 0;  // lowest position folded into acc so far (0 for an empty quad)
 #pragma unroll 1
     for (uint32_t s = 0; s < len; s++) {
         const uint32_t t = t0 + s;
-        const bool have = t < t1;
-        xyzz_t<F> e;
-        xyzz_set_inf(e);
+        F e;
+        f_set_zero(e);
         uint32_t dbl = 0;
-        if (have) {
-            load_xyzz(e, L + (size_t)(nwindows - 1 - t / nbits_w) * nbits_w + (nbits_w - 1 - t % nbits_w));
-            const uint32_t p = pos_of(t);
+        if (t < t1) {
+            const uint32_t w = nwindows - 1 - t / nbits_w, k = nbits_w - 1 - t % nbits_w;
+            dq_load(e, L + (size_t)w * nbits_w + k);
+            const uint32_t p = w * wbits + k;
             if (s > 0) dbl = low - p;
             low = p;
         }
         if (s == 0) { acc = e; continue; }  // warp-uniform
-        quad_xyzz_shift(acc, dbl);
-        quad_xyzz_add(acc, e);
+        dq_shift(acc, dbl);
+        dq_add(acc, e);
     }
     if (t0 >= t1) low = 0;
 #pragma unroll 1
     for (uint32_t o = 1; o < 8; o <<= 1) {
-        xyzz_t<F> other;
-        xyzz_shfl_down_any(other, acc, (int)(4 * o));
+        F other;
+        dq_shfl_down(other, acc, (int)(4 * o));
         const uint32_t low_other = __shfl_down_sync(0xffffffffu, low, 4 * o);
         const bool recv = (j % (2 * o)) == 0;
-        if (!recv) xyzz_set_inf(other);
-        quad_xyzz_shift(acc, recv ? low - low_other : 0u);
-        quad_xyzz_add(acc, other);
+        if (!recv) f_set_zero(other);
+        dq_shift(acc, recv ? low - low_other : 0u);
+        dq_add(acc, other);
         if (recv) low = low_other;
     }
-    quad_xyzz_shift(acc, j == 0 ? low : 0u);
+    dq_shift(acc, j == 0 ? low : 0u);
+    // gather the distributed result of quad 0 into one thread for the (single) inversion
+    if (j == 0) dq_store(scratch, acc);
+    __syncwarp();
     if (threadIdx.x != 0) return;
+    xyzz_t<F> full;
+    load_xyzz(full, scratch);
     jac_t<F> jj;
-    if (xyzz_is_inf(acc)) jac_set_inf(jj);
-    else xyzz_to_jac(jj, acc);
+    if (xyzz_is_inf(full)) jac_set_inf(jj);
+    else xyzz_to_jac(jj, full);
     if (out_jac) *out_jac = jj;
     if (out_aff) {
         aff_t<F> a;
@@ -1157,16 +1207,16 @@ template <class F>
 static __global__ void __launch_bounds__(128) point_op_coop_kernel(int op, const void *__restrict__ a, const void *__restrict__ b,
                                                                    void *__restrict__ out, size_t n) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    xyzz_t<F> x, y;
-    xyzz_set_inf(x);
-    xyzz_set_inf(y);
+    F x, y;
+    f_set_zero(x);
+    f_set_zero(y);
     if (i < n) {
-        x = ((const xyzz_t<F> *)a)[i];
-        if (op == 6) y = ((const xyzz_t<F> *)b)[i];
+        dq_load(x, (const xyzz_t<F> *)a + i);
+        if (op == 6) dq_load(y, (const xyzz_t<F> *)b + i);
     }
-    if (op == 6) quad_xyzz_add(x, y);
-    else { xyzz_t<F> d; quad_xyzz_double(d, x); x = d; }
-    if (i < n && (threadIdx.x & 3) == 0) ((xyzz_t<F> *)out)[i] = x;
+    if (op == 6) dq_add(x, y);
+    else { F d; dq_double(d, x); x = d; }
+    if (i < n) dq_store((xyzz_t<F> *)out + i, x);
 }
 template <class F>
 static __global__ void __launch_bounds__(128) point_op_misc_kernel(int op, const void *__restrict__ a, const void *__restrict__ b,
