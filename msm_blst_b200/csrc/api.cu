@@ -52,16 +52,19 @@ uint32_t pick_vspan_host(size_t max_value, uint32_t nwindows) {
 }
 
 // ---- digit-splitting reduction plan (see list_sum_kernel) ----
-// Quads per list for the cooperative list sums: a single warp per SM sub-partition runs at about half the pipe rate,
-// so up to 2 warps per sub-partition are free; beyond that the time grows with the number of warps.
-static uint32_t pick_quads(size_t total_lists, double avg_len, int subparts) {
+// Quads per list for the cooperative list sums. `resident` 128-thread blocks fit on an SM, i.e. `resident` warps per
+// sub-partition per wave; a sub-partition with one warp runs at about half the pipe rate, so up to 2 warps are free;
+// a partially filled last wave costs a whole chain again.
+static uint32_t pick_quads(size_t total_lists, double avg_len, int subparts, int resident) {
     uint32_t best = 8;
     double best_cost = 1e300;
     for (uint32_t tq = 8; tq >= 1; tq >>= 1) {
-        double warps = std::ceil((double)total_lists * tq / 8.0);
-        double load = std::max(2.0, std::ceil(warps / (double)subparts));
-        double chain = std::max(1.0, std::ceil(avg_len / tq) - 1.0 + std::log2((double)tq));
-        double cost = load * chain;
+        const double warps = std::ceil((double)total_lists * tq / 8.0), per_wave = (double)subparts * resident;
+        const double full = std::floor(warps / per_wave), rem = warps - full * per_wave;
+        double load = full * std::max(2.0, (double)resident);
+        if (rem > 0) load += std::max(2.0, std::ceil(rem / subparts));
+        const double chain = std::max(1.0, std::ceil(avg_len / tq) - 1.0 + std::log2((double)tq));
+        const double cost = load * chain;
         if (cost < best_cost) { best_cost = cost; best = tq; }
     }
     return best;
@@ -99,6 +102,7 @@ int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, u
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     const int subparts = 4 * sms;
+    const int res1 = c->ops->resident_blocks(0), resq = c->ops->resident_blocks(1);
     const uint32_t maxv = nbw > 1 ? (values ? (uint32_t)values[nbw - 1] : (uint32_t)(nbw - 1)) : 1u;
     uint32_t V = 0;
     while (V < 32 && (maxv >> V) != 0) V++;
@@ -126,9 +130,11 @@ int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, u
     }
     // stage 1: one LANE per slice of a digit list, slices sized so that ~3 warps per SM sub-partition have equal work
     // (perfect balance whatever the list lengths); stage 1b: the slices of each digit list, summed by quads
+    // slices sized so that the whole stage is ONE wave of resident blocks (a partially filled second wave would cost a
+    // full chain again); 8 % head-room for the ragged last slice of every list
     plan.s1_coop = getenv("MSMB200_S1COOP") && atoi(getenv("MSMB200_S1COOP")) != 0;
-    const size_t per_warp = plan.s1_coop ? 8 : 32;  // slices handled by one warp
-    uint32_t slice1 = (uint32_t)std::min<size_t>(plan.s1_coop ? 128 : 32, std::max<size_t>(2, idx.size() * nwindows / ((size_t)3 * subparts * per_warp)));
+    const double lanes1 = (plan.s1_coop ? 8.0 * resq : 32.0 * res1) * subparts * 0.92;
+    uint32_t slice1 = (uint32_t)std::max(2.0, std::ceil((double)idx.size() * nwindows / lanes1));
     if (const char *e = getenv("MSMB200_SLICE1")) slice1 = (uint32_t)std::max(1, atoi(e));
     std::vector<uint32_t> start_s, start_g, idx_g;
     slice_lists(start, slice1, start_s, start_g, idx_g);
@@ -137,7 +143,7 @@ int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, u
     plan.s1.tl = 1;
     rc = upload_list_plan(c, plan.s1b, start_g, idx_g);
     if (rc) return rc;
-    plan.s1b.tl = pick_quads((size_t)nl1 * nwindows, nl1 ? (double)idx_g.size() / nl1 : 1.0, subparts);
+    plan.s1b.tl = pick_quads((size_t)nl1 * nwindows, nl1 ? (double)idx_g.size() / nl1 : 1.0, subparts, resq);
     // stage 2a: bit k of the lo (k < c_lo) or hi (k >= c_lo) digit value, cut into slices of SLICE members; 2b: bit lists
     const uint32_t SLICE = 32, nbits = c_lo + chi;
     std::vector<uint32_t> start_a(1, 0), idx_a, start_as, start_b, idx_b;
@@ -151,10 +157,10 @@ int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, u
     slice_lists(start_a, SLICE, start_as, start_b, idx_b);
     rc = upload_list_plan(c, plan.s2a, start_as, idx_a);
     if (rc) return rc;
-    plan.s2a.tl = pick_quads((size_t)plan.s2a.nlists * nwindows, plan.s2a.nlists ? (double)idx_a.size() / plan.s2a.nlists : 1.0, subparts);
+    plan.s2a.tl = pick_quads((size_t)plan.s2a.nlists * nwindows, plan.s2a.nlists ? (double)idx_a.size() / plan.s2a.nlists : 1.0, subparts, resq);
     rc = upload_list_plan(c, plan.s2b, start_b, idx_b);
     if (rc) return rc;
-    plan.s2b.tl = pick_quads((size_t)nbits * nwindows, nbits ? (double)idx_b.size() / nbits : 1.0, subparts);
+    plan.s2b.tl = pick_quads((size_t)nbits * nwindows, nbits ? (double)idx_b.size() / nbits : 1.0, subparts, resq);
     plan.c_lo = c_lo;
     plan.nbits_w = nbits;
     plan.key_nbw = nbw;
@@ -178,7 +184,7 @@ static void ctx_free(Ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->scalars, &c->keys, &c->vals, &c->sorted, &c->count, &c->packed, &c->scanned, &c->tile_sums, &c->seg_start,
+    DevBuf *bufs[] = {&c->scalars, &c->keys, &c->vals, &c->ranks, &c->sorted, &c->count, &c->packed, &c->scanned, &c->tile_sums, &c->seg_start,
                       &c->item_start, &c->cursor, &c->item_begin, &c->item_cnt, &c->order, &c->len_hist, &c->len_start, &c->len_cursor,
                       &c->partial, &c->chunk_a, &c->chunk_b, &c->result, &c->flat, &c->signs, &c->pidx, &c->heavy, &c->light, &c->bucket_of0, &c->bo_a, &c->bo_b,
                       &c->pts_a, &c->pts_b, &c->base_a, &c->base_b, &c->tile_sums2, &c->maxcount, &c->red_a, &c->red_b, &c->red_c, &c->red_d};

@@ -64,7 +64,7 @@ struct Ctx {
     void *d_table_bgmw = nullptr;  bool have_bgmw = false;
 
     // workspace (grow-only)
-    DevBuf scalars, keys, vals, sorted, count, packed, scanned, tile_sums, seg_start, item_start, cursor,
+    DevBuf scalars, keys, vals, ranks, sorted, count, packed, scanned, tile_sums, seg_start, item_start, cursor,
         item_begin, item_cnt, order, len_hist, len_start, len_cursor, partial, chunk_a, chunk_b, result,
         flat, signs, pidx, heavy, light, bucket_of0, bo_a, bo_b, pts_a, pts_b, base_a, base_b, tile_sums2, maxcount;
     ReducePlan plan_ches, plan_bgmw, plan_pip;  // digit-splitting reduction plans (sparse CHES set / dense windows)
@@ -99,6 +99,9 @@ struct GroupOps {
     int (*field_op)(int field, int op, const void *a, const void *b, void *out, size_t n);
     int (*point_op)(int op, const void *a, const void *b, const unsigned char *flags, void *out, size_t n);
     int (*digits)(Ctx *, int kind, const void *d_scalars, size_t n, uint32_t *d_keys, uint32_t *d_vals);
+    // resident 128-thread blocks per SM of the list-sum kernels (0: list_sum_kernel stage 1, 1: list_sum_coop_kernel):
+    // the reduction plan sizes its grids to whole waves
+    int (*resident_blocks)(int which);
 };
 
 int measure_peaks(double *macs_per_s, double *fp_mul_per_s);

@@ -108,7 +108,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
                                                             (uint32_t *)c->seg_start.p, (uint32_t *)c->item_start.p,
                                                             (uint32_t *)c->cursor.p, nb);
     scatter_kernel<<<blocks_for(m, 256), 256, 0, st>>>((const uint32_t *)c->keys.p, (const uint32_t *)c->vals.p, m,
-                                                       (const uint32_t *)c->seg_start.p, (uint32_t *)c->cursor.p,
+                                                       (const uint32_t *)c->seg_start.p, (const uint32_t *)c->ranks.p,
                                                        (uint32_t *)c->sorted.p, batch_affine ? (uint32_t *)c->bucket_of0.p : nullptr);
     const uint64_t *totals = (const uint64_t *)c->tile_sums.p + ntiles;
     const void *bucket_points = nullptr;      // what the reduction reads: XYZZ partials or affine points
@@ -205,7 +205,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
             const unsigned g1 = blocks_for((size_t)nw * P.s1.nlists, 128);
             if (batch_affine)
                 list_sum_kernel<F, 1><<<g1, 128, 0, st>>>(bucket_points, count, bucket_point_index, L.nbw,
-                                                          (const uint32_t *)P.s1.start.p, (const uint32_t *)P.s1.idx.p, P.s1.nlists, nw, 1,
+                                                          (const uint32_t *)P.s1.start.p, (const uint32_t *)P.s1.idx.p, P.s1.nlists, nw,
                                                           (xyzz_t<F> *)c->red_a.p);
             else if (P.s1_coop)
                 list_sum_coop_kernel<FC, 0><<<blocks_for((size_t)nw * P.s1.nlists * 4, 128), 128, 0, st>>>(
@@ -213,7 +213,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
                     (const uint32_t *)P.s1.idx.p, P.s1.nlists, nw, 1, (xyzz_t<FC> *)c->red_a.p);
             else
                 list_sum_kernel<F, 0><<<g1, 128, 0, st>>>(bucket_points, count, bucket_point_index, L.nbw,
-                                                          (const uint32_t *)P.s1.start.p, (const uint32_t *)P.s1.idx.p, P.s1.nlists, nw, 1,
+                                                          (const uint32_t *)P.s1.start.p, (const uint32_t *)P.s1.idx.p, P.s1.nlists, nw,
                                                           (xyzz_t<F> *)c->red_a.p);
         }
         // stages 1b, 2a, 2b: quad-cooperative list sums over dense arrays
@@ -288,7 +288,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
 }
 
 static int prepare_entries(Ctx *c, size_t m, size_t nb) {
-    if (ensure(c, c->keys, m * 4) || ensure(c, c->vals, m * 4) || ensure(c, c->count, nb * 4)) return MSMB200_ECUDA;
+    if (ensure(c, c->keys, m * 4) || ensure(c, c->vals, m * 4) || ensure(c, c->ranks, m * 4) || ensure(c, c->count, nb * 4)) return MSMB200_ECUDA;
     MSM_CUDA(c, cudaMemsetAsync(c->count.p, 0, nb * 4, c->stream));
     return MSMB200_OK;
 }
@@ -314,7 +314,7 @@ static int pippenger_impl(Ctx *c, const void *d_points, size_t npoints, const vo
     shard_slice(c, nch, &clo, &ccnt);
     const uint32_t blo = 1 + clo * vs, bhi = std::min<uint32_t>(nbw, 1 + (clo + ccnt) * vs);
     digits_booth_kernel<<<blocks_for(npoints, 256), 256, 0, st>>>((const uint32_t *)d_scalars, npoints, nbits, w, tiles,
-                                                                  (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p, 1, blo, bhi);
+                                                                  (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p, (uint32_t *)c->ranks.p, 1, blo, bhi);
     c->launches += 1;
     MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
     Layout L{m, nbw, (uint32_t)tiles, (uint32_t)w, nullptr, 1, nullptr, vs, nch};
@@ -343,7 +343,7 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
         const uint32_t blo = (uint32_t)c->h_chunk_first[clo], bhi = (uint32_t)c->h_chunk_first[clo + ccnt];
         if (method == MSMB200_CHES) {
             digits_ches_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab,
-                                                                   (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p, 1, blo, bhi);
+                                                                   (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p, (uint32_t *)c->ranks.p, 1, blo, bhi);
             c->launches += 1;
         } else {
             if (ensure(c, c->flat, (m + 2) * 4) || ensure(c, c->signs, m) || ensure(c, c->pidx, m * 4)) return MSMB200_ECUDA;
@@ -352,7 +352,7 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
                                                                     n, cfg.h, c->d_dtab, c->d_bucket_vals);
             tile_lookup_kernel<<<blocks_for(m, 256), 256, 0, st>>>((const int *)c->flat.p, (const unsigned char *)c->signs.p,
                                                                    (const uint32_t *)c->pidx.p, m, c->d_v2i, (uint32_t *)c->keys.p,
-                                                                   (uint32_t *)c->vals.p, (uint32_t *)c->count.p, blo, bhi);
+                                                                   (uint32_t *)c->vals.p, (uint32_t *)c->count.p, (uint32_t *)c->ranks.p, blo, bhi);
             c->launches += 3;
         }
         MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
@@ -373,7 +373,7 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
         const uint32_t blo = 1 + clo * vs, bhi = std::min<uint32_t>(nbw, 1 + (clo + ccnt) * vs);
         digits_bgmw_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h_bgmw, cfg.e_bgmw,
                                                                bgmw_trick(cfg) ? 1 : 0, (uint32_t *)c->keys.p, (uint32_t *)c->vals.p,
-                                                               (uint32_t *)c->count.p, 1, blo, bhi);
+                                                               (uint32_t *)c->count.p, (uint32_t *)c->ranks.p, 1, blo, bhi);
         c->launches += 1;
         MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
         Layout L{m, nbw, 1, 0, nullptr, 1, nullptr, vs, nch};
@@ -396,7 +396,7 @@ static int tile_impl(Ctx *c, const void *d_table, const int *d_bvals, const unsi
     int rc = prepare_entries(c, m, nbuckets);
     if (rc) return rc;
     tile_lookup_kernel<<<blocks_for(m, 256), 256, 0, st>>>(d_bvals, d_signs, d_pidx, m, d_v2i, (uint32_t *)c->keys.p, (uint32_t *)c->vals.p,
-                                                           (uint32_t *)c->count.p, 0u, 0xffffffffu);
+                                                           (uint32_t *)c->count.p, (uint32_t *)c->ranks.p, 0u, 0xffffffffu);
     c->launches += 1;
     MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
     Layout L{m, (uint32_t)nbuckets, 1, 0, d_bucket_vals, d_max, d_chunk_first, vspan, nchunks};
@@ -487,14 +487,21 @@ template <class F> static int digits_impl(Ctx *c, int kind, const void *d_scalar
     if (ensure(c, c->count, nb * 4)) return MSMB200_ECUDA;
     MSM_CUDA(c, cudaMemsetAsync(c->count.p, 0, nb * 4, st));
     if (kind == 0)
-        digits_ches_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab, d_keys, d_vals, (uint32_t *)c->count.p, 0, 0u, 0xffffffffu);
+        digits_ches_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab, d_keys, d_vals, (uint32_t *)c->count.p, nullptr, 0, 0u, 0xffffffffu);
     else if (kind == 1)
-        digits_bgmw_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h_bgmw, cfg.e_bgmw, bgmw_trick(cfg) ? 1 : 0, d_keys, d_vals, (uint32_t *)c->count.p, 0, 0u, 0xffffffffu);
+        digits_bgmw_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h_bgmw, cfg.e_bgmw, bgmw_trick(cfg) ? 1 : 0, d_keys, d_vals, (uint32_t *)c->count.p, nullptr, 0, 0u, 0xffffffffu);
     else
-        digits_booth_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, 255, c->pip_window, c->pip_tiles, d_keys, d_vals, (uint32_t *)c->count.p, 0, 0u, 0xffffffffu);
+        digits_booth_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, 255, c->pip_window, c->pip_tiles, d_keys, d_vals, (uint32_t *)c->count.p, nullptr, 0, 0u, 0xffffffffu);
     MSM_CUDA(c, cudaGetLastError());
     MSM_CUDA(c, cudaStreamSynchronize(st));
     return MSMB200_OK;
+}
+
+template <class F, class FC> static int resident_blocks_impl(int which) {
+    int nb = 0;
+    cudaError_t e = which == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, list_sum_kernel<F, 0>, 128, 0)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, list_sum_coop_kernel<FC, 2>, 128, 0);
+    return e == cudaSuccess && nb > 0 ? nb : 2;
 }
 
 template <class F, class FC> static int point_op_impl(int op, const void *a, const void *b, const unsigned char *flags, void *out, size_t n) {

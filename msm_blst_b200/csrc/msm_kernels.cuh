@@ -46,7 +46,10 @@ __device__ __forceinline__ void load_scalar(uint32_t s[8], const uint32_t *scala
 // is 0 are skipped like `if(booth_idx)` in src/multi_scalar.c:445,:457.
 static __global__ void digits_ches_kernel(const uint32_t *__restrict__ scalars, size_t n, int h, int e,
                                    const uint32_t *__restrict__ dtab, uint32_t *__restrict__ keys,
-                                   uint32_t *__restrict__ vals, uint32_t *__restrict__ count, int digit_major, uint32_t lo, uint32_t hi) {
+                                   uint32_t *__restrict__ vals, uint32_t *__restrict__ count, uint32_t *__restrict__ ranks, int digit_major,
+                                   uint32_t lo, uint32_t hi) {
+    // ranks[at] = position of the entry inside its bucket (the value returned by the histogram atomic), so the
+    // scatter pass needs no second round of atomics; may be null (parity-test hook).
     // [lo, hi): bucket-index range owned by this context (bucket-range sharding over GPUs); others are skipped
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -61,14 +64,15 @@ static __global__ void digits_ches_kernel(const uint32_t *__restrict__ scalars, 
         uint32_t alpha = (ent >> 24) & 1u;
         carry = alpha;
         size_t slot = i * h + j;
-        uint32_t key = KEY_SKIP;
+        uint32_t key = KEY_SKIP, rank = 0;
         if (idx != 0 && idx >= lo && idx < hi) {
             key = idx;
-            atomicAdd(&count[idx], 1u);
+            rank = atomicAdd(&count[idx], 1u);
         }
         // digit-major placement (j*n + i) makes the warp's stores contiguous; the table index keeps the reference's i*h + j
         const size_t at = digit_major ? (size_t)j * n + i : slot;
         keys[at] = key;
+        if (ranks) ranks[at] = rank;
         vals[at] = (uint32_t)(3 * slot + m1) | (alpha << 31);
     }
 }
@@ -106,16 +110,18 @@ static __global__ void construct_nh_kernel(int *__restrict__ flat, unsigned char
 // bucket_value_to_its_index[scalars[k]], skip when 0. Also serves the literal blst-named shim.
 static __global__ void tile_lookup_kernel(const int *__restrict__ bvals, const unsigned char *__restrict__ signs,
                                    const uint32_t *__restrict__ pidx, size_t m, const int *__restrict__ v2i,
-                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count, uint32_t lo, uint32_t hi) {
+                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count,
+                                   uint32_t *__restrict__ ranks, uint32_t lo, uint32_t hi) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m) return;
     int idx = v2i ? v2i[bvals[k]] : bvals[k];
-    uint32_t key = KEY_SKIP;
+    uint32_t key = KEY_SKIP, rank = 0;
     if (idx != 0 && (uint32_t)idx >= lo && (uint32_t)idx < hi) {
         key = (uint32_t)idx;
-        atomicAdd(&count[idx], 1u);
+        rank = atomicAdd(&count[idx], 1u);
     }
     keys[k] = key;
+    ranks[k] = rank;
     vals[k] = pidx[k] | ((uint32_t)(signs[k] != 0) << 31);
 }
 
@@ -123,7 +129,8 @@ static __global__ void tile_lookup_kernel(const int *__restrict__ bvals, const u
 // front end of pippenger_variant_BGMW95 (main_p1.cpp:311-375) including the r - a switch for the
 // configurations with e'*h' == 255 (`trick`). r = group order (auxiliaryfunc.h:5-7).
 static __global__ void digits_bgmw_kernel(const uint32_t *__restrict__ scalars, size_t n, int h, int e, int trick,
-                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count, int digit_major, uint32_t lo, uint32_t hi) {
+                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count,
+                                   uint32_t *__restrict__ ranks, int digit_major, uint32_t lo, uint32_t hi) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -154,13 +161,14 @@ static __global__ void digits_bgmw_kernel(const uint32_t *__restrict__ scalars, 
         int mag = d < 0 ? -d : d;
         if (mag > qhalf) mag = qhalf;  // unreachable for scalars < r except with prob 2^-62; clamp
         size_t slot = i * h + j;
-        uint32_t key = KEY_SKIP;
+        uint32_t key = KEY_SKIP, rank = 0;
         if (mag != 0 && (uint32_t)mag >= lo && (uint32_t)mag < hi) {
             key = (uint32_t)mag;
-            atomicAdd(&count[mag], 1u);
+            rank = atomicAdd(&count[mag], 1u);
         }
         const size_t at = digit_major ? (size_t)j * n + i : slot;
         keys[at] = key;
+        if (ranks) ranks[at] = rank;
         vals[at] = (uint32_t)slot | ((sign ^ flip) << 31);
     }
 }
@@ -170,7 +178,8 @@ static __global__ void digits_bgmw_kernel(const uint32_t *__restrict__ scalars, 
 // [t*w, t*w + wb) plus the bit below it; the top tile has wb = nbits % w (possibly 0) and is unsigned.
 // key = t * (2^(w-1) + 1) + |digit|; all tiles are emitted at once (ntiles entries per scalar).
 static __global__ void digits_booth_kernel(const uint32_t *__restrict__ scalars, size_t n, int nbits, int w, int ntiles,
-                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count, int digit_major, uint32_t lo, uint32_t hi) {
+                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count,
+                                    uint32_t *__restrict__ ranks, int digit_major, uint32_t lo, uint32_t hi) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -187,13 +196,14 @@ static __global__ void digits_booth_kernel(const uint32_t *__restrict__ scalars,
         int d = (int)((wval + 1u) >> 1) - (sign ? (1 << cbits) : 0);
         int mag = d < 0 ? -d : d;
         size_t slot = i * ntiles + t;
-        uint32_t key = KEY_SKIP;
+        uint32_t key = KEY_SKIP, rank = 0;
         if (mag != 0 && (uint32_t)mag >= lo && (uint32_t)mag < hi) {
             key = (uint32_t)t * nbw + (uint32_t)mag;
-            atomicAdd(&count[key], 1u);
+            rank = atomicAdd(&count[key], 1u);
         }
         const size_t at = digit_major ? (size_t)t * n + i : slot;
         keys[at] = key;
+        if (ranks) ranks[at] = rank;
         vals[at] = (uint32_t)i | (sign << 31);
     }
 }
@@ -280,13 +290,14 @@ static __global__ void scan_finish_kernel(const uint64_t *__restrict__ scanned, 
     cursor[b] = 0;
 }
 static __global__ void scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, size_t m,
-                               const uint32_t *__restrict__ seg_start, uint32_t *__restrict__ cursor,
+                               const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ ranks,
                                uint32_t *__restrict__ sorted, uint32_t *__restrict__ bucket_of /* may be null */) {
+    // counting-sort scatter; the position inside the bucket was fixed by the histogram atomic (ranks), so no atomics here
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m) return;
     uint32_t key = keys[k];
     if (key == KEY_SKIP) return;
-    uint32_t pos = seg_start[key] + atomicAdd(&cursor[key], 1u);
+    uint32_t pos = seg_start[key] + ranks[k];
     sorted[pos] = vals[k];
     if (bucket_of) bucket_of[pos] = key;
 }
@@ -758,9 +769,9 @@ static __global__ void __launch_bounds__(256) tree_tail_kernel(xyzz_t<F> *in, ui
 //             its hi digit (2 additions per bucket, the reference's count) -> two dense arrays of <= 2^11 sums;
 //   stage 2   every dense entry v is added to the list of each set bit of v (sliced, then the slices summed);
 //   final     Horner over the bit positions (bits_finalize_kernel).
-// All three stages are the SAME kernel: a static plan (built once on the host from the bucket values, ReducePlan in
-// engine.hpp) names the members of every list; a team of `tl` lanes strides over one list and folds its partial
-// sums with a shuffle tree. Lists have near-equal lengths, so all lanes of the machine are busy.
+// Every stage is a LIST SUM: a static plan (built once on the host from the bucket values, ReducePlan in engine.hpp)
+// names the members of every list. Stage 1 cuts the digit lists into equal slices and gives each slice to one lane
+// (list_sum_kernel); the slices of a list, and all later stages, are summed by quads (list_sum_coop_kernel).
 //   MODE 0: members are buckets, sums are XYZZ partials at src[item_start[b]] (skipped when count[b] == 0)
 //   MODE 1: same, but the sums are affine points (batch-affine accumulation)
 //   MODE 2: members index a dense XYZZ array (output of the previous stage)
@@ -775,45 +786,35 @@ template <class F, int MODE>
 static __global__ void __launch_bounds__(128) list_sum_kernel(const void *__restrict__ src, const uint32_t *__restrict__ count,
                                                               const uint32_t *__restrict__ item_start, uint32_t in_stride,
                                                               const uint32_t *__restrict__ start, const uint32_t *__restrict__ idx,
-                                                              uint32_t nlists, uint32_t nwindows, uint32_t tl, xyzz_t<F> *__restrict__ out) {
-    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t gl = gt / tl, sl = gt % tl;  // tl is a power of two <= 32: teams never straddle a warp
-    const uint32_t total = nlists * nwindows;
+                                                              uint32_t nlists, uint32_t nwindows, xyzz_t<F> *__restrict__ out) {
+    // one LANE per list (stage 1: the lists are equal-length slices, so the lanes of a warp have equal trip counts);
+    // the accumulator never has its address taken, so it lives in registers
+    const uint32_t gl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gl >= nlists * nwindows) return;
+    const uint32_t w = gl / nlists, li = gl % nlists;
     xyzz_t<F> acc;
     xyzz_set_inf(acc);
-    if (gl < total) {
-        const uint32_t w = gl / nlists, li = gl % nlists;
-        const uint32_t e1 = start[li + 1];
+    const uint32_t e1 = start[li + 1];
 #pragma unroll 1
-        for (uint32_t e = start[li] + sl; e < e1; e += tl) {
-            const size_t b = (size_t)w * in_stride + idx[e];
-            if (MODE == 2) {
+    for (uint32_t e = start[li]; e < e1; e++) {
+        const size_t b = (size_t)w * in_stride + idx[e];
+        if (MODE == 2) {
+            xyzz_t<F> s;
+            load_xyzz(s, (const xyzz_t<F> *)src + b);
+            xyzz_add(acc, s);
+        } else if (count[b] != 0) {
+            if (MODE == 1) {
+                aff_t<F> a;
+                load_affine(a, (const aff_t<F> *)src, item_start[b]);
+                xyzz_add_affine(acc, a, false);
+            } else {
                 xyzz_t<F> s;
-                load_xyzz(s, (const xyzz_t<F> *)src + b);
+                load_xyzz(s, (const xyzz_t<F> *)src + item_start[b]);
                 xyzz_add(acc, s);
-            } else if (count[b] != 0) {
-                if (MODE == 1) {
-                    aff_t<F> a;
-                    load_affine(a, (const aff_t<F> *)src, item_start[b]);
-                    xyzz_add_affine(acc, a, false);
-                } else {
-                    xyzz_t<F> s;
-                    load_xyzz(s, (const xyzz_t<F> *)src + item_start[b]);
-                    xyzz_add(acc, s);
-                }
             }
         }
     }
-    __syncwarp();
-#pragma unroll 1
-    for (uint32_t o = tl >> 1; o > 0; o >>= 1) {
-        xyzz_t<F> other;
-        xyzz_shfl_down(other, acc, (int)o);
-        if (sl + o >= tl) xyzz_set_inf(other);  // partner belongs to another team (or wrapped): add nothing
-        xyzz_add_cold(acc, other);
-        __syncwarp();
-    }
-    if (gl < total && sl == 0) out[gl] = acc;
+    out[gl] = acc;
 }
 
 // Horner over bit positions: L[w * nbits_w + k] is the sum of everything whose value has bit k set in window w, i.e.
