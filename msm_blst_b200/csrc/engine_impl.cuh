@@ -155,7 +155,8 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         MSM_CUDA(c, cudaStreamSynchronize(st));
         int rounds = 1;
         while (((size_t)1 << rounds) < max_count) rounds++;
-        constexpr int BATCH = sizeof(F) > 48 ? 8 : 32;
+        int BATCH = sizeof(F) > 48 ? 8 : 32;
+        if (const char *e = getenv("MSMB200_BA_BATCH")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) BATCH = v; }
         const size_t out_cap = m / 2 + 2 * nb + 4;
         if (ensure(c, c->pts_a, out_cap * sizeof(aff_t<F>)) || ensure(c, c->pts_b, (out_cap / 2 + 2 * nb + 4) * sizeof(aff_t<F>)) ||
             ensure(c, c->bo_a, out_cap * 4) || ensure(c, c->bo_b, (out_cap / 2 + 2 * nb + 4) * 4) || ensure(c, c->base_a, nb * 4) ||
@@ -176,12 +177,18 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
             scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(ts[o], ntiles);
             ba_scan_finish_kernel<<<blocks_for(nb, 256), 256, 0, st>>>((const uint64_t *)c->scanned.p, ts[o], base[o], nb);
             const size_t threads = (bound_in / 2 + BATCH - 1) / BATCH + 1;
-            if (r == 0)
-                ba_round_kernel<F, true, BATCH><<<blocks_for(threads, 128), 128, 0, st>>>(d_table, (const uint32_t *)c->sorted.p, nullptr, bo_in, base_in,
-                                                                                          count, r, tot_in, base[o], pts[o], bo[o], getenv("MSMB200_BA_LANEINV") ? 1 : 0);
-            else
-                ba_round_kernel<F, false, BATCH><<<blocks_for(threads, 128), 128, 0, st>>>(d_table, nullptr, in_pts, bo_in, base_in, count, r, tot_in,
-                                                                                           base[o], pts[o], bo[o], getenv("MSMB200_BA_LANEINV") ? 1 : 0);
+            const int laneinv = getenv("MSMB200_BA_LANEINV") ? 1 : 0;
+#define MSM_BA_LAUNCH(B_)                                                                                                                          \
+    do {                                                                                                                                           \
+        if (r == 0)                                                                                                                                \
+            ba_round_kernel<F, true, B_><<<blocks_for(threads, 128), 128, 0, st>>>(d_table, (const uint32_t *)c->sorted.p, nullptr, bo_in, base_in, \
+                                                                                   count, r, tot_in, base[o], pts[o], bo[o], laneinv);             \
+        else                                                                                                                                       \
+            ba_round_kernel<F, false, B_><<<blocks_for(threads, 128), 128, 0, st>>>(d_table, nullptr, in_pts, bo_in, base_in, count, r, tot_in,     \
+                                                                                    base[o], pts[o], bo[o], laneinv);                              \
+    } while (0)
+            if (BATCH == 4) MSM_BA_LAUNCH(4); else if (BATCH == 8) MSM_BA_LAUNCH(8); else if (BATCH == 16) MSM_BA_LAUNCH(16); else MSM_BA_LAUNCH(32);
+#undef MSM_BA_LAUNCH
             c->launches += 5;
             in_pts = pts[o];
             bo_in = bo[o];
@@ -405,9 +412,12 @@ static int tile_impl(Ctx *c, const void *d_table, const int *d_bvals, const unsi
 }
 
 template <class F> static int sum_partials_impl(Ctx *c, const void *d_partials, int count) {
-    if (ensure(c, c->result, sizeof(jac_t<F>) + sizeof(aff_t<F>))) return MSMB200_ECUDA;
+    if (ensure(c, c->result, sizeof(jac_t<F>) + sizeof(aff_t<F>)) || ensure(c, c->red_c, sizeof(xyzz_t<F>) + 64)) return MSMB200_ECUDA;
     aff_t<F> *d_aff = (aff_t<F> *)((char *)c->result.p + sizeof(jac_t<F>));
-    sum_partials_kernel<F><<<1, 32, 0, c->stream>>>((const jac_t<F> *)d_partials, count, d_aff);
+    if (getenv("MSMB200_SERIAL_FINALIZE"))
+        sum_partials_kernel<F><<<1, 32, 0, c->stream>>>((const jac_t<F> *)d_partials, count, d_aff);
+    else
+        sum_partials_coop_kernel<F><<<1, 32, 0, c->stream>>>((const jac_t<F> *)d_partials, count, (xyzz_t<F> *)c->red_c.p, d_aff);
     MSM_CUDA(c, cudaMemcpyAsync(c->h_result, d_aff, sizeof(aff_t<F>), cudaMemcpyDeviceToHost, c->stream));
     MSM_CUDA(c, cudaStreamSynchronize(c->stream));
     return MSMB200_OK;

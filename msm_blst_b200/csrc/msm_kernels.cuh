@@ -1055,6 +1055,53 @@ static __global__ void sum_partials_kernel(const jac_t<F> *__restrict__ partials
     *out_aff = a;
 }
 
+// Quad-cooperative form: one warp, quad j folds partials j, j+8, ... (Jacobian (X, Y, Z) read as XYZZ (X, Y, Z^3, Z^2)),
+// then a 3-level tree over the quads: ~14 multiplication levels for 8 GPUs instead of 7 dependent 16M additions.
+template <class F>
+static __global__ void __launch_bounds__(32) sum_partials_coop_kernel(const jac_t<F> *__restrict__ partials, int count, xyzz_t<F> *__restrict__ scratch,
+                                                                     aff_t<F> *__restrict__ out_aff) {
+    const int l = threadIdx.x & 3, j = threadIdx.x >> 2;
+    F acc;
+    f_set_zero(acc);
+#pragma unroll 1
+    for (int base = 0; base < count; base += 8) {
+        const int k = base + j;
+        F c, z;
+        f_set_zero(c);
+        f_set_zero(z);
+        if (k < count) {
+            const F *p = reinterpret_cast<const F *>(partials + k);
+            z = p[2];
+            c = p[l < 2 ? l : 2];
+        }
+        F zz, zzz;
+        f_sqr(zz, z);
+        f_mul(zzz, zz, z);
+        if (l == 2) c = zzz;
+        if (l == 3) c = zz;
+        if (base == 0) acc = c;
+        else dq_add(acc, c);
+    }
+#pragma unroll 1
+    for (int o = 1; o < 8; o <<= 1) {
+        F other;
+        dq_shfl_down(other, acc, 4 * o);
+        if (j + o >= 8) f_set_zero(other);
+        dq_add(acc, other);
+    }
+    if (j == 0) dq_store(scratch, acc);
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    xyzz_t<F> full;
+    load_xyzz(full, scratch);
+    jac_t<F> jj;
+    if (xyzz_is_inf(full)) jac_set_inf(jj);
+    else xyzz_to_jac(jj, full);
+    aff_t<F> a;
+    jac_to_affine(a, jj);
+    *out_aff = a;
+}
+
 // ------------------------------------------------------------------------------------------------
 // precomputation tables and fixed points
 // ------------------------------------------------------------------------------------------------
