@@ -55,11 +55,11 @@ uint32_t pick_vspan_host(size_t max_value, uint32_t nwindows) {
 // Quads per list for the cooperative list sums. `resident` 128-thread blocks fit on an SM, i.e. `resident` warps per
 // sub-partition per wave; a sub-partition with one warp runs at about half the pipe rate, so up to 2 warps are free;
 // a partially filled last wave costs a whole chain again.
-static uint32_t pick_quads(size_t total_lists, double avg_len, int subparts, int resident) {
-    uint32_t best = 8;
+static uint32_t pick_quads(size_t total_lists, double avg_len, int subparts, int resident, int gpw) {
+    uint32_t best = (uint32_t)gpw;
     double best_cost = 1e300;
-    for (uint32_t tq = 8; tq >= 1; tq >>= 1) {
-        const double warps = std::ceil((double)total_lists * tq / 8.0), per_wave = (double)subparts * resident;
+    for (uint32_t tq = (uint32_t)gpw; tq >= 1; tq >>= 1) {
+        const double warps = std::ceil((double)total_lists * tq / (double)gpw), per_wave = (double)subparts * resident;
         const double full = std::floor(warps / per_wave), rem = warps - full * per_wave;
         double load = full * std::max(2.0, (double)resident);
         if (rem > 0) load += std::max(2.0, std::ceil(rem / subparts));
@@ -102,7 +102,7 @@ int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, u
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     const int subparts = 4 * sms;
-    const int res1 = c->ops->resident_blocks(0), resq = c->ops->resident_blocks(1);
+    const int res1 = c->ops->resident_blocks(0), resq = c->ops->resident_blocks(1), gpw = c->ops->resident_blocks(2);
     const uint32_t maxv = nbw > 1 ? (values ? (uint32_t)values[nbw - 1] : (uint32_t)(nbw - 1)) : 1u;
     uint32_t V = 0;
     while (V < 32 && (maxv >> V) != 0) V++;
@@ -128,13 +128,18 @@ int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, u
             if (v >> c_lo) idx[cur[nlo + (v >> c_lo) - 1]++] = (uint32_t)l;
         }
     }
-    // stage 1: one LANE per slice of a digit list, slices sized so that ~3 warps per SM sub-partition have equal work
-    // (perfect balance whatever the list lengths); stage 1b: the slices of each digit list, summed by quads
-    // slices sized so that the whole stage is ONE wave of resident blocks (a partially filled second wave would cost a
-    // full chain again); 8 % head-room for the ragged last slice of every list
+    // stage 1: one LANE per slice of a digit list (perfect balance whatever the list lengths), slices sized so that the
+    // whole stage is exactly ONE wave of resident blocks (a partially filled second wave would cost a full chain again);
+    // stage 1b: the slices of each digit list, summed by lane groups
     plan.s1_coop = getenv("MSMB200_S1COOP") && atoi(getenv("MSMB200_S1COOP")) != 0;
-    const double lanes1 = (plan.s1_coop ? 8.0 * resq : 32.0 * res1) * subparts * 0.92;
+    const double lanes1 = (plan.s1_coop ? (double)gpw * resq : 32.0 * res1) * subparts;
     uint32_t slice1 = (uint32_t)std::max(2.0, std::ceil((double)idx.size() * nwindows / lanes1));
+    auto count_slices = [&](uint32_t sl) {
+        size_t n = 0;
+        for (uint32_t i = 0; i < nl1; i++) n += (start[i + 1] - start[i] + sl - 1) / sl;
+        return n * nwindows;
+    };
+    while (slice1 < (1u << 20) && (double)count_slices(slice1) > lanes1) slice1 += std::max(1u, slice1 / 16);  // ragged last slices
     if (const char *e = getenv("MSMB200_SLICE1")) slice1 = (uint32_t)std::max(1, atoi(e));
     std::vector<uint32_t> start_s, start_g, idx_g;
     slice_lists(start, slice1, start_s, start_g, idx_g);
@@ -143,7 +148,7 @@ int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, u
     plan.s1.tl = 1;
     rc = upload_list_plan(c, plan.s1b, start_g, idx_g);
     if (rc) return rc;
-    plan.s1b.tl = pick_quads((size_t)nl1 * nwindows, nl1 ? (double)idx_g.size() / nl1 : 1.0, subparts, resq);
+    plan.s1b.tl = pick_quads((size_t)nl1 * nwindows, nl1 ? (double)idx_g.size() / nl1 : 1.0, subparts, resq, gpw);
     // stage 2a: bit k of the lo (k < c_lo) or hi (k >= c_lo) digit value, cut into slices of SLICE members; 2b: bit lists
     const uint32_t SLICE = 32, nbits = c_lo + chi;
     std::vector<uint32_t> start_a(1, 0), idx_a, start_as, start_b, idx_b;
@@ -157,10 +162,10 @@ int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, u
     slice_lists(start_a, SLICE, start_as, start_b, idx_b);
     rc = upload_list_plan(c, plan.s2a, start_as, idx_a);
     if (rc) return rc;
-    plan.s2a.tl = pick_quads((size_t)plan.s2a.nlists * nwindows, plan.s2a.nlists ? (double)idx_a.size() / plan.s2a.nlists : 1.0, subparts, resq);
+    plan.s2a.tl = pick_quads((size_t)plan.s2a.nlists * nwindows, plan.s2a.nlists ? (double)idx_a.size() / plan.s2a.nlists : 1.0, subparts, resq, gpw);
     rc = upload_list_plan(c, plan.s2b, start_b, idx_b);
     if (rc) return rc;
-    plan.s2b.tl = pick_quads((size_t)nbits * nwindows, nbits ? (double)idx_b.size() / nbits : 1.0, subparts, resq);
+    plan.s2b.tl = pick_quads((size_t)nbits * nwindows, nbits ? (double)idx_b.size() / nbits : 1.0, subparts, resq, gpw);
     plan.c_lo = c_lo;
     plan.nbits_w = nbits;
     plan.key_nbw = nbw;

@@ -100,7 +100,7 @@ struct GroupOps {
     int (*point_op)(int op, const void *a, const void *b, const unsigned char *flags, void *out, size_t n);
     int (*digits)(Ctx *, int kind, const void *d_scalars, size_t n, uint32_t *d_keys, uint32_t *d_vals);
     // resident 128-thread blocks per SM of the list-sum kernels (0: list_sum_kernel stage 1, 1: list_sum_coop_kernel):
-    // the reduction plan sizes its grids to whole waves
+    // the reduction plan sizes its grids to whole waves; which == 2: lane groups per warp of the cooperative kernels
     int (*resident_blocks)(int which);
 };
 

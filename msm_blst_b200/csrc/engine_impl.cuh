@@ -139,7 +139,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         if (heavy_items > 1) {
             // at most min(nb, m / item_len) buckets have more than one work item; grid sized for that bound, idle warps exit
             const size_t max_light = std::min(nb, m / item_len + 1);
-            combine_light_kernel<FC><<<blocks_for(max_light * 4, 128), 128, 0, st>>>(count, (const uint32_t *)c->item_start.p,
+            combine_light_kernel<FC><<<blocks_for(max_light * coop_group_lanes<typename coop_of<FC>::type>(), 128), 128, 0, st>>>(count, (const uint32_t *)c->item_start.p,
                                                                                     (const uint32_t *)c->light.p, item_len, (xyzz_t<FC> *)c->partial.p);
             c->launches += 1;
         }
@@ -215,7 +215,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
                                                           (const uint32_t *)P.s1.start.p, (const uint32_t *)P.s1.idx.p, P.s1.nlists, nw,
                                                           (xyzz_t<F> *)c->red_a.p);
             else if (P.s1_coop)
-                list_sum_coop_kernel<FC, 0><<<blocks_for((size_t)nw * P.s1.nlists * 4, 128), 128, 0, st>>>(
+                list_sum_coop_kernel<FC, 0><<<blocks_for((size_t)nw * P.s1.nlists * coop_group_lanes<typename coop_of<FC>::type>(), 128), 128, 0, st>>>(
                     (const xyzz_t<FC> *)bucket_points, count, bucket_point_index, L.nbw, (const uint32_t *)P.s1.start.p,
                     (const uint32_t *)P.s1.idx.p, P.s1.nlists, nw, 1, (xyzz_t<FC> *)c->red_a.p);
             else
@@ -225,7 +225,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         }
         // stages 1b, 2a, 2b: quad-cooperative list sums over dense arrays
         auto coop = [&](const ListPlan &lp, const void *src, uint32_t in_stride, void *dst) {
-            list_sum_coop_kernel<FC, 2><<<blocks_for((size_t)nw * lp.nlists * lp.tl * 4, 128), 128, 0, st>>>(
+            list_sum_coop_kernel<FC, 2><<<blocks_for((size_t)nw * lp.nlists * lp.tl * coop_group_lanes<typename coop_of<FC>::type>(), 128), 128, 0, st>>>(
                 (const xyzz_t<FC> *)src, nullptr, nullptr, in_stride, (const uint32_t *)lp.start.p, (const uint32_t *)lp.idx.p, lp.nlists, nw,
                 lp.tl, (xyzz_t<FC> *)dst);
         };
@@ -508,6 +508,7 @@ template <class F> static int digits_impl(Ctx *c, int kind, const void *d_scalar
 }
 
 template <class F, class FC> static int resident_blocks_impl(int which) {
+    if (which == 2) return 32 / coop_group_lanes<typename coop_of<FC>::type>();  // groups per warp of the cooperative kernels
     int nb = 0;
     cudaError_t e = which == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, list_sum_kernel<F, 0>, 128, 0)
                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, list_sum_coop_kernel<FC, 2>, 128, 0);
@@ -516,7 +517,8 @@ template <class F, class FC> static int resident_blocks_impl(int which) {
 
 template <class F, class FC> static int point_op_impl(int op, const void *a, const void *b, const unsigned char *flags, void *out, size_t n) {
     if (op == 2 || op == 3) point_op_xyzz_kernel<F><<<blocks_for(n, 128), 128>>>(op, a, b, flags, out, n);
-    else if (op == 6 || op == 7) point_op_coop_kernel<FC><<<blocks_for(4 * n, 128), 128>>>(op, a, b, out, n);
+    else if (op == 6 || op == 7)
+        point_op_coop_kernel<FC><<<blocks_for(coop_group_lanes<typename coop_of<FC>::type>() * n, 128), 128>>>(op, a, b, out, n);
     else point_op_misc_kernel<FC><<<blocks_for(n, 128), 128>>>(op, a, b, out, n);
     return cudaGetLastError() == cudaSuccess ? 0 : MSMB200_ECUDA;
 }

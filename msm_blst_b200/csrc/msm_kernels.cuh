@@ -855,9 +855,10 @@ static __global__ void bits_finalize_kernel(const xyzz_t<F> *__restrict__ L, uin
     }
 }
 
-// Quad-cooperative variants (coop.cuh: a point is distributed over 4 lanes): list sums with one QUAD per team slot
-// (tq quads per list, tq a power of two <= 8), and the Horner pass with the bit positions spread over the 8 quads of
-// one warp. Control flow is warp-uniform; trip counts are the warp maximum and idle quads add infinity.
+// Lane-cooperative variants (coop.cuh: a point is distributed over a GROUP of 4 lanes for G1, 8 lanes for G2): list
+// sums with one group per team slot (tq groups per list, tq a power of two <= groups per warp), and the Horner pass
+// with the bit positions spread over the groups of one warp. Control flow is warp-uniform; trip counts are the warp
+// maximum and idle groups add infinity.
 //   MODE 0: members are buckets; their sums are the XYZZ partials src[item_start[b]] (skipped when count[b] == 0)
 //   MODE 2: members index a dense XYZZ array
 template <class F, int MODE>
@@ -865,8 +866,10 @@ static __global__ void __launch_bounds__(128) list_sum_coop_kernel(const xyzz_t<
                                                                    const uint32_t *__restrict__ item_start, uint32_t in_stride,
                                                                    const uint32_t *__restrict__ start, const uint32_t *__restrict__ idx,
                                                                    uint32_t nlists, uint32_t nwindows, uint32_t tq, xyzz_t<F> *__restrict__ out) {
+    using C = typename coop_of<F>::type;
+    constexpr uint32_t GL = coop_group_lanes<C>();
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t gq = gt >> 2, gl = gq / tq, sq = gq % tq;
+    const uint32_t gq = gt / GL, gl = gq / tq, sq = gq % tq;
     const uint32_t total = nlists * nwindows;
     const bool live = gl < total;
     uint32_t e0 = 0, e1 = 0;
@@ -879,44 +882,41 @@ static __global__ void __launch_bounds__(128) list_sum_coop_kernel(const xyzz_t<
     }
     const uint32_t my_iters = e1 > e0 ? (e1 - e0 + tq - 1) / tq : 0u;
     const uint32_t iters = __reduce_max_sync(0xffffffffu, my_iters);
-    F acc;
+    C acc;
     f_set_zero(acc);
 #pragma unroll 1
     for (uint32_t it = 0; it < iters; it++) {
         const uint32_t e = e0 + it * tq;
         const bool have = e < e1;
+        C s;
+        f_set_zero(s);
         if (MODE == 2) {
-            F s;
-            f_set_zero(s);
             if (have) dq_load(s, src + base + idx[e]);
-            if (it == 0) acc = s;
-            else dq_add(acc, s);
-        } else {
-            F s;
-            f_set_zero(s);
-            if (have) {
-                const size_t b = base + idx[e];
-                if (count[b] != 0) dq_load(s, src + item_start[b]);
-            }
-            dq_add(acc, s);
+        } else if (have) {
+            const size_t b = base + idx[e];
+            if (count[b] != 0) dq_load(s, src + item_start[b]);
         }
+        if (it == 0) acc = s;
+        else dq_add(acc, s);
     }
 #pragma unroll 1
     for (uint32_t o = tq >> 1; o > 0; o >>= 1) {
-        F other;
-        dq_shfl_down(other, acc, (int)(4 * o));
+        C other;
+        dq_shfl_down(other, acc, (int)(GL * o));
         if (sq + o >= tq) f_set_zero(other);
         dq_add(acc, other);
     }
     if (live && sq == 0) dq_store(out + gl, acc);
 }
 
-// Buckets split into 2..heavy_items work items: one quad per bucket folds the partials into the first one.
+// Buckets split into 2..heavy_items work items: one group per bucket folds the partials into the first one.
 template <class F>
 static __global__ void __launch_bounds__(128) combine_light_kernel(const uint32_t *__restrict__ count, const uint32_t *__restrict__ item_start,
                                                                    const uint32_t *__restrict__ light, uint32_t item_len, xyzz_t<F> *partial) {
+    using C = typename coop_of<F>::type;
+    constexpr uint32_t GL = coop_group_lanes<C>();
     const uint32_t nlight = light[0];
-    const uint32_t gq = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const uint32_t gq = (blockIdx.x * blockDim.x + threadIdx.x) / GL;
     if (__all_sync(0xffffffffu, gq >= nlight)) return;
     uint32_t first = 0, nitems = 0;
     if (gq < nlight) {
@@ -925,11 +925,11 @@ static __global__ void __launch_bounds__(128) combine_light_kernel(const uint32_
         nitems = (count[b] + item_len - 1) / item_len;
     }
     const uint32_t maxitems = __reduce_max_sync(0xffffffffu, nitems);
-    F acc;
+    C acc;
     f_set_zero(acc);
 #pragma unroll 1
     for (uint32_t k = 0; k < maxitems; k++) {
-        F s;
+        C s;
         f_set_zero(s);
         if (k < nitems) dq_load(s, partial + first + k);
         if (k == 0) acc = s;
@@ -938,32 +938,35 @@ static __global__ void __launch_bounds__(128) combine_light_kernel(const uint32_
     if (nitems) dq_store(partial + first, acc);
 }
 
-template <class F> __device__ __forceinline__ void dq_shift(F &acc, uint32_t my_doublings) {
+template <class C> __device__ __forceinline__ void dq_shift(C &acc, uint32_t my_doublings) {
     const uint32_t maxd = __reduce_max_sync(0xffffffffu, my_doublings);
 #pragma unroll 1
     for (uint32_t i = 0; i < maxd; i++) {
-        F d;
+        C d;
         dq_double(d, acc);
         if (i < my_doublings) acc = d;
     }
 }
-// One warp. Entries in descending bit position: t = 0..G-1 <-> (w = nwindows-1 - t / nbits_w, k = nbits_w-1 - t % nbits_w),
-// position w * wbits + k. Quad j runs Horner over entries [j*len, (j+1)*len); the 8 partial results are combined by a
-// tree in which the quad holding the higher positions is doubled down to its partner's lowest position.
+// One warp of NG groups. Entries in descending bit position: t = 0..G-1 <-> (w = nwindows-1 - t / nbits_w,
+// k = nbits_w-1 - t % nbits_w), position w * wbits + k. Group j runs Horner over entries [j*len, (j+1)*len); the NG
+// partial results are combined by a tree in which the group holding the higher positions is doubled down to its
+// partner's lowest position.
 template <class F>
 static __global__ void __launch_bounds__(32) bits_finalize_coop_kernel(const xyzz_t<F> *__restrict__ L, uint32_t nwindows, uint32_t nbits_w,
                                                                       uint32_t wbits, xyzz_t<F> *__restrict__ scratch,
                                                                       jac_t<F> *__restrict__ out_jac, aff_t<F> *__restrict__ out_aff) {
-    const uint32_t G = nwindows * nbits_w, j = threadIdx.x >> 2;
-    const uint32_t len = (G + 7) / 8;
+    using C = typename coop_of<F>::type;
+    constexpr uint32_t GL = coop_group_lanes<C>(), NG = 32 / GL;
+    const uint32_t G = nwindows * nbits_w, j = threadIdx.x / GL;
+    const uint32_t len = (G + NG - 1) / NG;
     const uint32_t t0 = min(G, j * len), t1 = min(G, t0 + len);
-    F acc;
+    C acc;
     f_set_zero(acc);
-    uint32_t low = 0;  // lowest position folded into acc so far (0 for an empty quad)
+    uint32_t low = 0;  // lowest position folded into acc so far (0 for an empty group)
 #pragma unroll 1
     for (uint32_t s = 0; s < len; s++) {
         const uint32_t t = t0 + s;
-        F e;
+        C e;
         f_set_zero(e);
         uint32_t dbl = 0;
         if (t < t1) {
@@ -979,10 +982,10 @@ static __global__ void __launch_bounds__(32) bits_finalize_coop_kernel(const xyz
     }
     if (t0 >= t1) low = 0;
 #pragma unroll 1
-    for (uint32_t o = 1; o < 8; o <<= 1) {
-        F other;
-        dq_shfl_down(other, acc, (int)(4 * o));
-        const uint32_t low_other = __shfl_down_sync(0xffffffffu, low, 4 * o);
+    for (uint32_t o = 1; o < NG; o <<= 1) {
+        C other;
+        dq_shfl_down(other, acc, (int)(GL * o));
+        const uint32_t low_other = __shfl_down_sync(0xffffffffu, low, GL * o);
         const bool recv = (j % (2 * o)) == 0;
         if (!recv) f_set_zero(other);
         dq_shift(acc, recv ? low - low_other : 0u);
@@ -990,7 +993,7 @@ static __global__ void __launch_bounds__(32) bits_finalize_coop_kernel(const xyz
         if (recv) low = low_other;
     }
     dq_shift(acc, j == 0 ? low : 0u);
-    // gather the distributed result of quad 0 into one thread for the (single) inversion
+    // gather the distributed result of group 0 into one thread for the (single) inversion
     if (j == 0) dq_store(scratch, acc);
     __syncwarp();
     if (threadIdx.x != 0) return;
@@ -1055,38 +1058,41 @@ static __global__ void sum_partials_kernel(const jac_t<F> *__restrict__ partials
     *out_aff = a;
 }
 
-// Quad-cooperative form: one warp, quad j folds partials j, j+8, ... (Jacobian (X, Y, Z) read as XYZZ (X, Y, Z^3, Z^2)),
-// then a 3-level tree over the quads: ~14 multiplication levels for 8 GPUs instead of 7 dependent 16M additions.
+// Lane-cooperative form: one warp of NG groups, group j folds partials j, j+NG, ... (Jacobian (X, Y, Z) read as XYZZ
+// (X, Y, Z^3, Z^2)), then a tree over the groups: ~14 multiplication levels for 8 GPUs instead of 7 dependent 16M additions.
 template <class F>
 static __global__ void __launch_bounds__(32) sum_partials_coop_kernel(const jac_t<F> *__restrict__ partials, int count, xyzz_t<F> *__restrict__ scratch,
                                                                      aff_t<F> *__restrict__ out_aff) {
-    const int l = threadIdx.x & 3, j = threadIdx.x >> 2;
-    F acc;
+    using C = typename coop_of<F>::type;
+    constexpr int LPS = coop_traits<C>::LPS, GL = coop_group_lanes<C>(), NG = 32 / GL;
+    const int l = coop_slot<C>(), j = threadIdx.x / GL, sub = threadIdx.x & (LPS - 1);
+    C acc;
     f_set_zero(acc);
 #pragma unroll 1
-    for (int base = 0; base < count; base += 8) {
+    for (int base = 0; base < count; base += NG) {
         const int k = base + j;
-        F c, z;
+        C c, z;
         f_set_zero(c);
         f_set_zero(z);
         if (k < count) {
-            const F *p = reinterpret_cast<const F *>(partials + k);
-            z = p[2];
-            c = p[l < 2 ? l : 2];
+            const fp_t *p = reinterpret_cast<const fp_t *>(partials + k);  // pieces: x, y, z (each LPS x 48 bytes)
+            const fp_t zp = p[2 * LPS + sub], cp = p[(l < 2 ? l : 2) * LPS + sub];
+            *reinterpret_cast<fp_t *>(&z) = zp;
+            *reinterpret_cast<fp_t *>(&c) = cp;
         }
-        F zz, zzz;
+        C zz, zzz;
         f_sqr(zz, z);
         f_mul(zzz, zz, z);
-        if (l == 2) c = zzz;
-        if (l == 3) c = zz;
+        fq_sel(c, l == 2, zzz, c);
+        fq_sel(c, l == 3, zz, c);
         if (base == 0) acc = c;
         else dq_add(acc, c);
     }
 #pragma unroll 1
-    for (int o = 1; o < 8; o <<= 1) {
-        F other;
-        dq_shfl_down(other, acc, 4 * o);
-        if (j + o >= 8) f_set_zero(other);
+    for (int o = 1; o < NG; o <<= 1) {
+        C other;
+        dq_shfl_down(other, acc, GL * o);
+        if (j + o >= NG) f_set_zero(other);
         dq_add(acc, other);
     }
     if (j == 0) dq_store(scratch, acc);
@@ -1250,12 +1256,13 @@ static __global__ void __launch_bounds__(128) point_op_xyzz_kernel(int op, const
         ((xyzz_t<F> *)out)[i] = x;
     }
 }
-// ops 6,7: the quad-cooperative XYZZ addition / doubling (coop.cuh), one quad per element
+// ops 6,7: the lane-cooperative XYZZ addition / doubling (coop.cuh), one group (4 lanes G1, 8 lanes G2) per element
 template <class F>
 static __global__ void __launch_bounds__(128) point_op_coop_kernel(int op, const void *__restrict__ a, const void *__restrict__ b,
                                                                    void *__restrict__ out, size_t n) {
-    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    F x, y;
+    using C = typename coop_of<F>::type;
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / coop_group_lanes<C>();
+    C x, y;
     f_set_zero(x);
     f_set_zero(y);
     if (i < n) {
@@ -1263,7 +1270,7 @@ static __global__ void __launch_bounds__(128) point_op_coop_kernel(int op, const
         if (op == 6) dq_load(y, (const xyzz_t<F> *)b + i);
     }
     if (op == 6) dq_add(x, y);
-    else { F d; dq_double(d, x); x = d; }
+    else { C d; dq_double(d, x); x = d; }
     if (i < n) dq_store((xyzz_t<F> *)out + i, x);
 }
 template <class F>
