@@ -277,6 +277,12 @@ def cpu_baseline_leg(group, cfgname, method, n, sets, gpu_ctx):
 
 
 # ------------------------------------------------------------------------------------------------ main arm
+# From the committed `ncu --set full` capture of accumulate_kernel (profiles/r1c_ncu_full_g1_n21_summary.txt), per launch:
+# dram__bytes_read.sum + dram__bytes_write.sum, and the share of cycles the heavy FMA pipe (IMAD.WIDE) was busy.
+NCU_ACCUMULATE_DRAM_BYTES = {"g1_n21": 5221708000 + 163037184}
+NCU_ACCUMULATE_FMAHEAVY_PCT = {"g1_n21": 94.7}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -441,7 +447,8 @@ def main():
             line["roofline"] = {
                 "bound": "imad", "kernel": "accumulate_kernel (bucket accumulation, xyzz += affine)",
                 "achieved": achieved, "peak": peak_mac / 1e12, "unit": "TMAC/s (32x32+64-bit)", "frac": achieved / (peak_mac / 1e12),
-                "traffic": None,
+                "traffic": NCU_ACCUMULATE_DRAM_BYTES.get(args.workload) if method == 1 else None,
+                "fmaheavy_pipe_active_pct_ncu": NCU_ACCUMULATE_FMAHEAVY_PCT.get(args.workload) if method == 1 else None,
                 "note": "achieved = ALGORITHMIC MACs (n*h adds x C_add Fp-mul x 300 MAC, reference formulas SURVEY §8d) / CUDA-event time of the "
                         "accumulate phase; peak = IMAD.WIDE.U32 register-only microbenchmark measured in this run (MEASURED_PEAKS.json has no "
                         "integer figure). That microbenchmark reuses its multiplicands; with distinct operands the heavy FMA pipe issues one "
@@ -457,7 +464,8 @@ def main():
                 hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
             gbs = cm["gather_bytes"] / (acc_ms * 1e-3) / 1e9
             line["roofline_hbm"] = {"bound": "hbm", "kernel": "accumulate_kernel (table gather)", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                                    "frac": gbs / hbm_peak, "traffic": None, "peak_source": hbm_src}
+                                    "frac": gbs / hbm_peak, "traffic": NCU_ACCUMULATE_DRAM_BYTES.get(args.workload) if method == 1 else None,
+                                    "algorithmic_bytes": cm["gather_bytes"], "peak_source": hbm_src}
             if not args.no_cpu_baseline:
                 line["cpu_baseline"] = cpu_baseline_leg(group, cfgname, method, n, sets, ctx)
         print(json.dumps(line))

@@ -161,6 +161,23 @@ void msmb200_blst_p2_tile_pippenger_BGMW95(void *ret_jacobian, const void *const
 void msmb200_blst_p1s_add(void *ret_jacobian, const void *const points[], size_t npoints);
 void msmb200_blst_p2s_add(void *ret_jacobian, const void *const points[], size_t npoints);
 
+/* blst_p{1,2}s_mult_wbits_precompute{,_sizeof} / blst_p{1,2}s_mult_wbits{,_scratch_sizeof} (bindings/blst.h:228-236,
+ * :368-376; src/multi_scalar.c:81-261): the library's fixed-window table MSM (first half).
+ * table[i * 2^(wbits-1) + k] = (k + 1) * P_i, affine, in HOST memory in the reference's layout (byte-identical: affine
+ * points are canonical); mult_wbits recodes the scalars into signed wbits-windows like the reference, gathers the
+ * selected row entries on the device (one bucket per window) and combines the windows by Horner. `scratch` is
+ * ignored (scratch_sizeof returns 0). wbits in [1, 16], npoints * 2^(wbits-1) < 2^31. */
+size_t msmb200_blst_p1s_mult_wbits_precompute_sizeof(size_t wbits, size_t npoints);
+void msmb200_blst_p1s_mult_wbits_precompute(void *table_affine, size_t wbits, const void *const points[], size_t npoints);
+size_t msmb200_blst_p1s_mult_wbits_scratch_sizeof(size_t npoints);
+void msmb200_blst_p1s_mult_wbits(void *ret_jacobian, const void *table_affine, size_t wbits, size_t npoints,
+                                 const unsigned char *const scalars[], size_t nbits, void *scratch);
+size_t msmb200_blst_p2s_mult_wbits_precompute_sizeof(size_t wbits, size_t npoints);
+void msmb200_blst_p2s_mult_wbits_precompute(void *table_affine, size_t wbits, const void *const points[], size_t npoints);
+size_t msmb200_blst_p2s_mult_wbits_scratch_sizeof(size_t npoints);
+void msmb200_blst_p2s_mult_wbits(void *ret_jacobian, const void *table_affine, size_t wbits, size_t npoints,
+                                 const unsigned char *const scalars[], size_t nbits, void *scratch);
+
 /* ---- building blocks exposed for parity tests (each is a batched CUDA kernel launch; host buffers) ---
  * field ops on n elements. field: 1 = Fp (48 B), 2 = Fp2 (96 B).
  * op: 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 5 mul_by_3, 6 inverse        (blst_fp_mul ... bindings/blst.h:108-137),

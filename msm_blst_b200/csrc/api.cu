@@ -178,6 +178,15 @@ static int ctx_init_common(Ctx *c, int group, int device) {
     c->device = device;
     c->ops = group == 1 ? group_ops_g1() : group_ops_g2();
     MSM_CUDA(c, cudaSetDevice(device));
+    {
+        // The table gathers read 96 / 192-byte entries at random: ask L2 to fetch 32-byte sectors from DRAM instead of
+        // 128-byte lines (ncu: 5.2 GB read per n=2^21 launch for 2.4 GB of entries with the default granularity).
+        // A hint, device wide; MSMB200_L2_FETCH=0 leaves the default untouched.
+        const char *e = getenv("MSMB200_L2_FETCH");
+        int g = e ? atoi(e) : 32;
+        if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
+        cudaGetLastError();  // not supported -> ignore
+    }
     MSM_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
     for (auto &e : c->ev) MSM_CUDA(c, cudaEventCreate(&e));
@@ -564,10 +573,51 @@ static void shim_mult_pippenger(int group, void *ret, const void *const points[]
     }
     cudaMemcpyAsync(dp, hp.data(), hp.size(), cudaMemcpyHostToDevice, c->stream);
     cudaMemcpyAsync(ds, hs.data(), hs.size(), cudaMemcpyHostToDevice, c->stream);
-    if (c->ops->pippenger(c, dp, npoints, ds, (int)nbits, dj, false)) shim_fail(c, "blst_pNs_mult_pippenger");
+    if (c->ops->pippenger(c, dp, npoints, ds, (int)nbits, dj, false, 0)) shim_fail(c, "blst_pNs_mult_pippenger");
     cudaMemcpyAsync(ret, dj, jb, cudaMemcpyDeviceToHost, c->stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pNs_mult_pippenger"); }
     cudaFree(dp); cudaFree(ds); cudaFree(dj);
+}
+// blst_pNs_mult_wbits_precompute / blst_pNs_mult_wbits (bindings/blst.h:228-236,:368-376; src/multi_scalar.c:81-261): the
+// library's fixed-window table MSM. The table lives in HOST memory in the reference's layout (the caller owns it), so
+// the shim uploads it per call; it is gathered by the same accumulate kernel as the CHES / BGMW95 tables.
+static void shim_wbits_precompute(int group, void *table, size_t wbits, const void *const points[], size_t npoints) {
+    Ctx *c = shim_ctx(group);
+    size_t ab = c->ops->aff_bytes;
+    if (npoints == 0 || wbits == 0 || wbits > 16) return;
+    cudaSetDevice(c->device);
+    std::vector<unsigned char> hp;
+    gather_ptr_array(hp, points, npoints, ab, ab);
+    const size_t total = npoints << (wbits - 1);
+    void *dp = nullptr, *dt = nullptr;
+    if (cudaMalloc(&dp, hp.size()) != cudaSuccess || cudaMalloc(&dt, total * ab) != cudaSuccess) { c->err = "cudaMalloc"; shim_fail(c, "blst_pNs_mult_wbits_precompute"); }
+    cudaMemcpyAsync(dp, hp.data(), hp.size(), cudaMemcpyHostToDevice, c->stream);
+    if (c->ops->wbits_precompute(c, dp, npoints, (int)wbits, dt)) shim_fail(c, "blst_pNs_mult_wbits_precompute");
+    cudaMemcpyAsync(table, dt, total * ab, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pNs_mult_wbits_precompute"); }
+    cudaFree(dp); cudaFree(dt);
+}
+static void shim_mult_wbits(int group, void *ret, const void *table, size_t wbits, size_t npoints, const unsigned char *const scalars[], size_t nbits) {
+    Ctx *c = shim_ctx(group);
+    size_t ab = c->ops->aff_bytes, jb = c->ops->jac_bytes;
+    if (npoints == 0 || nbits == 0 || nbits > 255 || wbits == 0 || wbits > 16 || ((double)npoints * (double)((size_t)1 << (wbits - 1))) >= 2147483648.0) {
+        memset(ret, 0, jb);
+        return;
+    }
+    cudaSetDevice(c->device);
+    std::vector<unsigned char> hs;
+    gather_ptr_array(hs, (const void *const *)scalars, npoints, (nbits + 7) / 8, 32);
+    const size_t total = npoints << (wbits - 1);
+    void *dt = nullptr, *ds = nullptr, *dj = nullptr;
+    if (cudaMalloc(&dt, total * ab) != cudaSuccess || cudaMalloc(&ds, hs.size()) != cudaSuccess || cudaMalloc(&dj, jb) != cudaSuccess) {
+        c->err = "cudaMalloc"; shim_fail(c, "blst_pNs_mult_wbits");
+    }
+    cudaMemcpyAsync(dt, table, total * ab, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(ds, hs.data(), hs.size(), cudaMemcpyHostToDevice, c->stream);
+    if (c->ops->pippenger(c, dt, npoints, ds, (int)nbits, dj, false, (int)wbits)) shim_fail(c, "blst_pNs_mult_wbits");
+    cudaMemcpyAsync(ret, dj, jb, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pNs_mult_wbits"); }
+    cudaFree(dt); cudaFree(ds); cudaFree(dj);
 }
 static void shim_tile(int group, void *ret, const void *const points[], size_t npoints, const int scalars[], const unsigned char signs[],
                       const int *bucket_set_ascend, const int *v2i, size_t nbuckets, int d_max) {
@@ -641,6 +691,18 @@ static void shim_points_add(int group, void *ret, const void *const points[], si
 void msmb200_blst_p1s_add(void *ret, const void *const points[], size_t npoints) { shim_points_add(1, ret, points, npoints); }
 void msmb200_blst_p2s_add(void *ret, const void *const points[], size_t npoints) { shim_points_add(2, ret, points, npoints); }
 
+size_t msmb200_blst_p1s_mult_wbits_precompute_sizeof(size_t wbits, size_t npoints) { return ((size_t)96 * npoints) << (wbits - 1); }
+size_t msmb200_blst_p2s_mult_wbits_precompute_sizeof(size_t wbits, size_t npoints) { return ((size_t)192 * npoints) << (wbits - 1); }
+void msmb200_blst_p1s_mult_wbits_precompute(void *table, size_t wbits, const void *const points[], size_t npoints) { shim_wbits_precompute(1, table, wbits, points, npoints); }
+void msmb200_blst_p2s_mult_wbits_precompute(void *table, size_t wbits, const void *const points[], size_t npoints) { shim_wbits_precompute(2, table, wbits, points, npoints); }
+size_t msmb200_blst_p1s_mult_wbits_scratch_sizeof(size_t) { return 0; }  /* the device owns its scratch */
+size_t msmb200_blst_p2s_mult_wbits_scratch_sizeof(size_t) { return 0; }
+void msmb200_blst_p1s_mult_wbits(void *ret, const void *table, size_t wbits, size_t npoints, const unsigned char *const scalars[], size_t nbits, void *) {
+    shim_mult_wbits(1, ret, table, wbits, npoints, scalars, nbits);
+}
+void msmb200_blst_p2s_mult_wbits(void *ret, const void *table, size_t wbits, size_t npoints, const unsigned char *const scalars[], size_t nbits, void *) {
+    shim_mult_wbits(2, ret, table, wbits, npoints, scalars, nbits);
+}
 size_t msmb200_blst_p1s_mult_pippenger_scratch_sizeof(size_t npoints) { return (size_t)192 << (pippenger_window_size(npoints) - 1); }
 size_t msmb200_blst_p2s_mult_pippenger_scratch_sizeof(size_t npoints) { return (size_t)384 << (pippenger_window_size(npoints) - 1); }
 void msmb200_blst_p1s_mult_pippenger(void *ret, const void *const points[], size_t npoints, const unsigned char *const scalars[], size_t nbits, void *) {

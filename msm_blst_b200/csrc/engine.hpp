@@ -95,13 +95,15 @@ struct GroupOps {
                 size_t m, const int *d_v2i, const int *d_bucket_vals, size_t nbuckets, int d_max, const int *d_chunk_first, uint32_t vspan,
                 uint32_t nchunks, const ReducePlan *plan, void *d_out_jac);
     int (*pippenger)(Ctx *, const void *d_points, size_t npoints, const void *d_scalars, int nbits, void *d_out_jac,
-                     bool want_affine);
+                     bool want_affine, int wbits_table);
     int (*field_op)(int field, int op, const void *a, const void *b, void *out, size_t n);
     int (*point_op)(int op, const void *a, const void *b, const unsigned char *flags, void *out, size_t n);
     int (*digits)(Ctx *, int kind, const void *d_scalars, size_t n, uint32_t *d_keys, uint32_t *d_vals);
     // resident 128-thread blocks per SM of the list-sum kernels (0: list_sum_kernel stage 1, 1: list_sum_coop_kernel):
     // the reduction plan sizes its grids to whole waves; which == 2: lane groups per warp of the cooperative kernels
     int (*resident_blocks)(int which);
+    // table[i * 2^(wbits-1) + k] = (k + 1) * P_i (blst_pNs_mult_wbits_precompute), device buffers
+    int (*wbits_precompute)(Ctx *, const void *d_points, size_t npoints, int wbits, void *d_table);
 };
 
 int measure_peaks(double *macs_per_s, double *fp_mul_per_s);

@@ -179,12 +179,15 @@ static __global__ void digits_bgmw_kernel(const uint32_t *__restrict__ scalars, 
 // key = t * (2^(w-1) + 1) + |digit|; all tiles are emitted at once (ntiles entries per scalar).
 static __global__ void digits_booth_kernel(const uint32_t *__restrict__ scalars, size_t n, int nbits, int w, int ntiles,
                                     uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count,
-                                    uint32_t *__restrict__ ranks, int digit_major, uint32_t lo, uint32_t hi) {
+                                    uint32_t *__restrict__ ranks, int digit_major, uint32_t lo, uint32_t hi, uint32_t table_nwin) {
+    // table_nwin != 0: blst_p1s_mult_wbits mode (src/multi_scalar.c:176-261, same window recoding): the digit selects
+    // row entry |d| - 1 of point i's precomputed row (table_nwin = 2^(w-1) multiples per point) and every window has
+    // ONE bucket, so key = 2t + 1 and val = i * table_nwin + |d| - 1.
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
     load_scalar(s, scalars, i);
-    const uint32_t nbw = (1u << (w - 1)) + 1u;
+    const uint32_t nbw = table_nwin ? 2u : (1u << (w - 1)) + 1u;
     for (int t = 0; t < ntiles; t++) {
         int bit0 = t * w;
         int wb = (t == ntiles - 1) ? (nbits - bit0) : w;  // bits in this tile
@@ -198,13 +201,13 @@ static __global__ void digits_booth_kernel(const uint32_t *__restrict__ scalars,
         size_t slot = i * ntiles + t;
         uint32_t key = KEY_SKIP, rank = 0;
         if (mag != 0 && (uint32_t)mag >= lo && (uint32_t)mag < hi) {
-            key = (uint32_t)t * nbw + (uint32_t)mag;
+            key = (uint32_t)t * nbw + (table_nwin ? 1u : (uint32_t)mag);
             rank = atomicAdd(&count[key], 1u);
         }
         const size_t at = digit_major ? (size_t)t * n + i : slot;
         keys[at] = key;
         if (ranks) ranks[at] = rank;
-        vals[at] = (uint32_t)i | (sign << 31);
+        vals[at] = (table_nwin ? (uint32_t)(i * table_nwin + (size_t)(mag > 0 ? mag - 1 : 0)) : (uint32_t)i) | (sign << 31);
     }
 }
 
@@ -1185,6 +1188,28 @@ static __global__ void __launch_bounds__(128) scalar_mul_kernel(const aff_t<F> *
         if ((s[bit >> 5] >> (bit & 31)) & 1) jac_add(acc, acc, b);
     }
     out[i] = acc;
+}
+// blst_p1s_mult_wbits_precompute (src/multi_scalar.c:81-158): table[i * nwin + k] = (k + 1) * P_i, affine, nwin = 2^(wbits-1).
+// One thread per entry (MSB-first double-and-add over the <= wbits bits of k + 1, then to_affine); affine points are
+// canonical, so the bytes equal the reference's table. An infinity input gives a row of infinities.
+template <class F>
+static __global__ void __launch_bounds__(128) wbits_precompute_kernel(const aff_t<F> *__restrict__ points, size_t npoints, int wbits,
+                                                                      aff_t<F> *__restrict__ table) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nwin = (size_t)1 << (wbits - 1);
+    if (t >= npoints * nwin) return;
+    const uint32_t mult = (uint32_t)(t % nwin) + 1u;
+    jac_t<F> b, acc;
+    jac_from_affine(b, points[t / nwin]);
+    jac_set_inf(acc);
+#pragma unroll 1
+    for (int bit = 31 - __clz((int)mult); bit >= 0; bit--) {
+        jac_double(acc, acc);
+        if ((mult >> bit) & 1u) jac_add(acc, acc, b);
+    }
+    aff_t<F> a;
+    jac_to_affine(a, acc);
+    table[t] = a;
 }
 // init_fix_point_list (main_p1.cpp:52-66) in parallel: thread t starts from seeds[t] = 2^(first + t*chunk) G and
 // emits the next `chunk` doublings, each normalised (3 at a time) to canonical affine.

@@ -610,6 +610,61 @@ def test_blst_points_add_shim_vs_compiled_reference(M, golden, group, mode, monk
         assert (got == ra).all()
 
 
+@pytest.mark.parametrize("group", [1, 2])
+@pytest.mark.parametrize("wbits", [4, 7])
+def test_blst_mult_wbits_shims_vs_compiled_reference(M, golden, group, wbits):
+    """msmb200_blst_pNs_mult_wbits_precompute / _mult_wbits (the library's fixed-window table MSM, SURVEY §8f-1;
+    src/multi_scalar.c:81-261): the table is byte-identical to the compiled reference's, and the MSM over it equals
+    the oracle's naive MSM and the reference's own blst_pNs_mult_wbits after to_affine. nbits = 255 and 64."""
+    gd = golden["pippenger_unstructured"][str(group)]
+    ab, jb = O.AFF_BYTES[group], O.JAC_BYTES[group]
+    pts = np.frombuffer(bytes.fromhex(gd["points"]), dtype=np.uint8).reshape(gd["n"], ab)
+    pts = np.ascontiguousarray(pts[pts.any(axis=1)])  # the reference's precompute is undefined for infinity inputs
+    n = pts.shape[0]
+    nwin = 1 << (wbits - 1)
+    L = M.lib()
+    size_fn = getattr(L, "msmb200_blst_p%ds_mult_wbits_precompute_sizeof" % group)
+    size_fn.restype = C.c_size_t
+    assert size_fn(C.c_size_t(wbits), C.c_size_t(n)) == n * nwin * ab
+    pp = (C.c_void_p * 2)(pts.ctypes.data, None)
+    table = np.zeros((n * nwin, ab), dtype=np.uint8)
+    getattr(L, "msmb200_blst_p%ds_mult_wbits_precompute" % group)(O.ptr(table), C.c_size_t(wbits), pp, C.c_size_t(n))
+    # row entry k of point i is (k + 1) * P_i: spot-check through the oracle's naive MSM
+    rng = np.random.default_rng(wbits)
+    for i, k in zip(rng.integers(0, n, size=6), rng.integers(0, nwin, size=6)):
+        sc1 = np.zeros((1, 4), dtype=np.uint64)
+        sc1[0, 0] = k + 1
+        e = np.zeros(ab, dtype=np.uint8)
+        O.oracle().oracle_naive_msm(group, O.ptr(np.ascontiguousarray(pts[i])), O.ptr(sc1), 1, O.ptr(e))
+        assert (table[i * nwin + k] == e).all(), (i, k)
+    assert (table[::nwin] == pts).all()
+    ref = O.blst_ref() if O.has_ref() else None
+    if ref is not None:
+        rt = np.zeros_like(table)
+        getattr(ref, "blst_p%ds_mult_wbits_precompute" % group)(O.ptr(rt), C.c_size_t(wbits), pp, C.c_size_t(n))
+        assert (rt == table).all()
+    sc = O.gen_scalars(77 + wbits, n)
+    sc[3] = 0
+    for nbits in (255, 64):
+        scb = np.ascontiguousarray(sc.view(np.uint8).reshape(n, 32)[:, : (nbits + 7) // 8])
+        sp = (C.c_void_p * 2)(scb.ctypes.data, None)
+        ret = np.zeros(jb, dtype=np.uint8)
+        getattr(L, "msmb200_blst_p%ds_mult_wbits" % group)(O.ptr(ret), O.ptr(table), C.c_size_t(wbits), C.c_size_t(n), sp, C.c_size_t(nbits), None)
+        got = M.test_point_op(group, 5, ret)
+        sct = sc.copy()
+        if nbits == 64:
+            sct[:, 1:] = 0
+        exp = np.zeros(ab, dtype=np.uint8)
+        O.oracle().oracle_naive_msm(group, O.ptr(pts), O.ptr(sct), n, O.ptr(exp))
+        assert (got == exp).all(), nbits
+        if ref is not None:
+            rj = np.zeros(jb, dtype=np.uint8)
+            getattr(ref, "blst_p%ds_mult_wbits" % group)(O.ptr(rj), O.ptr(table), C.c_size_t(wbits), C.c_size_t(n), sp, C.c_size_t(nbits), None)
+            ra = np.zeros(ab, dtype=np.uint8)
+            getattr(ref, "blst_p%d_to_affine" % group)(O.ptr(ra), O.ptr(rj))
+            assert (got == ra).all(), nbits
+
+
 # ---------------------------------------------------------------- bucket-range sharding (tables replicated)
 @pytest.mark.parametrize("group", [1, 2])
 def test_bucket_range_shards_sum_to_full_result(M, group):
