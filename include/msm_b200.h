@@ -63,6 +63,13 @@ long msmb200_host_bucket_set(int e, int a, int *out, long cap);
 int msmb200_host_digit_table(int e, int a, int *out_triples);
 /* pippenger_window_size (src/multi_scalar.c:268-275) */
 size_t msmb200_pippenger_window_size(size_t npoints);
+/* Host-only check of the digit-splitting bucket-reduction plan (the static lists list_sum_kernel / list_sum_coop_kernel
+ * walk, replacing integrate_buckets_accumulation_d_CHES, src/multi_scalar.c:301-321): evaluates the plan on 64-bit
+ * integers x[0..nbw) instead of points; *out must equal sum_l value(l) * x[l] mod 2^64. values: ascending bucket values
+ * (values[0] = 0) or NULL for dense (value == index). out_info (8 words, may be NULL): c_lo, bit positions, stage-1 slice
+ * length, stage-1 slices, digit lists, groups per digit list, stage-2a lists, groups per 2a list. */
+int msmb200_host_reduce_plan_eval(const int *values, size_t nbw, int resident_stage1, int resident_coop, int groups_per_warp,
+                                  const uint64_t *x, uint64_t *out, uint32_t *out_info);
 
 /* ---- context ------------------------------------------------------------------------------------ */
 

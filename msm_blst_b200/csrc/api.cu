@@ -98,11 +98,12 @@ static void slice_lists(const std::vector<uint32_t> &start, uint32_t slice, std:
         start_g.push_back((uint32_t)idx_g.size());
     }
 }
-int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, uint32_t nwindows) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const int subparts = 4 * sms;
-    const int res1 = c->ops->resident_blocks(0), resq = c->ops->resident_blocks(1), gpw = c->ops->resident_blocks(2);
+// Host form of the plan: the four list stages as (start, idx) arrays plus the team sizes. Pure host code (no CUDA), so
+// the CPU test-suite can evaluate it on integers (msmb200_host_reduce_plan_eval).
+struct HostListPlan { std::vector<uint32_t> start, idx; uint32_t tl = 1; };
+struct HostReducePlan { HostListPlan s1, s1b, s2a, s2b; uint32_t c_lo = 0, nbits_w = 0, slice1 = 0; };
+static void compute_reduce_plan(HostReducePlan &H, const int *values, size_t nbw, uint32_t nwindows, int subparts, int res1, int resq, int gpw,
+                                bool s1_coop) {
     const uint32_t maxv = nbw > 1 ? (values ? (uint32_t)values[nbw - 1] : (uint32_t)(nbw - 1)) : 1u;
     uint32_t V = 0;
     while (V < 32 && (maxv >> V) != 0) V++;
@@ -112,14 +113,15 @@ int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, u
     while ((nhi >> chi) != 0) chi++;
     // digit lists: list (lo digit d) = d - 1, list (hi digit d) = nlo + d - 1; members are local bucket indices
     const uint32_t nl1 = nlo + nhi;
-    std::vector<uint32_t> start(nl1 + 1, 0), idx;
+    std::vector<uint32_t> start(nl1 + 1, 0);
+    std::vector<uint32_t> &idx = H.s1.idx;
     for (size_t l = 1; l < nbw; l++) {
         uint32_t v = values ? (uint32_t)values[l] : (uint32_t)l;
         if (v & nlo) start[(v & nlo) - 1 + 1]++;
         if (v >> c_lo) start[nlo + (v >> c_lo) - 1 + 1]++;
     }
     for (uint32_t i = 0; i < nl1; i++) start[i + 1] += start[i];
-    idx.resize(start[nl1]);
+    idx.assign(start[nl1], 0);
     {
         std::vector<uint32_t> cur(start.begin(), start.end() - 1);
         for (size_t l = 1; l < nbw; l++) {
@@ -131,8 +133,7 @@ int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, u
     // stage 1: one LANE per slice of a digit list (perfect balance whatever the list lengths), slices sized so that the
     // whole stage is exactly ONE wave of resident blocks (a partially filled second wave would cost a full chain again);
     // stage 1b: the slices of each digit list, summed by lane groups
-    plan.s1_coop = getenv("MSMB200_S1COOP") && atoi(getenv("MSMB200_S1COOP")) != 0;
-    const double lanes1 = (plan.s1_coop ? (double)gpw * resq : 32.0 * res1) * subparts;
+    const double lanes1 = (s1_coop ? (double)gpw * resq : 32.0 * res1) * subparts;
     uint32_t slice1 = (uint32_t)std::max(2.0, std::ceil((double)idx.size() * nwindows / lanes1));
     auto count_slices = [&](uint32_t sl) {
         size_t n = 0;
@@ -141,33 +142,43 @@ int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, u
     };
     while (slice1 < (1u << 20) && (double)count_slices(slice1) > lanes1) slice1 += std::max(1u, slice1 / 16);  // ragged last slices
     if (const char *e = getenv("MSMB200_SLICE1")) slice1 = (uint32_t)std::max(1, atoi(e));
-    std::vector<uint32_t> start_s, start_g, idx_g;
-    slice_lists(start, slice1, start_s, start_g, idx_g);
-    int rc = upload_list_plan(c, plan.s1, start_s, idx);
-    if (rc) return rc;
-    plan.s1.tl = 1;
-    rc = upload_list_plan(c, plan.s1b, start_g, idx_g);
-    if (rc) return rc;
-    plan.s1b.tl = pick_quads((size_t)nl1 * nwindows, nl1 ? (double)idx_g.size() / nl1 : 1.0, subparts, resq, gpw);
+    H.slice1 = slice1;
+    slice_lists(start, slice1, H.s1.start, H.s1b.start, H.s1b.idx);
+    H.s1.tl = 1;
+    H.s1b.tl = pick_quads((size_t)nl1 * nwindows, nl1 ? (double)H.s1b.idx.size() / nl1 : 1.0, subparts, resq, gpw);
     // stage 2a: bit k of the lo (k < c_lo) or hi (k >= c_lo) digit value, cut into slices of SLICE members; 2b: bit lists
     const uint32_t SLICE = 32, nbits = c_lo + chi;
-    std::vector<uint32_t> start_a(1, 0), idx_a, start_as, start_b, idx_b;
+    std::vector<uint32_t> start_a(1, 0);
     for (uint32_t k = 0; k < nbits; k++) {
         const bool hi = k >= c_lo;
         const uint32_t bit = hi ? k - c_lo : k, vmax = hi ? nhi : nlo, base = hi ? nlo : 0;
         for (uint32_t v = 1; v <= vmax; v++)
-            if ((v >> bit) & 1) idx_a.push_back(base + v - 1);
-        start_a.push_back((uint32_t)idx_a.size());
+            if ((v >> bit) & 1) H.s2a.idx.push_back(base + v - 1);
+        start_a.push_back((uint32_t)H.s2a.idx.size());
     }
-    slice_lists(start_a, SLICE, start_as, start_b, idx_b);
-    rc = upload_list_plan(c, plan.s2a, start_as, idx_a);
-    if (rc) return rc;
-    plan.s2a.tl = pick_quads((size_t)plan.s2a.nlists * nwindows, plan.s2a.nlists ? (double)idx_a.size() / plan.s2a.nlists : 1.0, subparts, resq, gpw);
-    rc = upload_list_plan(c, plan.s2b, start_b, idx_b);
-    if (rc) return rc;
-    plan.s2b.tl = pick_quads((size_t)nbits * nwindows, nbits ? (double)idx_b.size() / nbits : 1.0, subparts, resq, gpw);
-    plan.c_lo = c_lo;
-    plan.nbits_w = nbits;
+    slice_lists(start_a, SLICE, H.s2a.start, H.s2b.start, H.s2b.idx);
+    const size_t nl2a = H.s2a.start.size() - 1;
+    H.s2a.tl = pick_quads(nl2a * nwindows, nl2a ? (double)H.s2a.idx.size() / nl2a : 1.0, subparts, resq, gpw);
+    H.s2b.tl = pick_quads((size_t)nbits * nwindows, nbits ? (double)H.s2b.idx.size() / nbits : 1.0, subparts, resq, gpw);
+    H.c_lo = c_lo;
+    H.nbits_w = nbits;
+}
+int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, uint32_t nwindows) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    plan.s1_coop = getenv("MSMB200_S1COOP") && atoi(getenv("MSMB200_S1COOP")) != 0;
+    HostReducePlan H;
+    compute_reduce_plan(H, values, nbw, nwindows, 4 * sms, c->ops->resident_blocks(0), c->ops->resident_blocks(1), c->ops->resident_blocks(2),
+                        plan.s1_coop);
+    const HostListPlan *hs[4] = {&H.s1, &H.s1b, &H.s2a, &H.s2b};
+    ListPlan *ds[4] = {&plan.s1, &plan.s1b, &plan.s2a, &plan.s2b};
+    for (int k = 0; k < 4; k++) {
+        int rc = upload_list_plan(c, *ds[k], hs[k]->start, hs[k]->idx);
+        if (rc) return rc;
+        ds[k]->tl = hs[k]->tl;
+    }
+    plan.c_lo = H.c_lo;
+    plan.nbits_w = H.nbits_w;
     plan.key_nbw = nbw;
     plan.valid = true;
     return MSMB200_OK;
@@ -178,18 +189,11 @@ static int ctx_init_common(Ctx *c, int group, int device) {
     c->device = device;
     c->ops = group == 1 ? group_ops_g1() : group_ops_g2();
     MSM_CUDA(c, cudaSetDevice(device));
-    {
-        // The table gathers read 96 / 192-byte entries at random: ask L2 to fetch 32-byte sectors from DRAM instead of
-        // 128-byte lines (ncu: 5.2 GB read per n=2^21 launch for 2.4 GB of entries with the default granularity).
-        // A hint, device wide; MSMB200_L2_FETCH=0 leaves the default untouched.
-        const char *e = getenv("MSMB200_L2_FETCH");
-        int g = e ? atoi(e) : 32;
-        if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
-        cudaGetLastError();  // not supported -> ignore
-    }
     MSM_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
     for (auto &e : c->ev) MSM_CUDA(c, cudaEventCreate(&e));
+    MSM_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev_chunk) MSM_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     MSM_CUDA(c, cudaMallocHost(&c->h_result, 512));
     return MSMB200_OK;
 }
@@ -208,6 +212,8 @@ static void ctx_free(Ctx *c) {
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_result) cudaFreeHost(c->h_result);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->ev_chunk) if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -263,6 +269,33 @@ int msmb200_host_digit_table(int e, int a, int *out_triples) {
     return MSMB200_OK;
 }
 size_t msmb200_pippenger_window_size(size_t npoints) { return pippenger_window_size(npoints); }
+
+// Evaluates the digit-splitting reduction plan on 64-bit integers instead of points (host only): x[l] plays the bucket
+// sum of local bucket l, additions are mod 2^64, doubling is a shift; the result must equal sum_l value(l) * x[l].
+// Exercises exactly the arrays the GPU kernels walk (stage 1 slices, 1b, 2a, 2b, Horner over bit positions).
+int msmb200_host_reduce_plan_eval(const int *values, size_t nbw, int resident_stage1, int resident_coop, int groups_per_warp, const uint64_t *x,
+                                  uint64_t *out, uint32_t *out_info) {
+    if (nbw < 2 || !x || !out || resident_stage1 < 1 || resident_coop < 1 || groups_per_warp < 1) return MSMB200_EINVAL;
+    HostReducePlan H;
+    compute_reduce_plan(H, values, nbw, 1, 4 * 148, resident_stage1, resident_coop, groups_per_warp, false);
+    auto run = [](const HostListPlan &lp, const std::vector<uint64_t> &in) {
+        std::vector<uint64_t> o(lp.start.size() - 1, 0);
+        for (size_t i = 0; i + 1 < lp.start.size(); i++)
+            for (uint32_t e = lp.start[i]; e < lp.start[i + 1]; e++) o[i] += in[lp.idx[e]];
+        return o;
+    };
+    std::vector<uint64_t> in(x, x + nbw);
+    in[0] = 0;
+    std::vector<uint64_t> a = run(H.s1, in), b = run(H.s1b, a), c2 = run(H.s2a, b), d = run(H.s2b, c2);
+    uint64_t acc = 0;
+    for (int k = (int)H.nbits_w - 1; k >= 0; k--) acc = (acc << 1) + d[k];
+    *out = acc;
+    if (out_info) {
+        out_info[0] = H.c_lo; out_info[1] = H.nbits_w; out_info[2] = H.slice1; out_info[3] = (uint32_t)(H.s1.start.size() - 1);
+        out_info[4] = (uint32_t)(H.s1b.start.size() - 1); out_info[5] = H.s1b.tl; out_info[6] = (uint32_t)(H.s2a.start.size() - 1); out_info[7] = H.s2a.tl;
+    }
+    return MSMB200_OK;
+}
 
 const char *msmb200_last_error(const msmb200_ctx *ctx) { return ctx ? ctx->c.err.c_str() : g_create_err.c_str(); }
 
@@ -415,6 +448,15 @@ int msmb200_msm(msmb200_ctx *ctx, int method, const void *scalars_host, void *ou
     Ctx *c = C(ctx);
     MSM_CUDA(c, cudaSetDevice(c->device));
     if (ensure(c, c->scalars, c->n * 32)) return MSMB200_ECUDA;
+    if (method == MSMB200_CHES && !getenv("MSMB200_NO_OVERLAP")) {
+        // chunked upload overlapped with the digit decomposition (msm_impl)
+        c->h_scalars_pending = scalars_host;
+        int rc = c->ops->msm(c, method, c->scalars.p, nullptr, true);
+        c->h_scalars_pending = nullptr;
+        if (rc) return rc;
+        memcpy(out_affine_host, c->h_result, c->ops->aff_bytes);
+        return MSMB200_OK;
+    }
     MSM_CUDA(c, cudaMemcpyAsync(c->scalars.p, scalars_host, c->n * 32, cudaMemcpyHostToDevice, c->stream));
     return msmb200_msm_device(ctx, method, c->scalars.p, out_affine_host);
 }

@@ -75,6 +75,10 @@ struct Ctx {
     int shard_rank = 0, shard_world = 1;  // bucket-range sharding: this context owns 1/world of the reduction chunks
     int accum_mode = 0;  // 0 = default, 1 = XYZZ work items, 2 = batch-affine rounds
     void *h_result = nullptr;  // pinned staging for the result
+    // host-to-host CHES calls: chunked upload on a second stream overlapped with the digit kernel (msmb200_msm)
+    const void *h_scalars_pending = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_chunk[8] = {};
 
     // timing
     cudaEvent_t ev[8] = {};

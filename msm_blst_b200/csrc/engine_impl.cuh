@@ -352,9 +352,21 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
         shard_slice(c, c->red_nchunks, &clo, &ccnt);
         const uint32_t blo = (uint32_t)c->h_chunk_first[clo], bhi = (uint32_t)c->h_chunk_first[clo + ccnt];
         if (method == MSMB200_CHES) {
-            digits_ches_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab,
-                                                                   (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p, (uint32_t *)c->ranks.p, 1, blo, bhi);
-            c->launches += 1;
+            // host-to-host call: upload the scalars in chunks on the copy stream and decompose each chunk as it lands
+            const int K = c->h_scalars_pending ? 8 : 1;
+            for (int k = 0; k < K; k++) {
+                const size_t i0 = n * (size_t)k / K, i1 = n * (size_t)(k + 1) / K;
+                if (i1 == i0) continue;
+                if (c->h_scalars_pending) {
+                    MSM_CUDA(c, cudaMemcpyAsync((char *)const_cast<void *>(d_scalars) + i0 * 32, (const char *)c->h_scalars_pending + i0 * 32, (i1 - i0) * 32,
+                                                cudaMemcpyHostToDevice, c->copy_stream));
+                    MSM_CUDA(c, cudaEventRecord(c->ev_chunk[k], c->copy_stream));
+                    MSM_CUDA(c, cudaStreamWaitEvent(st, c->ev_chunk[k], 0));
+                }
+                digits_ches_kernel<<<blocks_for(i1 - i0, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab, (uint32_t *)c->keys.p,
+                                                                           (uint32_t *)c->vals.p, (uint32_t *)c->count.p, (uint32_t *)c->ranks.p, 1, blo, bhi, i0, i1 - i0);
+                c->launches += 1;
+            }
         } else {
             if (ensure(c, c->flat, (m + 2) * 4) || ensure(c, c->signs, m) || ensure(c, c->pidx, m * 4)) return MSMB200_ECUDA;
             digits_std_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, (int *)c->flat.p);
@@ -500,7 +512,7 @@ template <class F> static int digits_impl(Ctx *c, int kind, const void *d_scalar
     if (ensure(c, c->count, nb * 4)) return MSMB200_ECUDA;
     MSM_CUDA(c, cudaMemsetAsync(c->count.p, 0, nb * 4, st));
     if (kind == 0)
-        digits_ches_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab, d_keys, d_vals, (uint32_t *)c->count.p, nullptr, 0, 0u, 0xffffffffu);
+        digits_ches_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h, cfg.e, c->d_dtab, d_keys, d_vals, (uint32_t *)c->count.p, nullptr, 0, 0u, 0xffffffffu, 0, n);
     else if (kind == 1)
         digits_bgmw_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h_bgmw, cfg.e_bgmw, bgmw_trick(cfg) ? 1 : 0, d_keys, d_vals, (uint32_t *)c->count.p, nullptr, 0, 0u, 0xffffffffu);
     else

@@ -47,12 +47,14 @@ __device__ __forceinline__ void load_scalar(uint32_t s[8], const uint32_t *scala
 static __global__ void digits_ches_kernel(const uint32_t *__restrict__ scalars, size_t n, int h, int e,
                                    const uint32_t *__restrict__ dtab, uint32_t *__restrict__ keys,
                                    uint32_t *__restrict__ vals, uint32_t *__restrict__ count, uint32_t *__restrict__ ranks, int digit_major,
-                                   uint32_t lo, uint32_t hi) {
+                                   uint32_t lo, uint32_t hi, size_t i0, size_t cnt) {
+    // scalars [i0, i0 + cnt) of the n: the host-to-host entry point launches one slice per uploaded chunk so that the
+    // digit decomposition overlaps the PCIe copy of the next chunk
     // ranks[at] = position of the entry inside its bucket (the value returned by the histogram atomic), so the
     // scatter pass needs no second round of atomics; may be null (parity-test hook).
     // [lo, hi): bucket-index range owned by this context (bucket-range sharding over GPUs); others are skipped
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i0 + cnt || i >= n) return;
     uint32_t s[8];
     load_scalar(s, scalars, i);
     uint32_t carry = 0;
