@@ -204,7 +204,7 @@ static void ctx_free(Ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->scalars, &c->keys, &c->vals, &c->ranks, &c->sorted, &c->count, &c->packed, &c->scanned, &c->tile_sums, &c->seg_start,
                       &c->item_start, &c->cursor, &c->item_begin, &c->item_cnt, &c->order, &c->len_hist, &c->len_start, &c->len_cursor,
-                      &c->partial, &c->chunk_a, &c->chunk_b, &c->result, &c->flat, &c->signs, &c->pidx, &c->heavy, &c->light, &c->bucket_of0, &c->bo_a, &c->bo_b,
+                      &c->partial, &c->chunk_a, &c->chunk_b, &c->result, &c->flat, &c->signs, &c->pidx, &c->heavy, &c->light, &c->medium, &c->bucket_of0, &c->bo_a, &c->bo_b,
                       &c->pts_a, &c->pts_b, &c->base_a, &c->base_b, &c->tile_sums2, &c->maxcount, &c->red_a, &c->red_b, &c->red_c, &c->red_d};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     free_reduce_plan(c->plan_ches); free_reduce_plan(c->plan_bgmw); free_reduce_plan(c->plan_pip);

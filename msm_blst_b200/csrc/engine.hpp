@@ -66,7 +66,7 @@ struct Ctx {
     // workspace (grow-only)
     DevBuf scalars, keys, vals, ranks, sorted, count, packed, scanned, tile_sums, seg_start, item_start, cursor,
         item_begin, item_cnt, order, len_hist, len_start, len_cursor, partial, chunk_a, chunk_b, result,
-        flat, signs, pidx, heavy, light, bucket_of0, bo_a, bo_b, pts_a, pts_b, base_a, base_b, tile_sums2, maxcount;
+        flat, signs, pidx, heavy, light, medium, bucket_of0, bo_a, bo_b, pts_a, pts_b, base_a, base_b, tile_sums2, maxcount;
     ReducePlan plan_ches, plan_bgmw, plan_pip;  // digit-splitting reduction plans (sparse CHES set / dense windows)
     uint32_t plan_bgmw_windows = 0, plan_pip_windows = 0;
     DevBuf red_a, red_b, red_c, red_d;          // outputs of the list-sum stages

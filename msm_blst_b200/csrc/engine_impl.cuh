@@ -75,11 +75,16 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     // Small problems use short work items (>= ~3 warps per SM sub-partition of equal-length chains); the partials of a
     // split bucket are folded by one quad (combine_light_kernel) or, beyond heavy_items partials, by one block.
     const bool split_reduce = use_split_reduce(c, L);
-    uint32_t heavy_items = 8;  // buckets with 2..8 work items: one quad each (combine_light_kernel); more: one block each
+    // buckets with 2..8 work items: one lane group each; 9..64: one warp of lane groups each (combine_light_kernel);
+    // more: one block each (combine_heavy_kernel)
+    const uint32_t heavy_items = 8, medium_items = 64;
     if (split_reduce) {
         const size_t want_items = (size_t)3 * 592 * 32;
         if (nb < want_items) item_len = (uint32_t)std::max<size_t>(8, std::min<size_t>(item_len, m / want_items));
     }
+    // The longest chain is the critical path: with ~3 warps sharing a sub-partition it advances at a third of the pipe
+    // rate, so keep item_len * 3 below half of the ideal duration of the whole phase (m / (592 * 32) additions per lane).
+    item_len = (uint32_t)std::max<size_t>(8, std::min<size_t>(item_len, m / ((size_t)592 * 32 * 6)));
     if (const char *e = getenv("MSMB200_ITEM_LEN")) item_len = (uint32_t)std::max(1, atoi(e));
     const size_t max_items = std::min(nb, m) + m / item_len + 1;
     const size_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
@@ -116,11 +121,13 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     if (!batch_affine) {
         MSM_CUDA(c, cudaMemsetAsync(c->len_hist.p, 0, (item_len + 1) * 4, st));
         MSM_CUDA(c, cudaMemsetAsync(c->heavy.p, 0, 4, st));
-        if (ensure(c, c->light, (std::min(nb, m / item_len + 1) + 2) * 4)) return MSMB200_ECUDA;
+        if (ensure(c, c->light, (std::min(nb, m / item_len + 1) + 2) * 4) || ensure(c, c->medium, (std::min(nb, m / item_len + 1) + 2) * 4)) return MSMB200_ECUDA;
         MSM_CUDA(c, cudaMemsetAsync(c->light.p, 0, 4, st));
+        MSM_CUDA(c, cudaMemsetAsync(c->medium.p, 0, 4, st));
         itemize_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, (const uint32_t *)c->seg_start.p, (const uint32_t *)c->item_start.p,
                                                             nb, item_len, (uint32_t *)c->item_begin.p, (uint32_t *)c->item_cnt.p,
-                                                            (uint32_t *)c->len_hist.p, (uint32_t *)c->heavy.p, heavy_items, (uint32_t *)c->light.p);
+                                                            (uint32_t *)c->len_hist.p, (uint32_t *)c->heavy.p, heavy_items, (uint32_t *)c->light.p, medium_items,
+                                                            (uint32_t *)c->medium.p);
         len_scan_kernel<<<1, 32, 0, st>>>((const uint32_t *)c->len_hist.p, (uint32_t *)c->len_start.p, (uint32_t *)c->len_cursor.p, item_len);
         order_items_kernel<<<blocks_for(max_items, 256), 256, 0, st>>>((const uint32_t *)c->item_cnt.p, totals,
                                                                        (const uint32_t *)c->len_start.p, (uint32_t *)c->len_cursor.p,
@@ -136,12 +143,17 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
             combine_heavy_kernel<FC><<<max_heavy, 128, 0, st>>>(count, (const uint32_t *)c->item_start.p, (const uint32_t *)c->heavy.p, item_len,
                                                                (xyzz_t<FC> *)c->partial.p);
         }
-        if (heavy_items > 1) {
-            // at most min(nb, m / item_len) buckets have more than one work item; grid sized for that bound, idle warps exit
-            const size_t max_light = std::min(nb, m / item_len + 1);
-            combine_light_kernel<FC><<<blocks_for(max_light * coop_group_lanes<typename coop_of<FC>::type>(), 128), 128, 0, st>>>(count, (const uint32_t *)c->item_start.p,
-                                                                                    (const uint32_t *)c->light.p, item_len, (xyzz_t<FC> *)c->partial.p);
-            c->launches += 1;
+        {
+            // at most min(nb, m / item_len) buckets have more than one work item (grids sized for that bound, idle warps
+            // exit); medium buckets have more than heavy_items work items each
+            using CT = typename coop_of<FC>::type;
+            constexpr uint32_t GL = coop_group_lanes<CT>(), NG = 32 / GL;
+            const size_t max_light = std::min(nb, m / item_len + 1), max_medium = std::min(nb, m / ((size_t)item_len * heavy_items) + 1);
+            combine_light_kernel<FC><<<blocks_for(max_medium * 32, 128), 128, 0, st>>>(count, (const uint32_t *)c->item_start.p, (const uint32_t *)c->medium.p,
+                                                                                    item_len, NG, (xyzz_t<FC> *)c->partial.p);
+            combine_light_kernel<FC><<<blocks_for(max_light * GL, 128), 128, 0, st>>>(count, (const uint32_t *)c->item_start.p, (const uint32_t *)c->light.p,
+                                                                                   item_len, 1, (xyzz_t<FC> *)c->partial.p);
+            c->launches += 2;
         }
         c->launches += 2;
         bucket_points = c->partial.p;

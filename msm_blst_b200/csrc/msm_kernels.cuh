@@ -312,14 +312,16 @@ static __global__ void itemize_kernel(const uint32_t *__restrict__ count, const 
                                const uint32_t *__restrict__ item_start, size_t nb, uint32_t item_len,
                                uint32_t *__restrict__ item_begin, uint32_t *__restrict__ item_cnt,
                                uint32_t *__restrict__ len_hist, uint32_t *__restrict__ heavy /* [0] = count, then bucket ids */,
-                               uint32_t heavy_items, uint32_t *__restrict__ light /* [0] = count, then bucket ids; may be null */) {
-    // buckets with more than heavy_items work items are combined by a block each (combine_heavy_kernel), buckets with
-    // 2..heavy_items work items by a quad each (combine_light_kernel)
+                               uint32_t heavy_items, uint32_t *__restrict__ light /* [0] = count, then bucket ids */,
+                               uint32_t medium_items, uint32_t *__restrict__ medium /* same */) {
+    // buckets split into 2..heavy_items work items are folded by ONE lane group each, heavy_items+1..medium_items by one
+    // WARP of lane groups each (combine_light_kernel), more by a block each (combine_heavy_kernel)
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     uint32_t c = count[b];
     if (c == 0) return;
-    if (c > item_len * heavy_items) heavy[1 + atomicAdd(&heavy[0], 1u)] = (uint32_t)b;
+    if ((uint64_t)c > (uint64_t)item_len * medium_items) heavy[1 + atomicAdd(&heavy[0], 1u)] = (uint32_t)b;
+    else if (c > item_len * heavy_items) medium[1 + atomicAdd(&medium[0], 1u)] = (uint32_t)b;
     else if (c > item_len) light[1 + atomicAdd(&light[0], 1u)] = (uint32_t)b;
     uint32_t s = seg_start[b], it = item_start[b];
     for (uint32_t off = 0; off < c; off += item_len, it++) {
@@ -914,33 +916,44 @@ static __global__ void __launch_bounds__(128) list_sum_coop_kernel(const xyzz_t<
     if (live && sq == 0) dq_store(out + gl, acc);
 }
 
-// Buckets split into 2..heavy_items work items: one group per bucket folds the partials into the first one.
+// Buckets split into several work items: tq lane groups per bucket (1 for the light list, a whole warp for the medium
+// list) stride over the partials and fold them into the first one.
 template <class F>
 static __global__ void __launch_bounds__(128) combine_light_kernel(const uint32_t *__restrict__ count, const uint32_t *__restrict__ item_start,
-                                                                   const uint32_t *__restrict__ light, uint32_t item_len, xyzz_t<F> *partial) {
+                                                                   const uint32_t *__restrict__ list, uint32_t item_len, uint32_t tq,
+                                                                   xyzz_t<F> *partial) {
     using C = typename coop_of<F>::type;
     constexpr uint32_t GL = coop_group_lanes<C>();
-    const uint32_t nlight = light[0];
-    const uint32_t gq = (blockIdx.x * blockDim.x + threadIdx.x) / GL;
-    if (__all_sync(0xffffffffu, gq >= nlight)) return;
+    const uint32_t nlist = list[0];
+    const uint32_t gq = (blockIdx.x * blockDim.x + threadIdx.x) / GL, gb = gq / tq, sq = gq % tq;
+    if (__all_sync(0xffffffffu, gb >= nlist)) return;
     uint32_t first = 0, nitems = 0;
-    if (gq < nlight) {
-        const uint32_t b = light[1 + gq];
+    if (gb < nlist) {
+        const uint32_t b = list[1 + gb];
         first = item_start[b];
         nitems = (count[b] + item_len - 1) / item_len;
     }
-    const uint32_t maxitems = __reduce_max_sync(0xffffffffu, nitems);
+    const uint32_t my_iters = nitems > sq ? (nitems - sq + tq - 1) / tq : 0u;
+    const uint32_t iters = __reduce_max_sync(0xffffffffu, my_iters);
     C acc;
     f_set_zero(acc);
 #pragma unroll 1
-    for (uint32_t k = 0; k < maxitems; k++) {
+    for (uint32_t it = 0; it < iters; it++) {
+        const uint32_t k = sq + it * tq;
         C s;
         f_set_zero(s);
         if (k < nitems) dq_load(s, partial + first + k);
-        if (k == 0) acc = s;
+        if (it == 0) acc = s;
         else dq_add(acc, s);
     }
-    if (nitems) dq_store(partial + first, acc);
+#pragma unroll 1
+    for (uint32_t o = tq >> 1; o > 0; o >>= 1) {
+        C other;
+        dq_shfl_down(other, acc, (int)(GL * o));
+        if (sq + o >= tq) f_set_zero(other);
+        dq_add(acc, other);
+    }
+    if (nitems && sq == 0) dq_store(partial + first, acc);
 }
 
 template <class C> __device__ __forceinline__ void dq_shift(C &acc, uint32_t my_doublings) {
