@@ -109,6 +109,14 @@ int msmb200_table_build_ches(msmb200_ctx *ctx);
 int msmb200_table_build_bgmw95(msmb200_ctx *ctx);
 /* Copy `count` affine entries starting at `first` back to host. which: 0 = fixed points, 1 = T3nh, 2 = TBGMW. */
 int msmb200_download(msmb200_ctx *ctx, int which, size_t first, size_t count, void *out_host);
+/* Table persistence (the reference rebuilds its tables on every run, main_p1.cpp:615-617). which: 0 fixed
+ * points, 1 CHES 3nh table, 2 BGMW95 table. format 0: the in-memory blst_pN_affine layout (Montgomery limbs); format 1:
+ * blst_pN_affine_serialize of every entry (src/e1.c:153-162, src/e2.c:194-203: 96 / 192 bytes big-endian, infinity
+ * 0x40), readable by blst_pN_deserialize. A 72-byte header records group, configuration, npoints and entry count;
+ * load checks it against the context and validates EVERY entry on the device like blst_pN_deserialize does
+ * (flags, coordinates < p, y^2 = x^3 + B) before marking the array usable. */
+int msmb200_table_save(msmb200_ctx *ctx, int which, const char *path, int format);
+int msmb200_table_load(msmb200_ctx *ctx, int which, const char *path);
 /* bucket set (BUCKET_SET, ascending, [0] = 0); returns |B| (or negative error); fills out if cap >= |B| */
 long msmb200_bucket_set(msmb200_ctx *ctx, int *out, long cap);
 

@@ -69,6 +69,8 @@ def lib():
         L.msmb200_set_points.argtypes = [vp, vp]
         L.msmb200_set_accumulator.argtypes = [vp, ci]
         L.msmb200_set_reducer.argtypes = [vp, ci]
+        L.msmb200_table_save.argtypes = [vp, ci, C.c_char_p, ci]
+        L.msmb200_table_load.argtypes = [vp, ci, C.c_char_p]
         L.msmb200_set_bucket_shard.argtypes = [vp, ci, ci]
         L.msmb200_generate_fix_points.argtypes = [vp, sz]
         L.msmb200_table_build_ches.argtypes = [vp]
@@ -216,6 +218,14 @@ class MsmContext:
     def set_accumulator(self, mode):
         """0 default, 1 XYZZ work items, 2 batch-affine rounds (identical results)."""
         self._ck(lib().msmb200_set_accumulator(self._h, int(mode)))
+
+    def table_save(self, which, path, fmt=1):
+        """which: 0 fixed points, 1 CHES 3nh table, 2 BGMW95 table; fmt 0 raw Montgomery layout, 1 blst_pN_affine_serialize."""
+        self._ck(lib().msmb200_table_save(self._h, int(which), str(path).encode(), int(fmt)))
+
+    def table_load(self, which, path):
+        """Load (and validate entry by entry on the device) what table_save wrote; raises on a mismatching header or an invalid entry."""
+        self._ck(lib().msmb200_table_load(self._h, int(which), str(path).encode()))
 
     def set_reducer(self, mode):
         """0 default, 1 chunked running sums (reference's tmp_d[] form), 2 digit splitting (identical results)."""

@@ -427,6 +427,97 @@ int msmb200_download(msmb200_ctx *ctx, int which, size_t first, size_t count, vo
     MSM_CUDA(c, cudaStreamSynchronize(c->stream));
     return MSMB200_OK;
 }
+// ---- table persistence ----
+struct TableFileHeader {
+    char magic[8];       // "MSMB200T"
+    uint32_t version, group, format, which;
+    int32_t cfg[8];      // n_exp, e, h, a, d, bsize, e_bgmw, h_bgmw
+    uint64_t npoints, entries;
+};
+static int table_slot(Ctx *c, int which, void ***slot, size_t *entries, bool **have) {
+    if (which == 0) { *slot = &c->d_points; *entries = c->n; *have = &c->have_points; }
+    else if (which == 1) { *slot = &c->d_table_ches; *entries = c->n * (size_t)c->cfg.h * 3; *have = &c->have_ches; }
+    else if (which == 2) { *slot = &c->d_table_bgmw; *entries = c->n * (size_t)c->cfg.h_bgmw; *have = &c->have_bgmw; }
+    else return ctx_fail(c, MSMB200_EINVAL, "which must be 0 (points), 1 (CHES table) or 2 (BGMW95 table)");
+    return MSMB200_OK;
+}
+int msmb200_table_save(msmb200_ctx *ctx, int which, const char *path, int format) {
+    if (!ctx || !path || (format != 0 && format != 1)) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    void **slot; size_t entries; bool *have;
+    int rc = table_slot(c, which, &slot, &entries, &have);
+    if (rc) return rc;
+    if (!*have || !*slot) return ctx_fail(c, MSMB200_ESTATE, "requested array not built");
+    MSM_CUDA(c, cudaSetDevice(c->device));
+    FILE *f = fopen(path, "wb");
+    if (!f) return ctx_fail(c, MSMB200_EINVAL, std::string("cannot open ") + path);
+    TableFileHeader h{};
+    memcpy(h.magic, "MSMB200T", 8);
+    h.version = 1; h.group = (uint32_t)c->group; h.format = (uint32_t)format; h.which = (uint32_t)which;
+    const int32_t cf[8] = {c->cfg.n_exp, c->cfg.e, c->cfg.h, c->cfg.a, c->cfg.d, c->cfg.bsize, c->cfg.e_bgmw, c->cfg.h_bgmw};
+    memcpy(h.cfg, cf, sizeof(cf));
+    h.npoints = c->n; h.entries = entries;
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+    const size_t ab = c->ops->aff_bytes, chunk = (size_t)1 << 20;
+    std::vector<unsigned char> host(std::min(entries, chunk) * ab);
+    void *d_stage = nullptr;
+    if (format == 1 && cudaMalloc(&d_stage, std::min(entries, chunk) * ab) != cudaSuccess) { fclose(f); return ctx_fail(c, MSMB200_ECUDA, "cudaMalloc"); }
+    for (size_t off = 0; ok && off < entries; off += chunk) {
+        const size_t cnt = std::min(chunk, entries - off);
+        const void *src = (const char *)*slot + off * ab;
+        if (format == 1) {
+            if (c->ops->table_io(c, 0, 1, src, d_stage, cnt, nullptr)) { ok = false; break; }
+            src = d_stage;
+        }
+        ok = cudaMemcpyAsync(host.data(), src, cnt * ab, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess &&
+             fwrite(host.data(), ab, cnt, f) == cnt;
+    }
+    if (d_stage) cudaFree(d_stage);
+    ok = (fclose(f) == 0) && ok;
+    return ok ? MSMB200_OK : ctx_fail(c, MSMB200_ECUDA, std::string("writing ") + path + " failed");
+}
+int msmb200_table_load(msmb200_ctx *ctx, int which, const char *path) {
+    if (!ctx || !path) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    void **slot; size_t entries; bool *have;
+    int rc = table_slot(c, which, &slot, &entries, &have);
+    if (rc) return rc;
+    MSM_CUDA(c, cudaSetDevice(c->device));
+    FILE *f = fopen(path, "rb");
+    if (!f) return ctx_fail(c, MSMB200_EINVAL, std::string("cannot open ") + path);
+    TableFileHeader h{};
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "MSMB200T", 8) != 0 || h.version != 1 || h.format > 1) { fclose(f); return ctx_fail(c, MSMB200_EINVAL, "not a table file"); }
+    // the table depends on the group, the points (n) and the radix / length of its method; the points on group and n only
+    bool match = h.group == (uint32_t)c->group && h.which == (uint32_t)which && h.npoints == c->n && h.entries == entries;
+    if (which == 1) match = match && h.cfg[1] == c->cfg.e && h.cfg[2] == c->cfg.h;
+    if (which == 2) match = match && h.cfg[6] == c->cfg.e_bgmw && h.cfg[7] == c->cfg.h_bgmw;
+    if (!match) { fclose(f); return ctx_fail(c, MSMB200_EINVAL, "table file was written for another group / size / configuration"); }
+    const size_t ab = c->ops->aff_bytes, chunk = (size_t)1 << 20;
+    if (!*slot) MSM_CUDA(c, cudaMalloc(slot, entries * ab));
+    *have = false;
+    if (which == 0) c->have_ches = c->have_bgmw = false;
+    std::vector<unsigned char> host(std::min(entries, chunk) * ab);
+    void *d_stage = nullptr;
+    uint32_t *d_bad = nullptr, bad = 0;
+    if (cudaMalloc(&d_stage, std::min(entries, chunk) * ab) != cudaSuccess || cudaMalloc((void **)&d_bad, 4) != cudaSuccess) { fclose(f); return ctx_fail(c, MSMB200_ECUDA, "cudaMalloc"); }
+    cudaMemsetAsync(d_bad, 0, 4, c->stream);
+    bool ok = true;
+    for (size_t off = 0; ok && off < entries; off += chunk) {
+        const size_t cnt = std::min(chunk, entries - off);
+        ok = fread(host.data(), ab, cnt, f) == cnt &&
+             cudaMemcpyAsync(d_stage, host.data(), cnt * ab, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+             c->ops->table_io(c, 1, (int)h.format, d_stage, (char *)*slot + off * ab, cnt, d_bad) == MSMB200_OK &&
+             cudaStreamSynchronize(c->stream) == cudaSuccess;  // the host buffer is reused
+    }
+    fclose(f);
+    if (ok) ok = cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaFree(d_stage); cudaFree(d_bad);
+    if (!ok) return ctx_fail(c, MSMB200_ECUDA, std::string("reading ") + path + " failed");
+    if (bad) return ctx_fail(c, MSMB200_EINVAL, std::to_string(bad) + " entries are not valid curve points (range, flags or y^2 = x^3 + B)");
+    *have = true;
+    return MSMB200_OK;
+}
+
 long msmb200_bucket_set(msmb200_ctx *ctx, int *out, long cap) {
     if (!ctx) return MSMB200_EINVAL;
     Ctx *c = C(ctx);

@@ -108,6 +108,9 @@ struct GroupOps {
     int (*resident_blocks)(int which);
     // table[i * 2^(wbits-1) + k] = (k + 1) * P_i (blst_pNs_mult_wbits_precompute), device buffers
     int (*wbits_precompute)(Ctx *, const void *d_points, size_t npoints, int wbits, void *d_table);
+    // table persistence: dir 0 = affine entries -> blst_pN_affine_serialize bytes; dir 1 = bytes (serialized != 0) or raw
+    // Montgomery entries (serialized == 0) -> validated affine entries, *d_bad += number of invalid entries
+    int (*table_io)(Ctx *, int dir, int serialized, const void *d_src, void *d_dst, size_t n, uint32_t *d_bad);
 };
 
 int measure_peaks(double *macs_per_s, double *fp_mul_per_s);

@@ -78,7 +78,7 @@ int measure_peaks(double *macs_per_s, double *fp_mul_per_s) {
 static const GroupOps kOps = {
     sizeof(aff_t<fp_t>), sizeof(jac_t<fp_t>), sizeof(xyzz_t<fp_t>),
     msm_impl<fp_t, fpc_t>, generate_fix_points_impl<fpc_t>, table_build_impl<fpc_t>, sum_partials_impl<fpc_t>, tile_impl<fp_t, fpc_t>,
-    pippenger_impl<fp_t, fpc_t>, field_op_g, point_op_impl<fp_t, fpc_t>, digits_impl<fp_t>, resident_blocks_impl<fp_t, fpc_t>, wbits_precompute_impl<fpc_t>};
+    pippenger_impl<fp_t, fpc_t>, field_op_g, point_op_impl<fp_t, fpc_t>, digits_impl<fp_t>, resident_blocks_impl<fp_t, fpc_t>, wbits_precompute_impl<fpc_t>, table_io_impl<fpc_t>};
 const GroupOps *group_ops_g1() { return &kOps; }
 
 }  // namespace msmb200

@@ -541,6 +541,13 @@ template <class F> static int wbits_precompute_impl(Ctx *c, const void *d_points
     return MSMB200_OK;
 }
 
+template <class F> static int table_io_impl(Ctx *c, int dir, int serialized, const void *d_src, void *d_dst, size_t n, uint32_t *d_bad) {
+    if (dir == 0) table_serialize_kernel<F><<<blocks_for(n, 128), 128, 0, c->stream>>>((const aff_t<F> *)d_src, n, (uint32_t *)d_dst);
+    else table_deserialize_kernel<F><<<blocks_for(n, 128), 128, 0, c->stream>>>((const uint32_t *)d_src, n, serialized, (aff_t<F> *)d_dst, d_bad);
+    MSM_CUDA(c, cudaGetLastError());
+    return MSMB200_OK;
+}
+
 template <class F, class FC> static int resident_blocks_impl(int which) {
     if (which == 2) return 32 / coop_group_lanes<typename coop_of<FC>::type>();  // groups per warp of the cooperative kernels
     int nb = 0;

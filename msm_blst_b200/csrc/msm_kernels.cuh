@@ -1296,6 +1296,123 @@ static __global__ void __launch_bounds__(128) point_op_xyzz_kernel(int op, const
         ((xyzz_t<F> *)out)[i] = x;
     }
 }
+// ------------------------------------------------------------------------------------------------
+// table persistence: blst_p1_affine_serialize / blst_p2_affine_serialize for every entry
+// (src/e1.c:139-162, src/e2.c:176-203: from Montgomery, 48-byte big-endian X | Y, G2 as X.im | X.re | Y.im | Y.re,
+// infinity = 0x40 then zeros) and the inverse with the checks of blst_pN_deserialize (src/e1.c:303-330: flags,
+// coordinates < p, y^2 = x^3 + B with B = 4 resp. 4 + 4i, src/e1.c:14, src/e2.c:14).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fp_to_be48(uint32_t out[12], const fp_t &mont) {
+    fp_t v;
+    fp_from_mont(v, mont);
+#pragma unroll
+    for (int w = 0; w < 12; w++) out[w] = __byte_perm(v.l[11 - w], 0, 0x0123);
+}
+__device__ __forceinline__ bool fp_from_be48(fp_t &mont, const uint32_t in[12]) {  // false when the value is >= p
+    fp_t v, rr;
+#pragma unroll
+    for (int w = 0; w < 12; w++) { v.l[11 - w] = __byte_perm(in[w], 0, 0x0123); rr.l[w] = fp_rr_limb(w); }
+    uint32_t t = sub_cc(v.l[0], fp_p_limb(0));
+#pragma unroll
+    for (int i = 1; i < 12; i++) t = subc_cc(v.l[i], fp_p_limb(i));
+    (void)t;
+    const bool below = subc(0, 0) != 0;
+    fp_mul(mont, v, rr);
+    return below;
+}
+template <class F> struct fp_count;
+template <> struct fp_count<fp_t> { static constexpr int N = 1; };
+template <> struct fp_count<fpc_t> { static constexpr int N = 1; };
+template <> struct fp_count<fp2_t> { static constexpr int N = 2; };
+// y^2 == x^3 + B
+__device__ __forceinline__ bool on_curve(const aff_t<fpc_t> &p) {
+    fpc_t x2, x3, y2, b;
+    f_sqr(x2, p.x); f_mul(x3, x2, p.x); f_sqr(y2, p.y);
+    f_set_one(b); f_dbl(b, b); f_dbl(b, b);
+    f_add(x3, x3, b);
+    return f_eq(x3, y2);
+}
+__device__ __forceinline__ bool on_curve(const aff_t<fp2_t> &p) {
+    fp2_t x2, x3, y2, b;
+    f_sqr(x2, p.x); f_mul(x3, x2, p.x); f_sqr(y2, p.y);
+    fp_set_one(b.c0); fp_dbl(b.c0, b.c0); fp_dbl(b.c0, b.c0);
+    b.c1 = b.c0;
+    f_add(x3, x3, b);
+    return f_eq(x3, y2);
+}
+template <class F>
+static __global__ void __launch_bounds__(128) table_serialize_kernel(const aff_t<F> *__restrict__ in, size_t n, uint32_t *__restrict__ out) {
+    constexpr int NF = fp_count<F>::N;  // Fp elements per coordinate
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    aff_t<F> p = in[i];
+    uint32_t *o = out + i * (24 * NF);
+    if (aff_is_inf(p)) {
+#pragma unroll
+        for (int w = 0; w < 24 * NF; w++) o[w] = 0;
+        o[0] = 0x40u;  // first BYTE 0x40 (little-endian word)
+        return;
+    }
+    const fp_t *coord = reinterpret_cast<const fp_t *>(&p);  // G1: x, y; G2: x.c0, x.c1, y.c0, y.c1
+#pragma unroll
+    for (int k = 0; k < 2 * NF; k++) {
+        const int src = NF == 1 ? k : (k ^ 1);  // G2: imaginary part first
+        uint32_t be[12];
+        fp_to_be48(be, coord[src]);
+#pragma unroll
+        for (int w = 0; w < 12; w++) o[12 * k + w] = be[w];
+    }
+}
+// which entries fail is not needed: the count of bad entries (flags, range, curve equation) is accumulated
+template <class F>
+static __global__ void __launch_bounds__(128) table_deserialize_kernel(const uint32_t *__restrict__ in, size_t n, int serialized,
+                                                                       aff_t<F> *__restrict__ out, uint32_t *__restrict__ bad) {
+    constexpr int NF = fp_count<F>::N;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    aff_t<F> p;
+    bool ok = true;
+    if (serialized) {
+        const uint32_t *s = in + i * (24 * NF);
+        const uint32_t flags = s[0] & 0xe0u;
+        if (flags & 0x40u) {  // infinity: everything else must be zero
+            uint32_t acc = s[0] & ~0x40u;
+#pragma unroll
+            for (int w = 1; w < 24 * NF; w++) acc |= s[w];
+            ok = acc == 0 && flags == 0x40u;
+            fp_t *c = reinterpret_cast<fp_t *>(&p);
+#pragma unroll
+            for (int k = 0; k < 2 * NF; k++) fp_set_zero(c[k]);
+            if (ok) { out[i] = p; return; }
+        } else if (flags) {
+            ok = false;  // compressed encodings are not table entries
+        }
+        fp_t *c = reinterpret_cast<fp_t *>(&p);
+#pragma unroll
+        for (int k = 0; k < 2 * NF; k++) {
+            const int dst = NF == 1 ? k : (k ^ 1);
+            uint32_t be[12];
+#pragma unroll
+            for (int w = 0; w < 12; w++) be[w] = s[12 * k + w];
+            ok = fp_from_be48(c[dst], be) && ok;
+        }
+    } else {
+        p = reinterpret_cast<const aff_t<F> *>(in)[i];
+        const fp_t *c = reinterpret_cast<const fp_t *>(&p);
+#pragma unroll
+        for (int k = 0; k < 2 * NF; k++) {  // Montgomery limbs must be fully reduced
+            uint32_t t = sub_cc(c[k].l[0], fp_p_limb(0));
+#pragma unroll
+            for (int j = 1; j < 12; j++) t = subc_cc(c[k].l[j], fp_p_limb(j));
+            (void)t;
+            ok = (subc(0, 0) != 0) && ok;
+        }
+    }
+    if (ok && !aff_is_inf(p)) ok = on_curve(p);
+    if (!ok) atomicAdd(bad, 1u);
+    out[i] = p;
+}
+
 // ops 6,7: the lane-cooperative XYZZ addition / doubling (coop.cuh), one group (4 lanes G1, 8 lanes G2) per element
 template <class F>
 static __global__ void __launch_bounds__(128) point_op_coop_kernel(int op, const void *__restrict__ a, const void *__restrict__ b,

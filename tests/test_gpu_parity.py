@@ -665,6 +665,73 @@ def test_blst_mult_wbits_shims_vs_compiled_reference(M, golden, group, wbits):
             assert (got == ra).all(), nbits
 
 
+# ---------------------------------------------------------------- table persistence
+@pytest.mark.parametrize("group", [1, 2])
+def test_table_save_load_round_trip_and_serialized_bytes(M, group, tmp_path):
+    """msmb200_table_save / _load: format 0 is the in-memory blst_pN_affine layout, format 1 is blst_pN_affine_serialize
+    of every entry (checked against the compiled reference when present and against the oracle-pinned
+    msmb200_affine_serialize); a fresh context loads points and both tables from disk and reproduces the MSM; a
+    corrupted entry and a file written for another configuration are rejected."""
+    ab = O.AFF_BYTES[group]
+    HDR = 72  # magic, version, group, format, which, configuration, npoints, entries
+    ctx = M.MsmContext(group, "10")
+    ctx.init_fix_point_list()
+    ctx.init_pippenger_CHES_q_over_5()
+    ctx.init_pippenger_BGMW95()
+    sc = O.gen_scalars(5, ctx.n)
+    exp, _ = O.closed_form(group, sc)
+    files = {}
+    for which in (0, 1, 2):
+        for fmt in (0, 1):
+            files[(which, fmt)] = str(tmp_path / ("t%d_%d.bin" % (which, fmt)))
+            ctx.table_save(which, files[(which, fmt)], fmt)
+    tbl = ctx.download(1)
+    raw = np.fromfile(files[(1, 0)], dtype=np.uint8)
+    ser = np.fromfile(files[(1, 1)], dtype=np.uint8)
+    assert raw.size == HDR + tbl.size and ser.size == raw.size and bytes(raw[:8]) == b"MSMB200T"
+    assert (raw[HDR:] == tbl.reshape(-1)).all()
+    entries = tbl.reshape(-1, ab)
+    ser = ser[HDR:].reshape(-1, ab)
+    ref = O.blst_ref() if O.has_ref() else None
+    for k in (0, 1, 2, 777, entries.shape[0] - 1):
+        assert bytes(ser[k]) == bytes(M.affine_serialize(group, entries[k]))
+        if ref is not None:
+            out = np.zeros(ab, dtype=np.uint8)
+            getattr(ref, "blst_p%d_affine_serialize" % group)(O.ptr(out), O.ptr(np.ascontiguousarray(entries[k])))
+            assert (out == ser[k]).all()
+    ctx.close()
+    for fmt in (0, 1):
+        c2 = M.MsmContext(group, "10")
+        with pytest.raises(M.MsmB200Error):
+            c2.msm(1, sc)  # nothing loaded yet
+        for which in (0, 1, 2):
+            c2.table_load(which, files[(which, fmt)])
+        assert (c2.download(1) == tbl).all()
+        for method in (1, 2, 3, 4):
+            assert (c2.msm(method, sc) == exp).all(), (fmt, method)
+        c2.close()
+    # a flipped byte inside one entry -> not a curve point (or out of range): rejected
+    for fmt in (0, 1):
+        bad = np.fromfile(files[(1, fmt)], dtype=np.uint8)
+        bad[HDR + 5 * ab + 40] ^= 1
+        badpath = str(tmp_path / ("bad%d.bin" % fmt))
+        bad.tofile(badpath)
+        c3 = M.MsmContext(group, "10")
+        c3.table_load(0, files[(0, fmt)])
+        with pytest.raises(M.MsmB200Error):
+            c3.table_load(1, badpath)
+        with pytest.raises(M.MsmB200Error):
+            c3.msm(1, sc)  # the rejected table is not usable
+        c3.close()
+    # written for config 10 (e = 13, h = 20): a config-11 context (e = 14, h = 19) refuses it, as does the other slot
+    c4 = M.MsmContext(group, "11", npoints=1024)
+    with pytest.raises(M.MsmB200Error):
+        c4.table_load(1, files[(1, 0)])
+    with pytest.raises(M.MsmB200Error):
+        c4.table_load(2, files[(1, 0)])
+    c4.close()
+
+
 # ---------------------------------------------------------------- bucket-range sharding (tables replicated)
 @pytest.mark.parametrize("group", [1, 2])
 def test_bucket_range_shards_sum_to_full_result(M, group):
