@@ -173,6 +173,10 @@ void msmb200_blst_p2_tile_pippenger_BGMW95(void *ret_jacobian, const void *const
 
 /* blst_p1s_add / blst_p2s_add (bindings/blst.h:224,:364; src/bulk_addition.c:145-164): Jacobian sum of npoints affine
  * points (pointer-array convention as above). SURVEY §8f rank 1: the library's other consumer of bulk addition. */
+/* blst_p1s_to_affine / blst_p2s_to_affine (bindings/blst.h:222,:362; src/multi_scalar.c:17-59): batched normalisation of
+ * npoints Jacobian points (pointer-array convention as above) into dst[npoints]; SURVEY §8f rank 3. */
+void msmb200_blst_p1s_to_affine(void *dst_affine, const void *const points[], size_t npoints);
+void msmb200_blst_p2s_to_affine(void *dst_affine, const void *const points[], size_t npoints);
 void msmb200_blst_p1s_add(void *ret_jacobian, const void *const points[], size_t npoints);
 void msmb200_blst_p2s_add(void *ret_jacobian, const void *const points[], size_t npoints);
 
@@ -201,7 +205,7 @@ int msmb200_test_field_op(int device, int field, int op, const void *a, const vo
 /* point ops on n elements, group 1|2. op: 0 jac add-or-double (blst_p1_add_or_double), 1 jac double,
  * 2 xyzz += affine with sign flags (blst_p1xyzz_dadd_affine), 3 xyzz += xyzz (blst_p1xyzz_dadd),
  * 4 xyzz -> jacobian, 5 jacobian -> affine (blst_p1_to_affine), 6 / 7 quad-cooperative xyzz += xyzz / xyzz doubling
- * (csrc/coop.cuh: four lanes per point), 8 one-thread xyzz doubling */
+ * (csrc/coop.cuh: four lanes per point), 8 one-thread xyzz doubling, 9 batched jacobian -> affine (3 points per inversion) */
 int msmb200_test_point_op(int device, int group, int op, const void *a, const void *b, const unsigned char *flags,
                           void *out, size_t n);
 /* digit decomposition of the context's configuration for n scalars (host). kind 0: CHES -> out_key = bucket

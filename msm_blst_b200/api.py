@@ -168,8 +168,8 @@ def test_field_op(field, op, a, b=None, device=0):
 
 def test_point_op(group, op, a, b=None, flags=None, device=0):
     A, J, X = AFF_BYTES[group], JAC_BYTES[group], XYZZ_BYTES[group]
-    in_b = [J, J, X, X, X, J, X, X, X][op]
-    out_b = [J, J, X, X, J, A, X, X, X][op]
+    in_b = [J, J, X, X, X, J, X, X, X, J][op]
+    out_b = [J, J, X, X, J, A, X, X, X, A][op]
     a = np.ascontiguousarray(a, dtype=np.uint8)
     n = a.nbytes // in_b
     out = np.empty(n * out_b, dtype=np.uint8)

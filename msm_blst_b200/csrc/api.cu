@@ -651,10 +651,10 @@ static int point_fn(const void *a, const void *b, const unsigned char *flags, vo
     return ops->point_op(p->op, a, b, flags, out, p->n);
 }
 int msmb200_test_point_op(int device, int group, int op, const void *a, const void *b, const unsigned char *flags, void *out, size_t n) {
-    if ((group != 1 && group != 2) || op < 0 || op > 8 || !a || !out || n == 0) return MSMB200_EINVAL;
+    if ((group != 1 && group != 2) || op < 0 || op > 9 || !a || !out || n == 0) return MSMB200_EINVAL;
     const GroupOps *ops = group == 1 ? group_ops_g1() : group_ops_g2();
     size_t A = ops->aff_bytes, J = ops->jac_bytes, X = ops->xyzz_bytes;
-    size_t ab[9] = {J, J, X, X, X, J, X, X, X}, bb[9] = {J, 0, A, X, 0, 0, X, 0, 0}, ob[9] = {J, J, X, X, J, A, X, X, X};
+    size_t ab[10] = {J, J, X, X, X, J, X, X, X, J}, bb[10] = {J, 0, A, X, 0, 0, X, 0, 0, 0}, ob[10] = {J, J, X, X, J, A, X, X, X, A};
     if (bb[op] && !b) return MSMB200_EINVAL;
     PointArg arg{group, op, n};
     return with_device_buffers(device, a, n * ab[op], bb[op] ? b : nullptr, n * bb[op], flags, n, out, n * ob[op], point_fn, &arg);
@@ -821,6 +821,20 @@ static void shim_points_add(int group, void *ret, const void *const points[], si
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pNs_add"); }
     cudaFree(dp); cudaFree(dsc); cudaFree(dsg); cudaFree(dpi); cudaFree(dj);
 }
+// blst_pNs_to_affine (bindings/blst.h:222,:362; src/multi_scalar.c:17-59): batched Jacobian -> affine
+static void shim_points_to_affine(int group, void *dst, const void *const points[], size_t npoints) {
+    if (npoints == 0) return;
+    const GroupOps *ops = group == 1 ? group_ops_g1() : group_ops_g2();
+    std::vector<unsigned char> hp;
+    gather_ptr_array(hp, points, npoints, ops->jac_bytes, ops->jac_bytes);
+    const char *dev = getenv("MSMB200_DEVICE");
+    if (msmb200_test_point_op(dev ? atoi(dev) : 0, group, 9, hp.data(), nullptr, nullptr, dst, npoints)) {
+        fprintf(stderr, "msm_b200: blst_pNs_to_affine failed (no usable CUDA device?)\n");
+        abort();  // void blst signature: no error channel, and never a CPU fallback
+    }
+}
+void msmb200_blst_p1s_to_affine(void *dst, const void *const points[], size_t npoints) { shim_points_to_affine(1, dst, points, npoints); }
+void msmb200_blst_p2s_to_affine(void *dst, const void *const points[], size_t npoints) { shim_points_to_affine(2, dst, points, npoints); }
 void msmb200_blst_p1s_add(void *ret, const void *const points[], size_t npoints) { shim_points_add(1, ret, points, npoints); }
 void msmb200_blst_p2s_add(void *ret, const void *const points[], size_t npoints) { shim_points_add(2, ret, points, npoints); }
 

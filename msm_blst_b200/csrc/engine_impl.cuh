@@ -557,7 +557,8 @@ template <class F, class FC> static int resident_blocks_impl(int which) {
 }
 
 template <class F, class FC> static int point_op_impl(int op, const void *a, const void *b, const unsigned char *flags, void *out, size_t n) {
-    if (op == 2 || op == 3) point_op_xyzz_kernel<F><<<blocks_for(n, 128), 128>>>(op, a, b, flags, out, n);
+    if (op == 9) batch_to_affine_kernel<FC><<<blocks_for((n + 2) / 3, 128), 128>>>((const jac_t<FC> *)a, n, (aff_t<FC> *)out);
+    else if (op == 2 || op == 3) point_op_xyzz_kernel<F><<<blocks_for(n, 128), 128>>>(op, a, b, flags, out, n);
     else if (op == 6 || op == 7)
         point_op_coop_kernel<FC><<<blocks_for(coop_group_lanes<typename coop_of<FC>::type>() * n, 128), 128>>>(op, a, b, out, n);
     else point_op_misc_kernel<FC><<<blocks_for(n, 128), 128>>>(op, a, b, out, n);

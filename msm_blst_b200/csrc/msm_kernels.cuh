@@ -1153,6 +1153,24 @@ __device__ __forceinline__ void to_affine3(aff_t<F> *o0, const jac_t<F> &p0, aff
     if (z1) { f_set_zero(o1->x); f_set_zero(o1->y); }
     if (z2) { f_set_zero(o2->x); f_set_zero(o2->y); }
 }
+// blst_p1s_to_affine / blst_p2s_to_affine (src/multi_scalar.c:17-59): batched normalisation. The reference shares one
+// inversion over the whole batch (Montgomery's trick, serial); here every thread normalises 3 consecutive points with
+// one inversion, all threads in parallel. Affine output is canonical, so the bytes equal the reference's.
+template <class F>
+static __global__ void __launch_bounds__(128) batch_to_affine_kernel(const jac_t<F> *__restrict__ in, size_t n, aff_t<F> *__restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, i = 3 * t;
+    if (i >= n) return;
+    jac_t<F> p0 = in[i], p1, p2;
+    jac_set_inf(p1);
+    jac_set_inf(p2);
+    if (i + 1 < n) p1 = in[i + 1];
+    if (i + 2 < n) p2 = in[i + 2];
+    aff_t<F> a0, a1, a2;
+    to_affine3(&a0, p0, &a1, p1, &a2, p2);
+    out[i] = a0;
+    if (i + 1 < n) out[i + 1] = a1;
+    if (i + 2 < n) out[i + 2] = a2;
+}
 template <class F> __device__ __forceinline__ void jac_from_affine(jac_t<F> &j, const aff_t<F> &a) {
     j.x = a.x; j.y = a.y;
     if (aff_is_inf(a)) f_set_zero(j.z); else f_set_one(j.z);

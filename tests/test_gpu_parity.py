@@ -665,6 +665,44 @@ def test_blst_mult_wbits_shims_vs_compiled_reference(M, golden, group, wbits):
             assert (got == ra).all(), nbits
 
 
+@pytest.mark.parametrize("group", [1, 2])
+def test_blst_points_to_affine_shim(M, group):
+    """msmb200_blst_pNs_to_affine (batched normalisation, src/multi_scalar.c:17-59): same bytes as the
+    per-point blst_pN_to_affine of the oracle and, when present, as the compiled reference's batched call; infinity inputs
+    (Z = 0) give (0, 0); batch sizes that are not a multiple of the 3-point inversion groups."""
+    ab, jb, xb = O.AFF_BYTES[group], O.JAC_BYTES[group], O.XYZZ_BYTES[group]
+    oc = O.OracleCtx(group, "10", n=64)
+    oc.init_fix_points()
+    pts = oc.points().reshape(64, ab)
+    rng = np.random.default_rng(11)
+    n = 1000 + 1
+    # Jacobian points with non-trivial Z: sums of XYZZ accumulations converted with op 4
+    acc = np.zeros((n, xb), dtype=np.uint8)
+    for rounds in range(3):
+        acc = M.test_point_op(group, 2, acc, pts[rng.integers(0, 64, size=n)].copy(), rng.integers(0, 2, size=n).astype(np.uint8)).reshape(n, xb)
+    jac = M.test_point_op(group, 4, acc).reshape(n, jb).copy()
+    jac[5] = 0
+    jac[n - 1] = 0  # infinity in the ragged last group
+    for count in (n, n - 1, n - 2, 1, 2):
+        sub = np.ascontiguousarray(jac[:count])
+        pp = (C.c_void_p * 2)(sub.ctypes.data, None)
+        dst = np.zeros((count, ab), dtype=np.uint8)
+        getattr(M.lib(), "msmb200_blst_p%ds_to_affine" % group)(O.ptr(dst), pp, C.c_size_t(count))
+        exp = np.zeros_like(dst)
+        O.oracle().oracle_point_op(group, 5, O.ptr(sub), None, None, O.ptr(exp), count)
+        assert (dst == exp).all(), count
+        if count > 5:
+            assert not dst[5].any()
+    if O.has_ref():  # the reference's batched call is undefined for Z = 0 entries: compare on a finite range
+        sub = np.ascontiguousarray(jac[10:510])
+        pp = (C.c_void_p * 2)(sub.ctypes.data, None)
+        dst = np.zeros((500, ab), dtype=np.uint8)
+        getattr(M.lib(), "msmb200_blst_p%ds_to_affine" % group)(O.ptr(dst), pp, C.c_size_t(500))
+        rd = np.zeros_like(dst)
+        getattr(O.blst_ref(), "blst_p%ds_to_affine" % group)(O.ptr(rd), pp, C.c_size_t(500))
+        assert (rd == dst).all()
+
+
 # ---------------------------------------------------------------- table persistence (SURVEY §8f rank 2)
 @pytest.mark.parametrize("group", [1, 2])
 def test_table_save_load_round_trip_and_serialized_bytes(M, group, tmp_path):
