@@ -324,7 +324,7 @@ def main():
     method = args.method
     by_buckets = N > 1 and args.shard == "buckets"
     lo, hi = (0, n) if (by_buckets or N == 1) else D.shard_range(n, rank, N)
-    shard_cfgname = cfgname if (N == 1 or by_buckets) else (D.shard_config_name(hi - lo) if args.shard_config == "auto" else args.shard_config)
+    shard_cfgname = cfgname if (N == 1 or by_buckets) else (D.shard_config_name(hi - lo, group) if args.shard_config == "auto" else args.shard_config)
     ctx = M.MsmContext(group, shard_cfgname, npoints=hi - lo, device=local_rank, first=lo)
     if by_buckets:
         ctx.set_bucket_shard(rank, N)

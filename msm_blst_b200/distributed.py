@@ -23,10 +23,17 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def shard_config_name(n_shard):
+# Measured on B200 (tests/gpu_cfg_sweep_dev.py): configuration 16 (q = 2^19, h = 14) has an 8-bit top digit that piles
+# 256 extra entries on each of the lowest 256 bucket values, so a 2^16-point G2 shard is faster under configuration 17
+# (2.43 vs 2.92 ms); a 2^20-point G1 shard is faster with q = 2^20, h = 13 (6.00 vs 6.19 ms: the reduction shrinks more
+# than the accumulation grows).
+_SHARD_CONFIG_OVERRIDE = {(2, 16): "17", (1, 20): "19"}
+
+
+def shard_config_name(n_shard, group=1):
     """Reference configuration tuned for the shard size (legal: the output encoding is canonical)."""
     exp = max(8, min(21, (max(1, n_shard) - 1).bit_length()))
-    return str(exp)
+    return _SHARD_CONFIG_OVERRIDE.get((group, exp), str(exp))
 
 
 def all_gather_partials(partial, world=None):

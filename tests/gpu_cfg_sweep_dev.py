@@ -1,11 +1,14 @@
-"""Developer probe: same problem (n points) under different reference radices — which (e, h) is best on the GPU?"""
-import sys, os, time
+"""Developer probe: same problem (n points) under different reference radices — which (e, h) is best on the GPU for a
+shard of that size? (device time of the CHES method; the scalar upload is kept outside the timed events)"""
+import sys, os
+os.environ["MSMB200_NO_OVERLAP"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import oracle_lib as O
 import msm_blst_b200 as M
-for g, nexp, cfgs in ((1, 21, ["21", "20_beta", "17_beta", "16_beta", "13"]), (2, 18, ["18", "17_beta", "16_beta", "13"]), (1, 18, ["18", "16_beta", "13"])):
+CASES = ((2, 15, ["15", "16", "17"]), (2, 16, ["15", "16", "16_beta", "17", "18"]), (2, 17, ["16", "17", "18"]),
+         (1, 18, ["17", "18", "20"]), (1, 19, ["18", "19", "20"]), (1, 20, ["19", "20", "21"]))
+for g, nexp, cfgs in CASES:
     n = 1 << nexp
     sc = O.gen_scalars(1, n)
     cf, _ = O.closed_form(g, sc)
@@ -14,5 +17,5 @@ for g, nexp, cfgs in ((1, 21, ["21", "20_beta", "17_beta", "16_beta", "13"]), (2
         ctx.init_fix_point_list(); ctx.init_pippenger_CHES_q_over_5()
         for rep in range(3): r = ctx.msm(1, sc)
         tm = ctx.last_timings()
-        print("G%d n=2^%d cfg %-8s e=%d h=%d ok=%s dev %.2f ms | acc %.2f red %.2f" % (g, nexp, cfg, ctx.cfg.e, ctx.cfg.h, (r == cf).all(), tm["total"], tm["accumulate"], tm["reduce"]), flush=True)
+        print("G%d n=2^%d cfg %-8s e=%d h=%d ok=%s dev %.2f ms | acc %.2f red %.2f fin %.2f" % (g, nexp, cfg, ctx.cfg.e, ctx.cfg.h, (r == cf).all(), tm["total"], tm["accumulate"], tm["reduce"], tm["finalize"]), flush=True)
         ctx.close()

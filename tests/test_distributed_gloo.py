@@ -53,6 +53,7 @@ def test_shard_ranges():
             sizes = [b - a for a, b in r]
             assert max(sizes) - min(sizes) <= 1
     assert D.shard_config_name(1 << 18) == "18" and D.shard_config_name(1 << 21) == "21" and D.shard_config_name(100) == "8"
+    assert D.shard_config_name(1 << 16, 2) == "17" and D.shard_config_name(1 << 16, 1) == "16" and D.shard_config_name(1 << 20, 1) == "19"
 
 
 def test_two_rank_gather_and_sum_gloo():
