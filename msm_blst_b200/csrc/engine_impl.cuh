@@ -365,7 +365,7 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
         const uint32_t blo = (uint32_t)c->h_chunk_first[clo], bhi = (uint32_t)c->h_chunk_first[clo + ccnt];
         if (method == MSMB200_CHES) {
             // host-to-host call: upload the scalars in chunks on the copy stream and decompose each chunk as it lands
-            const int K = c->h_scalars_pending ? 8 : 1;
+            const int K = c->h_scalars_pending ? (int)std::min<size_t>(8, std::max<size_t>(1, (n * 32) >> 22)) : 1;  // >= 4 MB per chunk
             for (int k = 0; k < K; k++) {
                 const size_t i0 = n * (size_t)k / K, i1 = n * (size_t)(k + 1) / K;
                 if (i1 == i0) continue;
