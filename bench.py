@@ -277,10 +277,11 @@ def cpu_baseline_leg(group, cfgname, method, n, sets, gpu_ctx):
 
 
 # ------------------------------------------------------------------------------------------------ main arm
-# From the committed `ncu --set full` capture of accumulate_kernel (profiles/r1c_ncu_full_g1_n21_summary.txt), per launch:
+# From the committed `ncu --set full` captures of accumulate_kernel (profiles/r1c_ncu_full_g1_n21_summary.txt,
+# profiles/r1e_ncu_full_g2_n18_summary.txt), per launch:
 # dram__bytes_read.sum + dram__bytes_write.sum, and the share of cycles the heavy FMA pipe (IMAD.WIDE) was busy.
-NCU_ACCUMULATE_DRAM_BYTES = {"g1_n21": 5221708000 + 163037184}
-NCU_ACCUMULATE_FMAHEAVY_PCT = {"g1_n21": 94.7}
+NCU_ACCUMULATE_DRAM_BYTES = {"g1_n21": 5221708000 + 163037184, "g2_n18": 2821934000}
+NCU_ACCUMULATE_FMAHEAVY_PCT = {"g1_n21": 94.7, "g2_n18": 84.0}
 
 
 def main():
