@@ -29,7 +29,7 @@ __device__ __forceinline__ void f_inv(fp_t &r, const fp_t &a) { fp_inv(r, a); }
 struct __align__(16) fpc_t : fp_t {};
 __device__ __forceinline__ void fp_mul_call(fp_t &r, const fp_t &a, const fp_t &b) { r = fp_mul_fn(a, b); }
 __device__ __forceinline__ void f_mul(fpc_t &r, const fpc_t &a, const fpc_t &b) { fp_mul_call(r, a, b); }
-__device__ __forceinline__ void f_sqr(fpc_t &r, const fpc_t &a) { fp_mul_call(r, a, a); }
+__device__ __forceinline__ void f_sqr(fpc_t &r, const fpc_t &a) { fp_sqr(r, a); }
 __device__ __forceinline__ void f_add(fpc_t &r, const fpc_t &a, const fpc_t &b) { fp_add(r, a, b); }
 __device__ __forceinline__ void f_sub(fpc_t &r, const fpc_t &a, const fpc_t &b) { fp_sub(r, a, b); }
 __device__ __forceinline__ void f_cneg(fpc_t &r, const fpc_t &a, bool f) { fp_cneg(r, a, f); }
