@@ -180,6 +180,14 @@ void msmb200_blst_p2s_to_affine(void *dst_affine, const void *const points[], si
 void msmb200_blst_p1s_add(void *ret_jacobian, const void *const points[], size_t npoints);
 void msmb200_blst_p2s_add(void *ret_jacobian, const void *const points[], size_t npoints);
 
+/* blst_p{1,2}s_tile_pippenger (bindings/blst.h:242-246,:382-386; src/multi_scalar.c:587-600): ONE window of `window` bits
+ * starting at bit `bit0` (the top one when bit0 + window > nbits), result not shifted — the tile-grid entry point of the
+ * upstream Rust / Go bindings. scratch is ignored. */
+void msmb200_blst_p1s_tile_pippenger(void *ret_jacobian, const void *const points[], size_t npoints,
+                                     const unsigned char *const scalars[], size_t nbits, void *scratch, size_t bit0, size_t window);
+void msmb200_blst_p2s_tile_pippenger(void *ret_jacobian, const void *const points[], size_t npoints,
+                                     const unsigned char *const scalars[], size_t nbits, void *scratch, size_t bit0, size_t window);
+
 /* blst_p{1,2}s_mult_wbits_precompute{,_sizeof} / blst_p{1,2}s_mult_wbits{,_scratch_sizeof} (bindings/blst.h:228-236,
  * :368-376; src/multi_scalar.c:81-261): the library's fixed-window table MSM (first half).
  * table[i * 2^(wbits-1) + k] = (k + 1) * P_i, affine, in HOST memory in the reference's layout (byte-identical: affine

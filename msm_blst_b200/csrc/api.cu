@@ -692,10 +692,12 @@ static void shim_fail(Ctx *c, const char *what) {
     abort();  // void blst signature: no error channel, and never a CPU fallback
 }
 static void shim_mult_pippenger(int group, void *ret, const void *const points[], size_t npoints, const unsigned char *const scalars[],
-                                size_t nbits) {
+                                size_t nbits, int tile_bit0 = -1, int tile_window = 0) {
+    // tile_bit0 >= 0: blst_pNs_tile_pippenger — one window of tile_window bits starting at bit tile_bit0 (not shifted)
     Ctx *c = shim_ctx(group);
     size_t ab = c->ops->aff_bytes, jb = c->ops->jac_bytes;
     if (npoints == 0 || nbits == 0 || nbits > 255) { memset(ret, 0, jb); return; }
+    if (tile_bit0 >= 0 && (tile_window < 1 || tile_window > 24 || (size_t)tile_bit0 >= nbits)) { memset(ret, 0, jb); return; }
     cudaSetDevice(c->device);
     std::vector<unsigned char> hp, hs;
     gather_ptr_array(hp, points, npoints, ab, ab);
@@ -706,7 +708,7 @@ static void shim_mult_pippenger(int group, void *ret, const void *const points[]
     }
     cudaMemcpyAsync(dp, hp.data(), hp.size(), cudaMemcpyHostToDevice, c->stream);
     cudaMemcpyAsync(ds, hs.data(), hs.size(), cudaMemcpyHostToDevice, c->stream);
-    if (c->ops->pippenger(c, dp, npoints, ds, (int)nbits, dj, false, 0)) shim_fail(c, "blst_pNs_mult_pippenger");
+    if (c->ops->pippenger(c, dp, npoints, ds, (int)nbits, dj, false, 0, tile_bit0, tile_window)) shim_fail(c, "blst_pNs_mult_pippenger");
     cudaMemcpyAsync(ret, dj, jb, cudaMemcpyDeviceToHost, c->stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pNs_mult_pippenger"); }
     cudaFree(dp); cudaFree(ds); cudaFree(dj);
@@ -747,7 +749,7 @@ static void shim_mult_wbits(int group, void *ret, const void *table, size_t wbit
     }
     cudaMemcpyAsync(dt, table, total * ab, cudaMemcpyHostToDevice, c->stream);
     cudaMemcpyAsync(ds, hs.data(), hs.size(), cudaMemcpyHostToDevice, c->stream);
-    if (c->ops->pippenger(c, dt, npoints, ds, (int)nbits, dj, false, (int)wbits)) shim_fail(c, "blst_pNs_mult_wbits");
+    if (c->ops->pippenger(c, dt, npoints, ds, (int)nbits, dj, false, (int)wbits, -1, 0)) shim_fail(c, "blst_pNs_mult_wbits");
     cudaMemcpyAsync(ret, dj, jb, cudaMemcpyDeviceToHost, c->stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pNs_mult_wbits"); }
     cudaFree(dt); cudaFree(ds); cudaFree(dj);
@@ -857,6 +859,16 @@ void msmb200_blst_p1s_mult_pippenger(void *ret, const void *const points[], size
 }
 void msmb200_blst_p2s_mult_pippenger(void *ret, const void *const points[], size_t npoints, const unsigned char *const scalars[], size_t nbits, void *) {
     shim_mult_pippenger(2, ret, points, npoints, scalars, nbits);
+}
+// blst_pNs_tile_pippenger (bindings/blst.h:242-246,:382-386; src/multi_scalar.c:587-600): the tile-grid entry point the
+// upstream Rust / Go bindings use to spread windows over threads
+void msmb200_blst_p1s_tile_pippenger(void *ret, const void *const points[], size_t npoints, const unsigned char *const scalars[], size_t nbits, void *,
+                                     size_t bit0, size_t window) {
+    shim_mult_pippenger(1, ret, points, npoints, scalars, nbits, (int)bit0, (int)window);
+}
+void msmb200_blst_p2s_tile_pippenger(void *ret, const void *const points[], size_t npoints, const unsigned char *const scalars[], size_t nbits, void *,
+                                     size_t bit0, size_t window) {
+    shim_mult_pippenger(2, ret, points, npoints, scalars, nbits, (int)bit0, (int)window);
 }
 void msmb200_blst_p1_tile_pippenger_d_CHES(void *ret, const void *const points[], size_t npoints, const int scalars[], const unsigned char booth_signs[],
                                            void *, int bucket_set_ascend[], int bucket_value_to_its_index[], size_t bucket_set_size, int d_max) {

@@ -99,7 +99,7 @@ struct GroupOps {
                 size_t m, const int *d_v2i, const int *d_bucket_vals, size_t nbuckets, int d_max, const int *d_chunk_first, uint32_t vspan,
                 uint32_t nchunks, const ReducePlan *plan, void *d_out_jac);
     int (*pippenger)(Ctx *, const void *d_points, size_t npoints, const void *d_scalars, int nbits, void *d_out_jac,
-                     bool want_affine, int wbits_table);
+                     bool want_affine, int wbits_table, int tile_bit0, int tile_window);
     int (*field_op)(int field, int op, const void *a, const void *b, void *out, size_t n);
     int (*point_op)(int op, const void *a, const void *b, const unsigned char *flags, void *out, size_t n);
     int (*digits)(Ctx *, int kind, const void *d_scalars, size_t n, uint32_t *d_keys, uint32_t *d_vals);

@@ -318,14 +318,15 @@ static inline bool bgmw_trick(const msmb200_config &cfg) {
 
 template <class F, class FC>
 static int pippenger_impl(Ctx *c, const void *d_points, size_t npoints, const void *d_scalars, int nbits, void *d_out_jac,
-                          bool want_affine, int wbits_table) {
+                          bool want_affine, int wbits_table, int tile_bit0, int tile_window) {
     // wbits_table == 0: blst's Pippenger over the points themselves; > 0: blst_p1s_mult_wbits over a precomputed table of
-    // 2^(wbits-1) multiples per point (d_points is that table), one bucket per window
+    // 2^(wbits-1) multiples per point (d_points is that table), one bucket per window.
+    // tile_bit0 >= 0: only the tile of tile_window bits starting at that bit (blst_p1s_tile_pippenger), not shifted.
     cudaStream_t st = c->stream;
     c->launches = 0;
     MSM_CUDA(c, cudaEventRecord(c->ev[0], st));
-    int w = wbits_table ? wbits_table : (int)pippenger_window_size(npoints);
-    int tiles = nbits / w + 1;
+    int w = tile_bit0 >= 0 ? tile_window : wbits_table ? wbits_table : (int)pippenger_window_size(npoints);
+    int tiles = tile_bit0 >= 0 ? 1 : nbits / w + 1;
     uint32_t nbw = wbits_table ? 2u : (1u << (w - 1)) + 1u;
     size_t m = npoints * (size_t)tiles, nb = (size_t)nbw * tiles;
     int rc = prepare_entries(c, m, nb);
@@ -336,7 +337,7 @@ static int pippenger_impl(Ctx *c, const void *d_points, size_t npoints, const vo
     const uint32_t blo = 1 + clo * vs, bhi = std::min<uint32_t>(nbw, 1 + (clo + ccnt) * vs);
     digits_booth_kernel<<<blocks_for(npoints, 256), 256, 0, st>>>((const uint32_t *)d_scalars, npoints, nbits, w, tiles,
                                                                   (uint32_t *)c->keys.p, (uint32_t *)c->vals.p, (uint32_t *)c->count.p, (uint32_t *)c->ranks.p, 1,
-                                                                  wbits_table ? 1u : blo, wbits_table ? 0xffffffffu : bhi, wbits_table ? 1u << (w - 1) : 0u);
+                                                                  wbits_table ? 1u : blo, wbits_table ? 0xffffffffu : bhi, wbits_table ? 1u << (w - 1) : 0u, tile_bit0);
     c->launches += 1;
     MSM_CUDA(c, cudaEventRecord(c->ev[1], st));
     Layout L{m, nbw, (uint32_t)tiles, (uint32_t)w, nullptr, 1, nullptr, vs, nch};
@@ -351,7 +352,7 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
     const size_t n = c->n;
     if (method == MSMB200_PIPPENGER) {
         if (!c->have_points) return ctx_fail(c, MSMB200_ESTATE, "fixed points not set");
-        return pippenger_impl<F, FC>(c, c->d_points, n, d_scalars, 255, d_out_jac, want_affine, 0);
+        return pippenger_impl<F, FC>(c, c->d_points, n, d_scalars, 255, d_out_jac, want_affine, 0, -1, 0);
     }
     c->launches = 0;
     MSM_CUDA(c, cudaEventRecord(c->ev[0], st));
@@ -528,7 +529,7 @@ template <class F> static int digits_impl(Ctx *c, int kind, const void *d_scalar
     else if (kind == 1)
         digits_bgmw_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, cfg.h_bgmw, cfg.e_bgmw, bgmw_trick(cfg) ? 1 : 0, d_keys, d_vals, (uint32_t *)c->count.p, nullptr, 0, 0u, 0xffffffffu);
     else
-        digits_booth_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, 255, c->pip_window, c->pip_tiles, d_keys, d_vals, (uint32_t *)c->count.p, nullptr, 0, 0u, 0xffffffffu, 0u);
+        digits_booth_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t *)d_scalars, n, 255, c->pip_window, c->pip_tiles, d_keys, d_vals, (uint32_t *)c->count.p, nullptr, 0, 0u, 0xffffffffu, 0u, -1);
     MSM_CUDA(c, cudaGetLastError());
     MSM_CUDA(c, cudaStreamSynchronize(st));
     return MSMB200_OK;

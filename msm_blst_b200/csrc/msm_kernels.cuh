@@ -181,7 +181,10 @@ static __global__ void digits_bgmw_kernel(const uint32_t *__restrict__ scalars, 
 // key = t * (2^(w-1) + 1) + |digit|; all tiles are emitted at once (ntiles entries per scalar).
 static __global__ void digits_booth_kernel(const uint32_t *__restrict__ scalars, size_t n, int nbits, int w, int ntiles,
                                     uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count,
-                                    uint32_t *__restrict__ ranks, int digit_major, uint32_t lo, uint32_t hi, uint32_t table_nwin) {
+                                    uint32_t *__restrict__ ranks, int digit_major, uint32_t lo, uint32_t hi, uint32_t table_nwin,
+                                    int tile_bit0) {
+    // tile_bit0 >= 0: ONE tile starting at that bit (blst_p1s_tile_pippenger, src/multi_scalar.c:383-419,:587-600;
+    // ntiles must be 1): the tile is the top one when bit0 + w > nbits, exactly like the export's wrapper.
     // table_nwin != 0: blst_p1s_mult_wbits mode (src/multi_scalar.c:176-261, same window recoding): the digit selects
     // row entry |d| - 1 of point i's precomputed row (table_nwin = 2^(w-1) multiples per point) and every window has
     // ONE bucket, so key = 2t + 1 and val = i * table_nwin + |d| - 1.
@@ -191,9 +194,10 @@ static __global__ void digits_booth_kernel(const uint32_t *__restrict__ scalars,
     load_scalar(s, scalars, i);
     const uint32_t nbw = table_nwin ? 2u : (1u << (w - 1)) + 1u;
     for (int t = 0; t < ntiles; t++) {
-        int bit0 = t * w;
-        int wb = (t == ntiles - 1) ? (nbits - bit0) : w;  // bits in this tile
-        int cbits = (t == ntiles - 1) ? wb + 1 : w;
+        const int bit0 = tile_bit0 >= 0 ? tile_bit0 : t * w;
+        const bool top = tile_bit0 >= 0 ? (bit0 + w > nbits) : (t == ntiles - 1);
+        int wb = top ? (nbits - bit0) : w;  // bits in this tile
+        int cbits = top ? wb + 1 : w;
         uint32_t wval;
         if (bit0 == 0) wval = (scalar_bits(s, 0, wb) << 1);
         else wval = scalar_bits(s, bit0 - 1, wb + 1);

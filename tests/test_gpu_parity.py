@@ -665,6 +665,61 @@ def test_blst_mult_wbits_shims_vs_compiled_reference(M, golden, group, wbits):
             assert (got == ra).all(), nbits
 
 
+def _booth_tile_digit(s, nbits, bit0, window):
+    """Signed digit of scalar s for the tile (bit0, window): restatement of src/multi_scalar.c:587-600 + :395-400 +
+    booth_encode (src/ec_mult.h:45-56)."""
+    if bit0 + window > nbits:
+        wbits = nbits - bit0
+        cbits = wbits + 1
+    else:
+        wbits = cbits = window
+    wmask = (1 << (wbits + 1)) - 1
+    z = 1 if bit0 == 0 else 0
+    b0, wb = bit0 - (z ^ 1), wbits + (z ^ 1)
+    wval = (((s >> b0) & ((1 << wb) - 1)) << z) & wmask
+    sign = (wval >> cbits) & 1
+    v = (wval + 1) >> 1
+    return v - (1 << cbits) if sign else v
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_blst_tile_pippenger_shim(M, golden, group):
+    """msmb200_blst_pNs_tile_pippenger (one window, the grid entry point of the upstream bindings):
+    each tile equals sum_i digit_i * P_i with the reference's Booth digits (oracle naive MSM on digit mod r), the tiles
+    of a scalar recombine to the scalar, and the bytes equal the compiled reference's tile when oracle/_ref is present."""
+    gd = golden["pippenger_unstructured"][str(group)]
+    ab, jb = O.AFF_BYTES[group], O.JAC_BYTES[group]
+    pts = np.frombuffer(bytes.fromhex(gd["points"]), dtype=np.uint8).copy()
+    n = gd["n"]
+    sc = O.gen_scalars(91, n)
+    ints = O.scalars_to_ints(sc)
+    nbits, window = 255, 7
+    assert all(sum(_booth_tile_digit(s, nbits, b, window) << b for b in range(0, nbits + 1, window)) == s for s in ints[:50])
+    scb = np.ascontiguousarray(sc.view(np.uint8).reshape(n, 32))
+    pp = (C.c_void_p * 2)(pts.ctypes.data, None)
+    sp = (C.c_void_p * 2)(scb.ctypes.data, None)
+    fn = getattr(M.lib(), "msmb200_blst_p%ds_tile_pippenger" % group)
+    ref = O.blst_ref() if O.has_ref() else None
+    for bit0, w in ((0, 7), (7, 7), (119, 7), (252, 7), (245, 10), (13, 5)):
+        ret = np.zeros(jb, dtype=np.uint8)
+        fn(O.ptr(ret), pp, C.c_size_t(n), sp, C.c_size_t(nbits), None, C.c_size_t(bit0), C.c_size_t(w))
+        got = M.test_point_op(group, 5, ret)
+        dig = np.zeros((n, 4), dtype=np.uint64)
+        for i, s in enumerate(ints):
+            d = _booth_tile_digit(s, nbits, bit0, w) % O.R_ORDER
+            dig[i] = [(d >> (64 * k)) & (2**64 - 1) for k in range(4)]
+        exp = np.zeros(ab, dtype=np.uint8)
+        O.oracle().oracle_naive_msm(group, O.ptr(pts), O.ptr(dig), n, O.ptr(exp))
+        assert (got == exp).all(), (bit0, w)
+        if ref is not None:
+            scratch = np.zeros(O.XYZZ_BYTES[group] << (w - 1), dtype=np.uint8)
+            rj = np.zeros(jb, dtype=np.uint8)
+            getattr(ref, "blst_p%ds_tile_pippenger" % group)(O.ptr(rj), pp, C.c_size_t(n), sp, C.c_size_t(nbits), O.ptr(scratch), C.c_size_t(bit0), C.c_size_t(w))
+            ra = np.zeros(ab, dtype=np.uint8)
+            getattr(ref, "blst_p%d_to_affine" % group)(O.ptr(ra), O.ptr(rj))
+            assert (got == ra).all(), (bit0, w)
+
+
 @pytest.mark.parametrize("group", [1, 2])
 def test_blst_points_to_affine_shim(M, group):
     """msmb200_blst_pNs_to_affine (batched normalisation, src/multi_scalar.c:17-59): same bytes as the
