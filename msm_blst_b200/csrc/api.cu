@@ -220,6 +220,9 @@ static void ctx_free(Ctx *c) {
 
 // lazily created context used by the context-free blst-named shims
 static std::mutex g_shim_mu;
+// the blst functions are re-entrant; the shims share one lazily created context per group, so calls of the
+// same group are serialised (the GPU runs one MSM at a time anyway)
+static std::mutex g_shim_call_mu[3];
 static Ctx *g_shim[3] = {nullptr, nullptr, nullptr};
 static Ctx *shim_ctx(int group) {
     std::lock_guard<std::mutex> lk(g_shim_mu);
@@ -695,6 +698,7 @@ static void shim_mult_pippenger(int group, void *ret, const void *const points[]
                                 size_t nbits, int tile_bit0 = -1, int tile_window = 0) {
     // tile_bit0 >= 0: blst_pNs_tile_pippenger — one window of tile_window bits starting at bit tile_bit0 (not shifted)
     Ctx *c = shim_ctx(group);
+    std::lock_guard<std::mutex> call_lock(g_shim_call_mu[group]);
     size_t ab = c->ops->aff_bytes, jb = c->ops->jac_bytes;
     if (npoints == 0 || nbits == 0 || nbits > 255) { memset(ret, 0, jb); return; }
     if (tile_bit0 >= 0 && (tile_window < 1 || tile_window > 24 || (size_t)tile_bit0 >= nbits)) { memset(ret, 0, jb); return; }
@@ -718,6 +722,7 @@ static void shim_mult_pippenger(int group, void *ret, const void *const points[]
 // the shim uploads it per call; it is gathered by the same accumulate kernel as the CHES / BGMW95 tables.
 static void shim_wbits_precompute(int group, void *table, size_t wbits, const void *const points[], size_t npoints) {
     Ctx *c = shim_ctx(group);
+    std::lock_guard<std::mutex> call_lock(g_shim_call_mu[group]);
     size_t ab = c->ops->aff_bytes;
     if (npoints == 0 || wbits == 0 || wbits > 16) return;
     cudaSetDevice(c->device);
@@ -734,6 +739,7 @@ static void shim_wbits_precompute(int group, void *table, size_t wbits, const vo
 }
 static void shim_mult_wbits(int group, void *ret, const void *table, size_t wbits, size_t npoints, const unsigned char *const scalars[], size_t nbits) {
     Ctx *c = shim_ctx(group);
+    std::lock_guard<std::mutex> call_lock(g_shim_call_mu[group]);
     size_t ab = c->ops->aff_bytes, jb = c->ops->jac_bytes;
     if (npoints == 0 || nbits == 0 || nbits > 255 || wbits == 0 || wbits > 16 || ((double)npoints * (double)((size_t)1 << (wbits - 1))) >= 2147483648.0) {
         memset(ret, 0, jb);
@@ -757,6 +763,7 @@ static void shim_mult_wbits(int group, void *ret, const void *table, size_t wbit
 static void shim_tile(int group, void *ret, const void *const points[], size_t npoints, const int scalars[], const unsigned char signs[],
                       const int *bucket_set_ascend, const int *v2i, size_t nbuckets, int d_max) {
     Ctx *c = shim_ctx(group);
+    std::lock_guard<std::mutex> call_lock(g_shim_call_mu[group]);
     size_t ab = c->ops->aff_bytes, jb = c->ops->jac_bytes;
     cudaSetDevice(c->device);
     // points[k] are arbitrary host pointers (main_p1.cpp:219,:224 point into the 3nh table): gather them
@@ -802,6 +809,7 @@ static void shim_tile(int group, void *ret, const void *const points[], size_t n
 // work is exactly the bucket-accumulation stage (batch-affine rounds or XYZZ work items + block combine).
 static void shim_points_add(int group, void *ret, const void *const points[], size_t npoints) {
     Ctx *c = shim_ctx(group);
+    std::lock_guard<std::mutex> call_lock(g_shim_call_mu[group]);
     size_t ab = c->ops->aff_bytes, jb = c->ops->jac_bytes;
     if (npoints == 0) { memset(ret, 0, jb); return; }
     cudaSetDevice(c->device);
