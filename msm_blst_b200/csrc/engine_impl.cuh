@@ -60,6 +60,14 @@ static inline uint32_t pick_vspan(size_t max_value, uint32_t nwindows) {
     return v;
 }
 
+// experimental register-resident G2 accumulator (fp2v_t: inlined Fp2 operations); a no-op for G1
+template <class F> static inline void launch_accumulate_regacc(unsigned, cudaStream_t, const void *, const uint32_t *, const uint32_t *, const uint32_t *,
+                                                              const uint32_t *, const uint64_t *, void *) {}
+template <> inline void launch_accumulate_regacc<fp2_t>(unsigned grid, cudaStream_t st, const void *table, const uint32_t *sorted, const uint32_t *item_begin,
+                                                        const uint32_t *item_cnt, const uint32_t *order, const uint64_t *totals, void *partial) {
+    accumulate_kernel<fp2v_t><<<grid, 128, 0, st>>>((const aff_t<fp2v_t> *)table, sorted, item_begin, item_cnt, order, totals, (xyzz_t<fp2v_t> *)partial);
+}
+
 // sort + accumulate + reduce + finalize over entries already in c->keys / c->vals with histogram in c->count
 // F: field type of the hot kernels (multiplier inlined); FC: same layout, out-of-line multiplier, for the rest
 template <class F, class FC>
@@ -135,9 +143,13 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         c->launches += 8;
         MSM_CUDA(c, cudaEventRecord(c->ev[2], st));
         // ---- accumulate: XYZZ mixed additions, one thread per work item ----
-        accumulate_kernel<F><<<blocks_for(max_items, 128), 128, 0, st>>>(d_table, (const uint32_t *)c->sorted.p,
-                                                                         (const uint32_t *)c->item_begin.p, (const uint32_t *)c->item_cnt.p,
-                                                                         (const uint32_t *)c->order.p, totals, (xyzz_t<F> *)c->partial.p);
+        if (sizeof(F) > 48 && getenv("MSMB200_G2_REGACC"))  // experimental: Fp2 accumulator kept in registers
+            launch_accumulate_regacc<F>(blocks_for(max_items, 128), st, d_table, (const uint32_t *)c->sorted.p, (const uint32_t *)c->item_begin.p,
+                                        (const uint32_t *)c->item_cnt.p, (const uint32_t *)c->order.p, totals, c->partial.p);
+        else
+            accumulate_kernel<F><<<blocks_for(max_items, 128), 128, 0, st>>>(d_table, (const uint32_t *)c->sorted.p,
+                                                                             (const uint32_t *)c->item_begin.p, (const uint32_t *)c->item_cnt.p,
+                                                                             (const uint32_t *)c->order.p, totals, (xyzz_t<F> *)c->partial.p);
         {
             unsigned max_heavy = (unsigned)std::min<size_t>(m / item_len + 1, 592);
             combine_heavy_kernel<FC><<<max_heavy, 128, 0, st>>>(count, (const uint32_t *)c->item_start.p, (const uint32_t *)c->heavy.p, item_len,
