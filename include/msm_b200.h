@@ -99,6 +99,11 @@ int msmb200_set_accumulator(msmb200_ctx *ctx, int mode);
  * per-digit lists, then per-bit lists and one Horner pass; no long dependent chain). Results are identical. */
 int msmb200_set_reducer(msmb200_ctx *ctx, int mode);
 
+/* Performance knobs of one context (never change results). Keys: "ba_batch_max" (upper bound of the batch-affine slots
+ * per lane per round), "ba_batch" (forced value, 0 = automatic), "item_len" (XYZZ work-item length, 0 = automatic).
+ * The same keys are read once from the environment at context creation as MSMB200_<KEY IN CAPITALS>. */
+int msmb200_set_tuning(msmb200_ctx *ctx, const char *key, int value);
+
 /* FIX_POINTS_LIST (main_p1.cpp:47): upload caller's affine points (host memory, npoints entries). */
 int msmb200_set_points(msmb200_ctx *ctx, const void *points_affine_host);
 /* init_fix_point_list (main_p1.cpp:52-66): P_i = 2^(first+i+1) * G computed on the device. */

@@ -68,6 +68,7 @@ def lib():
         L.msmb200_set_stream.argtypes = [vp, vp]
         L.msmb200_set_points.argtypes = [vp, vp]
         L.msmb200_set_accumulator.argtypes = [vp, ci]
+        L.msmb200_set_tuning.argtypes = [vp, C.c_char_p, ci]
         L.msmb200_set_reducer.argtypes = [vp, ci]
         L.msmb200_table_save.argtypes = [vp, ci, C.c_char_p, ci]
         L.msmb200_table_load.argtypes = [vp, ci, C.c_char_p]
@@ -218,6 +219,10 @@ class MsmContext:
     def set_accumulator(self, mode):
         """0 default, 1 XYZZ work items, 2 batch-affine rounds (identical results)."""
         self._ck(lib().msmb200_set_accumulator(self._h, int(mode)))
+
+    def set_tuning(self, key, value):
+        """Performance knobs ("ba_batch_max", "ba_batch", "item_len"); results never change."""
+        self._ck(lib().msmb200_set_tuning(self._h, str(key).encode(), int(value)))
 
     def table_save(self, which, path, fmt=1):
         """which: 0 fixed points, 1 CHES 3nh table, 2 BGMW95 table; fmt 0 raw Montgomery layout, 1 blst_pN_affine_serialize."""

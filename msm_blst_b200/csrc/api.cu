@@ -195,6 +195,12 @@ static int ctx_init_common(Ctx *c, int group, int device) {
     MSM_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto &e : c->ev_chunk) MSM_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     MSM_CUDA(c, cudaMallocHost(&c->h_result, 512));
+    MSM_CUDA(c, cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device));
+    if (const char *e = getenv("MSMB200_BA_BATCH")) c->ba_batch_fixed = atoi(e);
+    if (const char *e = getenv("MSMB200_ITEM_LEN")) c->item_len_fixed = std::max(0, atoi(e));
+    if (const char *e = getenv("MSMB200_ACCUM")) c->accum_env = atoi(e);
+    if (const char *e = getenv("MSMB200_REDUCE")) c->reduce_env = atoi(e);
+    if (const char *e = getenv("MSMB200_BA_BATCH_MAX")) c->ba_batch_max = std::max(1, atoi(e));
     return MSMB200_OK;
 }
 
@@ -204,13 +210,15 @@ static void ctx_free(Ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->scalars, &c->keys, &c->vals, &c->ranks, &c->sorted, &c->count, &c->packed, &c->scanned, &c->tile_sums, &c->seg_start,
                       &c->item_start, &c->cursor, &c->item_begin, &c->item_cnt, &c->order, &c->len_hist, &c->len_start, &c->len_cursor,
-                      &c->partial, &c->chunk_a, &c->chunk_b, &c->result, &c->flat, &c->signs, &c->pidx, &c->heavy, &c->light, &c->medium, &c->bucket_of0, &c->bo_a, &c->bo_b,
-                      &c->pts_a, &c->pts_b, &c->base_a, &c->base_b, &c->tile_sums2, &c->maxcount, &c->red_a, &c->red_b, &c->red_c, &c->red_d};
+                      &c->partial, &c->chunk_a, &c->chunk_b, &c->result, &c->flat, &c->signs, &c->pidx, &c->heavy, &c->light, &c->medium,
+                      &c->ba_totals, &c->ba_tile_sums, &c->ba_bases, &c->ba_adesc, &c->ba_cdesc, &c->ba_heavy, &c->pts_a, &c->pts_b, &c->ba_scratch,
+                      &c->bucket_sum, &c->iota, &c->maxcount, &c->red_a, &c->red_b, &c->red_c, &c->red_d};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     free_reduce_plan(c->plan_ches); free_reduce_plan(c->plan_bgmw); free_reduce_plan(c->plan_pip);
     void *ptrs[] = {c->d_bucket_vals, c->d_v2i, c->d_dtab, c->d_chunk_first, c->d_points, c->d_table_ches, c->d_table_bgmw};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_result) cudaFreeHost(c->h_result);
+    if (c->h_totals) cudaFreeHost(c->h_totals);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->ev_chunk) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -384,6 +392,16 @@ int msmb200_set_accumulator(msmb200_ctx *ctx, int mode) {
 int msmb200_set_reducer(msmb200_ctx *ctx, int mode) {
     if (!ctx || mode < 0 || mode > 2) return MSMB200_EINVAL;
     C(ctx)->reduce_mode = mode;
+    return MSMB200_OK;
+}
+int msmb200_set_tuning(msmb200_ctx *ctx, const char *key, int value) {
+    if (!ctx || !key || value < 0) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    const std::string k(key);
+    if (k == "ba_batch_max") c->ba_batch_max = std::max(1, value);
+    else if (k == "ba_batch") c->ba_batch_fixed = value;
+    else if (k == "item_len") c->item_len_fixed = value;
+    else return ctx_fail(c, MSMB200_EINVAL, "unknown tuning key " + k);
     return MSMB200_OK;
 }
 int msmb200_set_points(msmb200_ctx *ctx, const void *points_affine_host) {

@@ -31,7 +31,7 @@ struct Layout {
 
 static inline bool use_split_reduce(const Ctx *c, const Layout &L) {
     int mode = c->reduce_mode;
-    if (const char *e = getenv("MSMB200_REDUCE")) mode = atoi(e);
+    if (c->reduce_env) mode = c->reduce_env;
     return L.plan && L.plan->valid && mode != 1 && (L.nwindows == 1 || L.plan->nbits_w <= L.wbits);
 }
 // dense plans (value == local index) are built on first use and cached per (buckets per window, windows)
@@ -68,6 +68,99 @@ template <> inline void launch_accumulate_regacc<fp2_t>(unsigned grid, cudaStrea
     accumulate_kernel<fp2v_t><<<grid, 128, 0, st>>>((const aff_t<fp2v_t> *)table, sorted, item_begin, item_cnt, order, totals, (xyzz_t<fp2v_t> *)partial);
 }
 
+static __global__ void iota_kernel(uint32_t *out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)i;
+}
+
+// Batch-affine bucket accumulation (batch_affine.cuh). Entries are in c->keys / c->vals / c->ranks with the bucket
+// histogram in `count`; on return c->bucket_sum[b] holds the affine sum of every non-empty bucket. Steps: per-round
+// totals (one small read-back: the number of rounds and the slot counts size every later launch exactly), the
+// exclusive scans of all rounds in one pass, the counting-sort scatter, the slot descriptors, then one arithmetic
+// kernel per round. Records ev[2] between planning and arithmetic ("sort" / "accumulate" phases).
+template <class F>
+static int ba_accumulate(Ctx *c, const aff_t<F> *d_table, uint32_t *count, size_t nb, size_t m) {
+    cudaStream_t st = c->stream;
+    if (ensure(c, c->ba_totals, (3 * BA_RMAX + 1) * 4)) return MSMB200_ECUDA;
+    if (!c->h_totals) MSM_CUDA(c, cudaMallocHost((void **)&c->h_totals, (3 * BA_RMAX + 1) * 4));
+    MSM_CUDA(c, cudaMemsetAsync(c->ba_totals.p, 0, (3 * BA_RMAX + 1) * 4, st));
+    ba_totals_kernel<<<(unsigned)std::min<size_t>(blocks_for(nb, 256), (size_t)c->sms * 4), 256, 0, st>>>(count, nb, (uint32_t *)c->ba_totals.p);
+    MSM_CUDA(c, cudaMemcpyAsync(c->h_totals, c->ba_totals.p, (3 * BA_RMAX + 1) * 4, cudaMemcpyDeviceToHost, st));
+    MSM_CUDA(c, cudaStreamSynchronize(st));
+    const uint32_t *T = c->h_totals;
+    BaRounds rd{};
+    uint32_t R = 0;
+    while (R < BA_RMAX && T[3 * R] != 0) R++;
+    const uint32_t Rs = std::max<uint32_t>(R, 1);  // round 0 always exists: single-entry buckets are copied there
+    rd.R = Rs;
+    size_t a_total = 0, c_total = 0, e_odd = 1, e_even = 1;
+    for (uint32_t r = 0; r < Rs; r++) {
+        rd.aoff[r] = (uint32_t)a_total; a_total += T[3 * r];
+        rd.coff[r] = (uint32_t)c_total; c_total += T[3 * r + 1];
+        if (r >= 1) (r & 1 ? e_odd : e_even) = std::max<size_t>(r & 1 ? e_odd : e_even, T[3 * r + 2]);
+    }
+    rd.aoff[Rs] = (uint32_t)a_total; rd.coff[Rs] = (uint32_t)c_total;
+    const size_t ntiles = (nb + BA_TILE - 1) / BA_TILE, nbs = ntiles * BA_TILE, NR = 3 * (size_t)Rs;
+    const size_t scratch_stride = ((size_t)T[0] + 31) & ~(size_t)31;
+    if (ensure(c, c->ba_tile_sums, ntiles * NR * 4) || ensure(c, c->ba_bases, NR * nbs * 4) || ensure(c, c->ba_adesc, (a_total + 1) * 8) ||
+        ensure(c, c->ba_cdesc, (c_total + 1) * 8) || ensure(c, c->ba_heavy, (m / BA_HEAVY + 2) * 4) || ensure(c, c->pts_a, e_odd * sizeof(aff_t<F>)) ||
+        ensure(c, c->pts_b, e_even * sizeof(aff_t<F>)) || ensure(c, c->ba_scratch, (scratch_stride + 1) * sizeof(F)) ||
+        ensure(c, c->bucket_sum, nb * sizeof(aff_t<F>)) || ensure(c, c->sorted, (m + 2) * 4))
+        return MSMB200_ECUDA;
+    if (c->iota_n < nb) {
+        if (ensure(c, c->iota, nb * 4)) return MSMB200_ECUDA;
+        iota_kernel<<<blocks_for(nb, 256), 256, 0, st>>>((uint32_t *)c->iota.p, nb);
+        c->iota_n = nb;
+    }
+    const unsigned warp_blocks = blocks_for(ntiles * 32, 256);
+    ba_scan_tiles_kernel<<<warp_blocks, 256, 0, st>>>(count, nb, Rs, (uint32_t *)c->ba_tile_sums.p, ntiles);
+    ba_scan_sums_kernel<<<(unsigned)NR, 256, 0, st>>>((uint32_t *)c->ba_tile_sums.p, ntiles, (uint32_t)NR);
+    ba_scan_apply_kernel<<<warp_blocks, 256, 0, st>>>(count, nb, Rs, (const uint32_t *)c->ba_tile_sums.p, ntiles, (uint32_t *)c->ba_bases.p, nbs);
+    const uint32_t *bases = (const uint32_t *)c->ba_bases.p;
+    scatter_kernel<<<blocks_for(m, 256), 256, 0, st>>>((const uint32_t *)c->keys.p, (const uint32_t *)c->vals.p, m, bases + 2 * nbs,
+                                                       (const uint32_t *)c->ranks.p, (uint32_t *)c->sorted.p);
+    MSM_CUDA(c, cudaMemsetAsync(c->ba_heavy.p, 0, 4, st));
+    ba_emit_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, nb, bases, nbs, rd, (uint2 *)c->ba_adesc.p, (uint2 *)c->ba_cdesc.p, (uint32_t *)c->ba_heavy.p);
+    if (T[3 * BA_RMAX] > BA_HEAVY)
+        ba_emit_heavy_kernel<<<(unsigned)std::min<size_t>(m / BA_HEAVY + 1, (size_t)c->sms * 2), 256, 0, st>>>(count, bases, nbs, rd, (uint2 *)c->ba_adesc.p,
+                                                                                                          (uint2 *)c->ba_cdesc.p, (const uint32_t *)c->ba_heavy.p);
+    c->launches += 8;
+    MSM_CUDA(c, cudaEventRecord(c->ev[2], st));
+    // ---- arithmetic rounds ----
+    if (c->ba_resident <= 0) {
+        int nbk = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, ba_round_kernel<F, false>, BA_THREADS, 0) != cudaSuccess || nbk < 1) nbk = 2;
+        c->ba_resident = nbk;
+    }
+    const size_t wave = (size_t)c->sms * c->ba_resident;   // co-resident blocks
+    aff_t<F> *pts[2] = {(aff_t<F> *)c->pts_b.p, (aff_t<F> *)c->pts_a.p};  // round r writes pts[(r + 1) & 1]: round 0 -> pts_a (E_1)
+    for (uint32_t r = 0; r < Rs; r++) {
+        const uint32_t A = T[3 * r], Cn = T[3 * r + 1];
+        // batch per lane: whole waves of equal blocks, at most ba_batch_max slots per lane
+        uint32_t B = 1;
+        if (A) {
+            const size_t per_wave = wave * BA_THREADS;
+            size_t w = 1;
+            while ((A + per_wave * w - 1) / (per_wave * w) > (size_t)c->ba_batch_max) w++;
+            B = (uint32_t)std::max<size_t>(1, (A + per_wave * w - 1) / (per_wave * w));
+        }
+        if (c->ba_batch_fixed > 0) B = (uint32_t)c->ba_batch_fixed;
+        const size_t add_blocks = A ? ((size_t)A + (size_t)B * BA_THREADS - 1) / ((size_t)B * BA_THREADS) : 0;
+        const size_t copy_blocks = std::min<size_t>(blocks_for(Cn, BA_THREADS), wave);
+        const unsigned grid = (unsigned)std::max<size_t>(1, std::max(add_blocks, copy_blocks));
+        const uint2 *ad = (const uint2 *)c->ba_adesc.p + rd.aoff[r], *cd = (const uint2 *)c->ba_cdesc.p + rd.coff[r];
+        if (r == 0)
+            ba_round_kernel<F, true><<<grid, BA_THREADS, 0, st>>>(d_table, (const uint32_t *)c->sorted.p, ad, A, cd, Cn, pts[1], (aff_t<F> *)c->bucket_sum.p,
+                                                                  (uint4 *)c->ba_scratch.p, scratch_stride, B);
+        else
+            ba_round_kernel<F, false><<<grid, BA_THREADS, 0, st>>>(pts[r & 1], nullptr, ad, A, cd, Cn, pts[(r + 1) & 1], (aff_t<F> *)c->bucket_sum.p,
+                                                                   (uint4 *)c->ba_scratch.p, scratch_stride, B);
+        c->launches += 1;
+    }
+    MSM_CUDA(c, cudaGetLastError());
+    return MSMB200_OK;
+}
+
 // sort + accumulate + reduce + finalize over entries already in c->keys / c->vals with histogram in c->count
 // F: field type of the hot kernels (multiplier inlined); FC: same layout, out-of-line multiplier, for the rest
 template <class F, class FC>
@@ -93,7 +186,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     // The longest chain is the critical path: with ~3 warps sharing a sub-partition it advances at a third of the pipe
     // rate, so keep item_len * 3 below half of the ideal duration of the whole phase (m / (592 * 32) additions per lane).
     item_len = (uint32_t)std::max<size_t>(8, std::min<size_t>(item_len, m / ((size_t)592 * 32 * 6)));
-    if (const char *e = getenv("MSMB200_ITEM_LEN")) item_len = (uint32_t)std::max(1, atoi(e));
+    if (c->item_len_fixed > 0) item_len = (uint32_t)c->item_len_fixed;
     const size_t max_items = std::min(nb, m) + m / item_len + 1;
     const size_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
 
@@ -108,21 +201,22 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     uint32_t *count = (uint32_t *)c->count.p;
     // ---- sort by bucket ----
     int mode = c->accum_mode;
-    if (const char *e = getenv("MSMB200_ACCUM")) mode = atoi(e);
+    if (c->accum_env) mode = c->accum_env;
     if (mode == 0) mode = MSMB200_DEFAULT_ACCUM;
     const bool batch_affine = mode == 2;
-    if (batch_affine && ensure(c, c->bucket_of0, (m + nb + 2) * 4)) return MSMB200_ECUDA;
-    MSM_CUDA(c, cudaMemsetAsync(c->maxcount.p, 0, 4, st));
-    prep_counts_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, (uint64_t *)c->packed.p, nb, item_len, (uint32_t *)c->maxcount.p);
-    scan_tiles_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>((const uint64_t *)c->packed.p, (uint64_t *)c->scanned.p,
-                                                                   (uint64_t *)c->tile_sums.p, nb);
-    scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>((uint64_t *)c->tile_sums.p, ntiles);
-    scan_finish_kernel<<<blocks_for(nb, 256), 256, 0, st>>>((const uint64_t *)c->scanned.p, (const uint64_t *)c->tile_sums.p,
-                                                            (uint32_t *)c->seg_start.p, (uint32_t *)c->item_start.p,
-                                                            (uint32_t *)c->cursor.p, nb);
-    scatter_kernel<<<blocks_for(m, 256), 256, 0, st>>>((const uint32_t *)c->keys.p, (const uint32_t *)c->vals.p, m,
-                                                       (const uint32_t *)c->seg_start.p, (const uint32_t *)c->ranks.p,
-                                                       (uint32_t *)c->sorted.p, batch_affine ? (uint32_t *)c->bucket_of0.p : nullptr);
+    if (!batch_affine) {
+        MSM_CUDA(c, cudaMemsetAsync(c->maxcount.p, 0, 4, st));
+        prep_counts_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, (uint64_t *)c->packed.p, nb, item_len, (uint32_t *)c->maxcount.p);
+        scan_tiles_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>((const uint64_t *)c->packed.p, (uint64_t *)c->scanned.p,
+                                                                       (uint64_t *)c->tile_sums.p, nb);
+        scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>((uint64_t *)c->tile_sums.p, ntiles);
+        scan_finish_kernel<<<blocks_for(nb, 256), 256, 0, st>>>((const uint64_t *)c->scanned.p, (const uint64_t *)c->tile_sums.p,
+                                                                (uint32_t *)c->seg_start.p, (uint32_t *)c->item_start.p,
+                                                                (uint32_t *)c->cursor.p, nb);
+        scatter_kernel<<<blocks_for(m, 256), 256, 0, st>>>((const uint32_t *)c->keys.p, (const uint32_t *)c->vals.p, m,
+                                                           (const uint32_t *)c->seg_start.p, (const uint32_t *)c->ranks.p,
+                                                           (uint32_t *)c->sorted.p);
+    }
     const uint64_t *totals = (const uint64_t *)c->tile_sums.p + ntiles;
     const void *bucket_points = nullptr;      // what the reduction reads: XYZZ partials or affine points
     const uint32_t *bucket_point_index = nullptr;
@@ -171,57 +265,10 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         bucket_points = c->partial.p;
         bucket_point_index = (const uint32_t *)c->item_start.p;
     } else {
-        c->launches += 5;
-        MSM_CUDA(c, cudaEventRecord(c->ev[2], st));
-        // ---- accumulate: batch-affine pairwise rounds ----
-        uint32_t max_count = 0;
-        MSM_CUDA(c, cudaMemcpyAsync(&max_count, c->maxcount.p, 4, cudaMemcpyDeviceToHost, st));
-        MSM_CUDA(c, cudaStreamSynchronize(st));
-        int rounds = 1;
-        while (((size_t)1 << rounds) < max_count) rounds++;
-        int BATCH = sizeof(F) > 48 ? 8 : 32;
-        if (const char *e = getenv("MSMB200_BA_BATCH")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) BATCH = v; }
-        const size_t out_cap = m / 2 + 2 * nb + 4;
-        if (ensure(c, c->pts_a, out_cap * sizeof(aff_t<F>)) || ensure(c, c->pts_b, (out_cap / 2 + 2 * nb + 4) * sizeof(aff_t<F>)) ||
-            ensure(c, c->bo_a, out_cap * 4) || ensure(c, c->bo_b, (out_cap / 2 + 2 * nb + 4) * 4) || ensure(c, c->base_a, nb * 4) ||
-            ensure(c, c->base_b, nb * 4) || ensure(c, c->tile_sums2, (ntiles + 1) * 8))
-            return MSMB200_ECUDA;
-        const aff_t<F> *in_pts = nullptr;
-        const uint32_t *bo_in = (const uint32_t *)c->bucket_of0.p, *base_in = (const uint32_t *)c->seg_start.p;
-        const uint64_t *tot_in = totals;
-        aff_t<F> *pts[2] = {(aff_t<F> *)c->pts_a.p, (aff_t<F> *)c->pts_b.p};
-        uint32_t *bo[2] = {(uint32_t *)c->bo_a.p, (uint32_t *)c->bo_b.p};
-        uint32_t *base[2] = {(uint32_t *)c->base_a.p, (uint32_t *)c->base_b.p};
-        uint64_t *ts[2] = {(uint64_t *)c->tile_sums2.p, (uint64_t *)c->tile_sums.p};
-        size_t bound_in = m + nb + 2;  // upper bound of the padded input length of the round
-        for (int r = 0; r < rounds; r++) {
-            const int o = r & 1;
-            ba_plan_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, (uint64_t *)c->packed.p, nb, r + 1);
-            scan_tiles_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>((const uint64_t *)c->packed.p, (uint64_t *)c->scanned.p, ts[o], nb);
-            scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(ts[o], ntiles);
-            ba_scan_finish_kernel<<<blocks_for(nb, 256), 256, 0, st>>>((const uint64_t *)c->scanned.p, ts[o], base[o], nb);
-            const size_t threads = (bound_in / 2 + BATCH - 1) / BATCH + 1;
-            const int laneinv = getenv("MSMB200_BA_LANEINV") ? 1 : 0;
-#define MSM_BA_LAUNCH(B_)                                                                                                                          \
-    do {                                                                                                                                           \
-        if (r == 0)                                                                                                                                \
-            ba_round_kernel<F, true, B_><<<blocks_for(threads, 128), 128, 0, st>>>(d_table, (const uint32_t *)c->sorted.p, nullptr, bo_in, base_in, \
-                                                                                   count, r, tot_in, base[o], pts[o], bo[o], laneinv);             \
-        else                                                                                                                                       \
-            ba_round_kernel<F, false, B_><<<blocks_for(threads, 128), 128, 0, st>>>(d_table, nullptr, in_pts, bo_in, base_in, count, r, tot_in,     \
-                                                                                    base[o], pts[o], bo[o], laneinv);                              \
-    } while (0)
-            if (BATCH == 4) MSM_BA_LAUNCH(4); else if (BATCH == 8) MSM_BA_LAUNCH(8); else if (BATCH == 16) MSM_BA_LAUNCH(16); else MSM_BA_LAUNCH(32);
-#undef MSM_BA_LAUNCH
-            c->launches += 5;
-            in_pts = pts[o];
-            bo_in = bo[o];
-            base_in = base[o];
-            tot_in = ts[o] + ntiles;
-            bound_in = bound_in / 2 + nb + 2;
-        }
-        bucket_points = in_pts;
-        bucket_point_index = base_in;
+        int rc = ba_accumulate<F>(c, d_table, count, nb, m);
+        if (rc) return rc;
+        bucket_points = c->bucket_sum.p;
+        bucket_point_index = (const uint32_t *)c->iota.p;
     }
     MSM_CUDA(c, cudaEventRecord(c->ev[3], st));
     // ---- reduce ----

@@ -13,19 +13,33 @@ using namespace msmb200;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
-constexpr int ITERS = 4096;
 
-// A: mad.wide.u32 (IMAD.WIDE.U32), 8 independent 64-bit accumulators
-__global__ void k_imad_wide(uint64_t *out, uint32_t a, uint32_t b, long long *cyc) {
+// How the variants differ (SASS of each checked with cuobjdump; ptxas folds `acc += x * y` with loop-invariant x, y into
+// ONE multiplication plus 64-bit adds — the round-1 "peak" kernel measured IADD3, not IMAD.WIDE — so every variant here
+// takes at least one multiplicand from a value that changes every iteration):
+//   A  c += lo(c) * y          y shared by all instructions (operand-reuse cache can serve it)
+//   B  c += lo(c) * hi(c')     both multiplicands change, one is the accumulator's own low word
+//   C  c += lo(c') * hi(c'')   4 distinct source registers per instruction (what a field multiplier issues)
+//   I  c += lo(c) * imm        multiplicand is an immediate (the m * p rows of the Montgomery reduction)
+//   L  32-bit IMAD (lo only)   a = a * y + z
+#define WIDE(acc, x, y) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(x), "r"(y))
+__device__ __forceinline__ uint32_t lo32(uint64_t v) { return (uint32_t)v; }
+__device__ __forceinline__ uint32_t hi32(uint64_t v) { return (uint32_t)(v >> 32); }
+template <int VARIANT> __global__ void k_imad_wide(uint64_t *out, uint32_t a, uint32_t b, int iters, long long *cyc) {
     uint64_t acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = threadIdx.x + k;
-    uint32_t x = a + threadIdx.x, y = b;
+    for (int k = 0; k < 8; k++) acc[k] = ((uint64_t)(threadIdx.x * 2654435761u + k) << 32) | (a * (k + 1) + threadIdx.x);
+    const uint32_t y = b | 1u;
     long long t0 = clock64();
 #pragma unroll 1
-    for (int i = 0; i < ITERS; i++) {
+    for (int i = 0; i < iters; i++) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(x), "r"(y));
+        for (int k = 0; k < 8; k++) {
+            if (VARIANT == 0) WIDE(acc[k], lo32(acc[k]), y);
+            else if (VARIANT == 1) WIDE(acc[k], lo32(acc[k]), hi32(acc[(k + 1) & 7]));
+            else if (VARIANT == 2) WIDE(acc[k], lo32(acc[(k + 1) & 7]), hi32(acc[(k + 3) & 7]));
+            else asm volatile("mad.wide.u32 %0, %1, 0x1eabfffe, %0;" : "+l"(acc[k]) : "r"(lo32(acc[k])));
+        }
     }
     long long t1 = clock64();
     uint64_t s = 0;
@@ -34,49 +48,87 @@ __global__ void k_imad_wide(uint64_t *out, uint32_t a, uint32_t b, long long *cy
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
-// B: carry-chained pairs mad.lo.cc/madc.hi.cc (IMAD.WIDE.U32.X) exactly as the field multiplier issues them
-__global__ void k_imad_chain(uint32_t *out, uint32_t a, uint32_t b, long long *cyc) {
-    uint32_t acc[16];
+__global__ void k_imad_lo(uint32_t *out, uint32_t a, uint32_t b, int iters, long long *cyc) {
+    uint32_t acc[8];
 #pragma unroll
-    for (int k = 0; k < 16; k++) acc[k] = threadIdx.x + k;
-    uint32_t x = a + threadIdx.x, y = b;
+    for (int k = 0; k < 8; k++) acc[k] = a * (k + 1) + threadIdx.x;
+    const uint32_t y = b | 1u;
     long long t0 = clock64();
 #pragma unroll 1
-    for (int i = 0; i < ITERS; i++) {
-        acc[0] = mad_lo_cc(x, y, acc[0]);
-        acc[1] = madc_hi_cc(x, y, acc[1]);
+    for (int i = 0; i < iters; i++) {
 #pragma unroll
-        for (int k = 2; k < 16; k += 2) {
-            acc[k] = madc_lo_cc(x, y, acc[k]);
-            acc[k + 1] = madc_hi_cc(x, y, acc[k + 1]);
-        }
+        for (int k = 0; k < 8; k++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(acc[k]) : "r"(y), "r"(acc[(k + 1) & 7]));
     }
     long long t1 = clock64();
     uint32_t s = 0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) s ^= acc[k];
+    for (int k = 0; k < 8; k++) s ^= acc[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
-// C: 32-bit mad.lo (IMAD) + mad.hi (IMAD.HI) as separate instructions: 2 issue slots per full MAC
-__global__ void k_imad_lohi(uint32_t *out, uint32_t a, uint32_t b, long long *cyc) {
-    uint32_t acc[16];
+// P: pure 32x32->64 products (IMAD.WIDE.U32 with RZ addend) consumed by ONE 3-input LOP3 each; H: IMAD.HI.U32 only;
+// U: ALU-pipe reference, 3-input integer adds (the two adds per element fuse into one IADD3)
+template <int VARIANT> __global__ void k_prod(uint32_t *out, uint32_t a, uint32_t b, int iters, long long *cyc) {
+    uint32_t x[8];
 #pragma unroll
-    for (int k = 0; k < 16; k++) acc[k] = threadIdx.x + k;
-    uint32_t x = a + threadIdx.x, y = b;
+    for (int k = 0; k < 8; k++) x[k] = a * (2 * k + 1) + threadIdx.x * 2654435761u;
+    const uint32_t y = b | 1u;
     long long t0 = clock64();
 #pragma unroll 1
-    for (int i = 0; i < ITERS; i++) {
+    for (int i = 0; i < iters; i++) {
 #pragma unroll
-        for (int k = 0; k < 16; k += 2) {
-            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(x), "r"(y));
-            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(acc[k + 1]) : "r"(x), "r"(y));
+        for (int k = 0; k < 8; k++) {
+            if (VARIANT == 0) {
+                uint64_t t;
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(x[k]), "r"(x[(k + 3) & 7]));
+                x[k] = lo32(t) ^ hi32(t) ^ y;
+            } else if (VARIANT == 1) {
+                uint32_t t;
+                asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(t) : "r"(x[k]), "r"(x[(k + 3) & 7]));
+                x[k] = t ^ x[(k + 1) & 7] ^ y;
+            } else {
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(x[k]) : "r"(x[(k + 1) & 7]));
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(x[k]) : "r"(y));
+            }
         }
     }
     long long t1 = clock64();
     uint32_t s = 0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) s ^= acc[k];
+    for (int k = 0; k < 8; k++) s ^= x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+// X: carry-chained IMAD.WIDE.U32.X rows exactly as the field multiplier issues them (two interleaved chains of 6, the
+// multiplicands a[k] distinct, b_i shared by the row and replaced every row)
+__global__ void k_imad_chain(uint32_t *out, uint32_t a, uint32_t b, int iters, long long *cyc) {
+    uint32_t ev[12], od[12], x[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) { ev[k] = threadIdx.x + k; od[k] = a + k; x[k] = a * (2 * k + 1) + threadIdx.x; }
+    uint32_t y = b | 1u;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+        od[0] = mad_lo_cc(x[1], y, od[0]);
+        od[1] = madc_hi_cc(x[1], y, od[1]);
+#pragma unroll
+        for (int k = 2; k < 12; k += 2) {
+            od[k] = madc_lo_cc(x[k + 1], y, od[k]);
+            od[k + 1] = madc_hi_cc(x[k + 1], y, od[k + 1]);
+        }
+        ev[0] = mad_lo_cc(x[0], y, ev[0]);
+        ev[1] = madc_hi_cc(x[0], y, ev[1]);
+#pragma unroll
+        for (int k = 2; k < 12; k += 2) {
+            ev[k] = madc_lo_cc(x[k], y, ev[k]);
+            ev[k + 1] = madc_hi_cc(x[k], y, ev[k + 1]);
+        }
+        y = ev[0] ^ od[1];  // next row's b_i depends on this row: nothing is loop-invariant
+    }
+    long long t1 = clock64();
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 12; k++) s ^= ev[k] ^ od[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -150,11 +202,19 @@ int main() {
     CK(cudaMemcpy(d_in, h.data(), sizeof(fp_t) * 1024, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_in + 1024, h.data(), sizeof(fp_t) * 1024, cudaMemcpyHostToDevice));
     printf("{\n  \"device\": \"%s\", \"sms\": %d, \"clock_khz_max\": %d,\n", pr.name, sms, pr.clockRate);
-    // MAC-peak kernels: 4 blocks/SM x 256 threads = 32 warps/SM
-    run("imad_wide_u32", 8.0 * ITERS, sms * 4, 256, k_imad_wide, d_cyc, false, (uint64_t *)d_out, 3u, 5u);
-    run("imad_wide_x_chain", 8.0 * ITERS, sms * 4, 256, k_imad_chain, d_cyc, false, (uint32_t *)d_out, 3u, 5u);
-    run("imad_lo_hi_pair", 8.0 * ITERS, sms * 4, 256, k_imad_lohi, d_cyc, false, (uint32_t *)d_out, 3u, 5u);
-    run("imad_wide_u32_8w", 8.0 * ITERS, sms * 1, 256, k_imad_wide, d_cyc, false, (uint64_t *)d_out, 3u, 5u);
+    // MAC-peak kernels: 4 blocks/SM x 256 threads = 32 warps/SM, >= 50 ms each so that the SM clock has settled; the
+    // per-clock figure comes from clock64 inside the kernel, eff_mhz = cycles / wall time is the clock it ran at
+    const int big = 400000;
+    run("imad_wide_A_shared_multiplicand", 8.0 * big, sms * 4, 256, k_imad_wide<0>, d_cyc, false, (uint64_t *)d_out, 3u, 5u, big);
+    run("imad_wide_B_two_changing", 8.0 * big, sms * 4, 256, k_imad_wide<1>, d_cyc, false, (uint64_t *)d_out, 3u, 5u, big);
+    run("imad_wide_C_four_distinct_regs", 8.0 * big, sms * 4, 256, k_imad_wide<2>, d_cyc, false, (uint64_t *)d_out, 3u, 5u, big);
+    run("imad_wide_I_immediate", 8.0 * big, sms * 4, 256, k_imad_wide<3>, d_cyc, false, (uint64_t *)d_out, 3u, 5u, big);
+    run("imad_wide_C_8w", 8.0 * big, sms * 1, 256, k_imad_wide<2>, d_cyc, false, (uint64_t *)d_out, 3u, 5u, big);
+    run("imad_wide_P_product_plus_lop3", 8.0 * big, sms * 4, 256, k_prod<0>, d_cyc, false, (uint32_t *)d_out, 3u, 5u, big);
+    run("imad_hi_32bit", 8.0 * big, sms * 4, 256, k_prod<1>, d_cyc, false, (uint32_t *)d_out, 3u, 5u, big);
+    run("alu_iadd3", 8.0 * big, sms * 4, 256, k_prod<2>, d_cyc, false, (uint32_t *)d_out, 3u, 5u, big);
+    run("imad_lo_32bit", 8.0 * big, sms * 4, 256, k_imad_lo, d_cyc, false, (uint32_t *)d_out, 3u, 5u, big);
+    run("imad_wide_x_chain_rows", 12.0 * (big / 2), sms * 4, 256, k_imad_chain, d_cyc, false, (uint32_t *)d_out, 3u, 5u, big / 2);
     // fp_mul: 2 muls per iteration; vary warps per SM
     const int it = 512;
     run("fp_mul_4w", 2.0 * it, sms * 1, 128, k_fp_mul, d_cyc, false, (fp_t *)d_out, (const fp_t *)d_in, it);

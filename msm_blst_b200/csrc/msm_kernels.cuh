@@ -11,6 +11,7 @@
 #include <cstdint>
 #include "ec.cuh"
 #include "coop.cuh"
+#include "batch_affine.cuh"
 
 namespace msmb200 {
 
@@ -225,8 +226,7 @@ constexpr int SCAN_ITEMS = 8;  // per thread
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 // packs (count, nitems) into one u64 so one scan yields segment starts and item starts
-// Segments are padded to an even length so that the batch-affine rounds can pair elements (2s, 2s+1) without
-// straddling buckets. Also records the largest bucket (number of pairwise rounds needed).
+// Also records the largest bucket.
 static __global__ void prep_counts_kernel(const uint32_t *__restrict__ count, uint64_t *__restrict__ packed, size_t nb, uint32_t item_len,
                                           uint32_t *__restrict__ max_count) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -235,7 +235,7 @@ static __global__ void prep_counts_kernel(const uint32_t *__restrict__ count, ui
     if ((threadIdx.x & 31) == 0 && wmax) atomicMax(max_count, wmax);
     if (b >= nb) return;
     uint32_t items = (c + item_len - 1) / item_len;
-    packed[b] = (uint64_t)(c + (c & 1u)) | ((uint64_t)items << 32);
+    packed[b] = (uint64_t)c | ((uint64_t)items << 32);
 }
 __device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t *total) {
     __shared__ uint64_t warp_sums[SCAN_THREADS / 32];
@@ -300,7 +300,7 @@ static __global__ void scan_finish_kernel(const uint64_t *__restrict__ scanned, 
 }
 static __global__ void scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, size_t m,
                                const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ ranks,
-                               uint32_t *__restrict__ sorted, uint32_t *__restrict__ bucket_of /* may be null */) {
+                               uint32_t *__restrict__ sorted) {
     // counting-sort scatter; the position inside the bucket was fixed by the histogram atomic (ranks), so no atomics here
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m) return;
@@ -308,7 +308,6 @@ static __global__ void scatter_kernel(const uint32_t *__restrict__ keys, const u
     if (key == KEY_SKIP) return;
     uint32_t pos = seg_start[key] + ranks[k];
     sorted[pos] = vals[k];
-    if (bucket_of) bucket_of[pos] = key;
 }
 // One work item = up to item_len consecutive entries of one bucket (a bucket with a huge count is split so
 // that no thread serialises more than item_len additions). Also builds the histogram of item lengths.
@@ -437,194 +436,7 @@ static __global__ void __launch_bounds__(128) combine_heavy_kernel(const uint32_
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// [3'] bucket accumulation by BATCH-AFFINE pairwise rounds — the GPU analogue of the reference's
-// POINTonE1s_accumulate / HEAD / TAIL (src/bulk_addition.c:51-143): affine + affine -> affine with the
-// slope denominators of a whole batch inverted together by Montgomery's trick (5M+1S per addition plus the
-// shared inversion, :27), doubling folded into the same batch with denominator 2y (:63-74), P + (-P) and
-// infinity inputs resolved without arithmetic.
-// Round r turns every bucket's list of k = ceil(count / 2^r) points into ceil(k/2) points; lists sit at even
-// offsets (base_in), slot s pairs elements (2s, 2s+1) of one bucket. One thread handles BATCH consecutive slots:
-// forward pass (denominators, running product kept in local memory), ONE field inversion (binary GCD: ALU
-// pipe, not the saturated multiplier pipe), backward pass (slopes, results). Round 0 reads the table through
-// the sorted (index | sign) references, later rounds read the previous round's points.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ba_len(uint32_t count, int r) { return count ? ((count - 1u) >> r) + 1u : 0u; }
-
-static __global__ void ba_plan_kernel(const uint32_t *__restrict__ count, uint64_t *__restrict__ packed, size_t nb, int r_next) {
-    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    uint32_t k = ba_len(count[b], r_next);
-    packed[b] = (uint64_t)(k + (k & 1u));
-}
-static __global__ void ba_scan_finish_kernel(const uint64_t *__restrict__ scanned, const uint64_t *__restrict__ tile_sums,
-                                             uint32_t *__restrict__ base_next, size_t nb) {
-    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    base_next[b] = (uint32_t)(scanned[b] + tile_sums[b / SCAN_TILE]);
-}
-enum { BA_NONE = 0, BA_ADD = 1, BA_DBL = 2, BA_COPY_P = 3, BA_COPY_Q = 4, BA_INF = 5 };
-
-// warp shuffles of whole field elements (12 / 24 words)
-__device__ __forceinline__ void f_shfl_up(fp_t &r, const fp_t &a, int o) {
-#pragma unroll
-    for (int k = 0; k < 12; k++) r.l[k] = __shfl_up_sync(0xffffffffu, a.l[k], o);
-}
-__device__ __forceinline__ void f_shfl_down(fp_t &r, const fp_t &a, int o) {
-#pragma unroll
-    for (int k = 0; k < 12; k++) r.l[k] = __shfl_down_sync(0xffffffffu, a.l[k], o);
-}
-__device__ __forceinline__ void f_shfl_idx(fp_t &r, const fp_t &a, int src) {
-#pragma unroll
-    for (int k = 0; k < 12; k++) r.l[k] = __shfl_sync(0xffffffffu, a.l[k], src);
-}
-__device__ __forceinline__ void f_shfl_up(fp2_t &r, const fp2_t &a, int o) { f_shfl_up(r.c0, a.c0, o); f_shfl_up(r.c1, a.c1, o); }
-__device__ __forceinline__ void f_shfl_down(fp2_t &r, const fp2_t &a, int o) { f_shfl_down(r.c0, a.c0, o); f_shfl_down(r.c1, a.c1, o); }
-__device__ __forceinline__ void f_shfl_idx(fp2_t &r, const fp2_t &a, int src) { f_shfl_idx(r.c0, a.c0, src); f_shfl_idx(r.c1, a.c1, src); }
-__device__ __forceinline__ void f_shfl_up(fpc_t &r, const fpc_t &a, int o) { f_shfl_up((fp_t &)r, (const fp_t &)a, o); }
-__device__ __forceinline__ void f_shfl_down(fpc_t &r, const fpc_t &a, int o) { f_shfl_down((fp_t &)r, (const fp_t &)a, o); }
-__device__ __forceinline__ void f_shfl_idx(fpc_t &r, const fpc_t &a, int src) { f_shfl_idx((fp_t &)r, (const fp_t &)a, src); }
-
-// Montgomery's trick ACROSS the warp: every lane holds a non-zero `run`; returns 1/run in every lane with ONE field
-// inversion per warp (all lanes invert the same total, so the data-dependent GCD loop does not diverge):
-// prefix and suffix products by shuffles (5 + 5 multiplications), 1/run = 1/total * prefix_excl * suffix_excl.
-template <class F> __device__ __noinline__ void warp_batch_invert(F &inv, const F &run) {
-    // control flow is kept warp-uniform (lanes that have nothing to fold multiply by one): no divergent calls between shuffles
-    __syncwarp();
-    const int lane = threadIdx.x & 31;
-    F pre = run, suf = run, other, one;
-    f_set_one(one);
-#pragma unroll 1
-    for (int o = 1; o < 32; o <<= 1) {
-        f_shfl_up(other, pre, o);
-        if (lane < o) other = one;
-        f_mul(pre, pre, other);
-        f_shfl_down(other, suf, o);
-        if (lane + o >= 32) other = one;
-        f_mul(suf, suf, other);
-    }
-    F total, tinv, pre_ex, suf_ex;
-    f_shfl_idx(total, pre, 31);
-    f_inv(tinv, total);
-    f_shfl_up(pre_ex, pre, 1);
-    f_shfl_down(suf_ex, suf, 1);
-    if (lane == 0) pre_ex = one;
-    if (lane == 31) suf_ex = one;
-    f_mul(tinv, tinv, pre_ex);
-    f_mul(tinv, tinv, suf_ex);
-    inv = tinv;
-    __syncwarp();
-}
-template <class F, bool FIRST>
-__device__ __forceinline__ void ba_load(aff_t<F> &p, size_t e, const aff_t<F> *__restrict__ table, const uint32_t *__restrict__ sorted,
-                                        const aff_t<F> *__restrict__ in_pts) {
-    if (FIRST) {
-        uint32_t v = sorted[e];
-        load_affine(p, table, v & 0x7fffffffu);
-        f_cneg(p.y, p.y, (v >> 31) != 0);  // infinity (0,0) stays (0,0)
-    } else {
-        load_affine(p, in_pts, (uint32_t)e);
-    }
-}
-template <class F, bool FIRST, int BATCH>
-static __global__ void __launch_bounds__(128) ba_round_kernel(const aff_t<F> *__restrict__ table, const uint32_t *__restrict__ sorted,
-                                                              const aff_t<F> *__restrict__ in_pts, const uint32_t *__restrict__ bucket_of_in,
-                                                              const uint32_t *__restrict__ base_in, const uint32_t *__restrict__ count, int r,
-                                                              const uint64_t *__restrict__ total_in, const uint32_t *__restrict__ base_out,
-                                                              aff_t<F> *__restrict__ out_pts, uint32_t *__restrict__ bucket_of_out, int lane_inversion) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t s0 = t * BATCH;
-    const size_t nslots = (size_t)((uint32_t)*total_in) >> 1;  // padded total (low half of the packed scan total) is even
-    if (__all_sync(0xffffffffu, s0 >= nslots)) return;  // whole warp idle; otherwise every lane takes part in the shuffles
-    F prefix[BATCH];
-    unsigned char tag[BATCH];
-    F run;
-    f_set_one(run);
-    // ---- forward: classify, collect denominators ----
-#pragma unroll 1
-    for (int j = 0; j < BATCH; j++) {
-        const size_t s = s0 + j;
-        unsigned char tg = BA_NONE;
-        if (s < nslots) {
-            const uint32_t b = bucket_of_in[2 * s];
-            const uint32_t i = (uint32_t)(2 * s) - base_in[b];
-            const uint32_t k = ba_len(count[b], r);
-            if (i + 1 < k) {
-                aff_t<F> P, Q;
-                ba_load<F, FIRST>(P, 2 * s, table, sorted, in_pts);
-                ba_load<F, FIRST>(Q, 2 * s + 1, table, sorted, in_pts);
-                F d;
-                if (aff_is_inf(P)) tg = BA_COPY_Q;
-                else if (aff_is_inf(Q)) tg = BA_COPY_P;
-                else {
-                    f_sub(d, Q.x, P.x);
-                    if (!f_is_zero(d)) tg = BA_ADD;
-                    else if (f_eq(P.y, Q.y) && !f_is_zero(P.y)) { tg = BA_DBL; f_dbl(d, P.y); }
-                    else tg = BA_INF;
-                }
-                if (tg == BA_ADD || tg == BA_DBL) {
-                    prefix[j] = run;
-                    f_mul(run, run, d);
-                }
-            } else if (i < k) {
-                tg = BA_COPY_P;
-            }
-        }
-        tag[j] = tg;
-    }
-    F inv;
-    if (lane_inversion) f_inv(inv, run);  // one GCD per lane (diverges); kept as a fallback knob
-    else warp_batch_invert(inv, run);    // one GCD per warp
-    // ---- backward: slopes and results ----
-#pragma unroll 1
-    for (int j = BATCH - 1; j >= 0; j--) {
-        const unsigned char tg = tag[j];
-        if (tg == BA_NONE) continue;
-        const size_t s = s0 + j;
-        const uint32_t b = bucket_of_in[2 * s];
-        const uint32_t i = (uint32_t)(2 * s) - base_in[b];
-        const uint32_t o = base_out[b] + (i >> 1);
-        aff_t<F> P, R;
-        ba_load<F, FIRST>(P, 2 * s, table, sorted, in_pts);
-        if (tg == BA_COPY_P) {
-            R = P;
-        } else if (tg == BA_INF) {
-            f_set_zero(R.x);
-            f_set_zero(R.y);
-        } else {
-            aff_t<F> Q;
-            ba_load<F, FIRST>(Q, 2 * s + 1, table, sorted, in_pts);
-            if (tg == BA_COPY_Q) {
-                R = Q;
-            } else {
-                F d, dinv, lam, t1;
-                if (tg == BA_ADD) f_sub(d, Q.x, P.x);
-                else f_dbl(d, P.y);
-                f_mul(dinv, inv, prefix[j]);
-                f_mul(inv, inv, d);
-                if (tg == BA_ADD) {
-                    f_sub(t1, Q.y, P.y);
-                    f_mul(lam, t1, dinv);            // lambda = (y2 - y1) / (x2 - x1)
-                    f_sqr(t1, lam);
-                    f_sub(t1, t1, P.x);
-                    f_sub(R.x, t1, Q.x);             // x3 = lambda^2 - x1 - x2
-                } else {
-                    f_sqr(t1, P.x);
-                    f_mul3(t1, t1);
-                    f_mul(lam, t1, dinv);            // lambda = 3 x1^2 / (2 y1)
-                    f_sqr(t1, lam);
-                    f_sub(t1, t1, P.x);
-                    f_sub(R.x, t1, P.x);             // x3 = lambda^2 - 2 x1
-                }
-                f_sub(t1, P.x, R.x);
-                f_mul(t1, t1, lam);
-                f_sub(R.y, t1, P.y);                 // y3 = lambda (x1 - x3) - y1
-            }
-        }
-        out_pts[o] = R;
-        bucket_of_out[o] = b;
-    }
-}
+// [3'] bucket accumulation by batch-affine pairwise rounds (default): batch_affine.cuh
 
 // ------------------------------------------------------------------------------------------------
 // [4] bucket reduction. Replaces POINTonE1_integrate_buckets_accumulation_d_CHES (src/multi_scalar.c:301-321)
@@ -787,12 +599,6 @@ static __global__ void __launch_bounds__(256) tree_tail_kernel(xyzz_t<F> *in, ui
 //   MODE 1: same, but the sums are affine points (batch-affine accumulation)
 //   MODE 2: members index a dense XYZZ array (output of the previous stage)
 // ------------------------------------------------------------------------------------------------
-template <class F> __device__ __forceinline__ void xyzz_shfl_down(xyzz_t<F> &r, const xyzz_t<F> &a, int o) {
-    f_shfl_down(r.x, a.x, o);
-    f_shfl_down(r.y, a.y, o);
-    f_shfl_down(r.zzz, a.zzz, o);
-    f_shfl_down(r.zz, a.zz, o);
-}
 template <class F, int MODE>
 static __global__ void __launch_bounds__(128) list_sum_kernel(const void *__restrict__ src, const uint32_t *__restrict__ count,
                                                               const uint32_t *__restrict__ item_start, uint32_t in_stride,
@@ -1278,11 +1084,10 @@ static __global__ void __launch_bounds__(128) fix_points_kernel(const jac_t<F> *
 template <class F>
 static __global__ void field_op_kernel(int op, const F *__restrict__ a, const F *__restrict__ b, F *__restrict__ out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (op == 7) {  // warp-level Montgomery trick (warp_batch_invert): every lane participates, idle lanes hold one
+    if (op == 7) {  // the per-lane branch-free inversion of the batch-affine rounds (inv.cuh): every lane takes part in the vote
         F x, r;
         if (i < n) x = a[i]; else f_set_one(x);
-        if (f_is_zero(x)) f_set_one(x);
-        warp_batch_invert(r, x);
+        f_inv_warp(r, x);
         if (i < n) out[i] = r;
         return;
     }
