@@ -29,6 +29,17 @@ constexpr int BA_RMAX = 32;                   // rounds: counts are < 2^32
 constexpr uint32_t BA_FINAL = 0x80000000u;    // output descriptor: bucket_sum[b] instead of the next round's buffer
 constexpr uint32_t BA_HEAVY = 2048;           // buckets with more entries are planned by a whole block
 constexpr int BA_THREADS = 128;
+// resident blocks per SM the round kernel is compiled for (register budget 65536 / (128 x blocks) per thread)
+#ifndef BA_MIN_BLOCKS_FP
+#define BA_MIN_BLOCKS_FP 3
+#endif
+#ifndef BA_STAGE_Y_FP
+#define BA_STAGE_Y_FP 1
+#endif
+#ifndef BA_MIN_BLOCKS_FP2
+#define BA_MIN_BLOCKS_FP2 2
+#endif
+template <class F> struct ba_cfg { static constexpr int MIN_BLOCKS = sizeof(F) > 48 ? BA_MIN_BLOCKS_FP2 : BA_MIN_BLOCKS_FP; };
 
 // filled by the host once the per-round totals are known
 struct BaRounds {
@@ -173,36 +184,50 @@ static __global__ void __launch_bounds__(256) ba_scan_apply_kernel(const uint32_
 }
 
 // ---- descriptors: one thread per bucket (block per heavy bucket) writes every round's slots of its bucket ----
+// Descriptors are RESOLVED: {p, q, out, 0} with p, q = index of the operand in the round's source array (the
+// precomputation table in round 0, bit 31 = negate; the previous round's points later) — the arithmetic kernel needs no
+// further indirection. Copy descriptors are {p, out}.
 __device__ __forceinline__ void ba_emit_round(uint32_t b, uint32_t c, uint32_t r, const uint32_t *__restrict__ bases, size_t nbs,
-                                              const BaRounds &rd, uint2 *__restrict__ adesc, uint2 *__restrict__ cdesc, uint32_t i0, uint32_t istep) {
+                                              const BaRounds &rd, const uint32_t *__restrict__ sorted, uint4 *__restrict__ adesc,
+                                              uint2 *__restrict__ cdesc, uint32_t i0, uint32_t istep) {
     const uint32_t k = ba_len(c, r), a = k >> 1, k1 = (k + 1) >> 1;
     const uint32_t eb = bases[(size_t)(3 * r + 2) * nbs + b];
     const uint32_t ob = k1 == 1 ? (BA_FINAL | b) : bases[(size_t)(3 * r + 5) * nbs + b];
     const uint32_t ab = rd.aoff[r] + bases[(size_t)(3 * r) * nbs + b];
-    for (uint32_t i = i0; i < a; i += istep) adesc[ab + i] = make_uint2(eb + 2 * i, k1 == 1 ? ob : ob + i);
-    if (i0 == 0 && (k & 1u)) cdesc[rd.coff[r] + bases[(size_t)(3 * r + 1) * nbs + b]] = make_uint2(eb + k - 1, ob + a);  // k >= 3 here
+    for (uint32_t i = i0; i < a; i += istep) {
+        const uint32_t in = eb + 2 * i;
+        adesc[ab + i] = make_uint4(r == 0 ? sorted[in] : in, r == 0 ? sorted[in + 1] : in + 1, k1 == 1 ? ob : ob + i, 0u);
+    }
+    if (i0 == 0 && (k & 1u)) {  // k >= 3 here
+        const uint32_t in = eb + k - 1;
+        cdesc[rd.coff[r] + bases[(size_t)(3 * r + 1) * nbs + b]] = make_uint2(r == 0 ? sorted[in] : in, ob + a);
+    }
 }
 static __global__ void __launch_bounds__(256) ba_emit_kernel(const uint32_t *__restrict__ count, size_t nb, const uint32_t *__restrict__ bases, size_t nbs,
-                                                             BaRounds rd, uint2 *__restrict__ adesc, uint2 *__restrict__ cdesc,
-                                                             uint32_t *__restrict__ heavy /* [0] = count, then bucket ids */) {
+                                                             BaRounds rd, const uint32_t *__restrict__ sorted, uint4 *__restrict__ adesc,
+                                                             uint2 *__restrict__ cdesc, uint32_t *__restrict__ heavy /* [0] = count, then bucket ids */,
+                                                             uint4 *__restrict__ bucket_sum16, uint32_t aff_chunks) {
     const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     const uint32_t c = count[b];
-    if (c == 0) return;
+    if (c == 0) {  // an empty bucket sums to infinity (the reduction may read it)
+        for (uint32_t k = 0; k < aff_chunks; k++) bucket_sum16[b * aff_chunks + k] = make_uint4(0, 0, 0, 0);
+        return;
+    }
     if (c == 1) {  // a single entry goes straight to the bucket sum (copy list of round 0)
-        cdesc[rd.coff[0] + bases[(size_t)1 * nbs + b]] = make_uint2(bases[(size_t)2 * nbs + b], BA_FINAL | (uint32_t)b);
+        cdesc[rd.coff[0] + bases[(size_t)1 * nbs + b]] = make_uint2(sorted[bases[(size_t)2 * nbs + b]], BA_FINAL | (uint32_t)b);
         return;
     }
     if (c > BA_HEAVY) { heavy[1 + atomicAdd(&heavy[0], 1u)] = (uint32_t)b; return; }
-    for (uint32_t r = 0; r < rd.R && ba_len(c, r) >= 2; r++) ba_emit_round((uint32_t)b, c, r, bases, nbs, rd, adesc, cdesc, 0, 1);
+    for (uint32_t r = 0; r < rd.R && ba_len(c, r) >= 2; r++) ba_emit_round((uint32_t)b, c, r, bases, nbs, rd, sorted, adesc, cdesc, 0, 1);
 }
 static __global__ void __launch_bounds__(256) ba_emit_heavy_kernel(const uint32_t *__restrict__ count, const uint32_t *__restrict__ bases, size_t nbs,
-                                                                   BaRounds rd, uint2 *__restrict__ adesc, uint2 *__restrict__ cdesc,
-                                                                   const uint32_t *__restrict__ heavy) {
+                                                                   BaRounds rd, const uint32_t *__restrict__ sorted, uint4 *__restrict__ adesc,
+                                                                   uint2 *__restrict__ cdesc, const uint32_t *__restrict__ heavy) {
     const uint32_t nheavy = heavy[0];
     for (uint32_t hi = blockIdx.x; hi < nheavy; hi += gridDim.x) {
         const uint32_t b = heavy[1 + hi], c = count[b];
-        for (uint32_t r = 0; r < rd.R && ba_len(c, r) >= 2; r++) ba_emit_round(b, c, r, bases, nbs, rd, adesc, cdesc, threadIdx.x, blockDim.x);
+        for (uint32_t r = 0; r < rd.R && ba_len(c, r) >= 2; r++) ba_emit_round(b, c, r, bases, nbs, rd, sorted, adesc, cdesc, threadIdx.x, blockDim.x);
     }
 }
 
@@ -263,136 +288,300 @@ template <class F> __device__ __forceinline__ void ba_scratch_ld(F &v, const uin
 
 enum { BA_TAG_ADD = 0, BA_TAG_DBL = 1, BA_TAG_COPY_P = 2, BA_TAG_COPY_Q = 3, BA_TAG_INF = 4 };
 
-// where the two operands of a slot live: round 0 reads the precomputation table through the bucket-sorted
-// (index | sign << 31) references, later rounds read the previous round's points
-template <class F, bool FIRST> struct ba_operands {
-    const aff_t<F> *p, *q;
-    bool sp, sq;
-    __device__ __forceinline__ ba_operands(const aff_t<F> *__restrict__ src, const uint32_t *__restrict__ sorted, uint32_t in, bool two) {
-        if (FIRST) {
-            const uint32_t v0 = sorted[in], v1 = two ? sorted[in + 1] : v0;
-            p = src + (v0 & 0x7fffffffu); sp = (v0 >> 31) != 0;
-            q = src + (v1 & 0x7fffffffu); sq = (v1 >> 31) != 0;
-        } else {
-            p = src + in; q = src + in + (two ? 1 : 0);
-            sp = sq = false;
-        }
-    }
-};
-// rare operand patterns (an infinity operand, equal x): decided from the full points, identically in both passes
+// rare operand patterns (an infinity operand, equal x): decided from the full points, identically in both passes.
+// Everything by value: nothing of the hot loops has its address taken (no local memory).
+template <class F> struct ba_cold_t { F d; int tag; };
 template <class F>
-static __device__ __noinline__ int ba_classify_cold(const aff_t<F> *p, bool sp, const aff_t<F> *q, bool sq, F &d) {
+static __device__ __noinline__ ba_cold_t<F> ba_classify_cold(const F *px, const F *py, bool sp, const F *qx, const F *qy, bool sq) {
+    ba_cold_t<F> r;
     F x1, y1, x2, y2;
-    f_ld(x1, &p->x); f_ld(y1, &p->y); f_ld(x2, &q->x); f_ld(y2, &q->y);
+    f_ld(x1, px); f_ld(y1, py); f_ld(x2, qx); f_ld(y2, qy);
     f_cneg(y1, y1, sp);
     f_cneg(y2, y2, sq);
-    if (f_is_zero(x1) && f_is_zero(y1)) return BA_TAG_COPY_Q;
-    if (f_is_zero(x2) && f_is_zero(y2)) return BA_TAG_COPY_P;
-    f_sub(d, x2, x1);
-    if (!f_is_zero(d)) return BA_TAG_ADD;
-    if (f_eq(y1, y2) && !f_is_zero(y1)) { f_dbl(d, y1); return BA_TAG_DBL; }
-    return BA_TAG_INF;
+    f_sub(r.d, x2, x1);
+    if (f_is_zero(x1) && f_is_zero(y1)) r.tag = BA_TAG_COPY_Q;
+    else if (f_is_zero(x2) && f_is_zero(y2)) r.tag = BA_TAG_COPY_P;
+    else if (!f_is_zero(r.d)) r.tag = BA_TAG_ADD;
+    else if (f_eq(y1, y2) && !f_is_zero(y1)) { f_dbl(r.d, y1); r.tag = BA_TAG_DBL; }
+    else r.tag = BA_TAG_INF;
+    return r;
 }
 
-template <class F> __device__ __forceinline__ void ba_store_point(uint32_t out, aff_t<F> *__restrict__ pts_out, aff_t<F> *__restrict__ bucket_sum,
-                                                                  const F &x, const F &y) {
-    aff_t<F> *dst = (out & BA_FINAL) ? bucket_sum + (out & ~BA_FINAL) : pts_out + out;
-    f_st(&dst->x, x);
-    f_st(&dst->y, y);
+// Where a round reads its operands and writes its results. Round 0 reads the precomputation table (array of {x, y});
+// between rounds the points live in SEPARATE x[] and y[] arrays, so the forward pass, which needs only x, streams half the
+// bytes. Final results (one per bucket) go to bucket_sum as {x, y} for the reducers.
+template <class F> struct ba_io {
+    const aff_t<F> *table;       // round 0 only
+    const F *in_x, *in_y;        // rounds >= 1
+    F *out_x, *out_y;
+    aff_t<F> *bucket_sum;
+};
+template <class F, bool FIRST> __device__ __forceinline__ const F *ba_px(const ba_io<F> &io, uint32_t i) { return FIRST ? &io.table[i].x : io.in_x + i; }
+template <class F, bool FIRST> __device__ __forceinline__ const F *ba_py(const ba_io<F> &io, uint32_t i) { return FIRST ? &io.table[i].y : io.in_y + i; }
+template <class F> __device__ __forceinline__ void ba_store_point(uint32_t out, const ba_io<F> &io, const F &x, const F &y) {
+    if (out & BA_FINAL) {
+        aff_t<F> *dst = io.bucket_sum + (out & ~BA_FINAL);
+        f_st(&dst->x, x);
+        f_st(&dst->y, y);
+    } else {
+        f_st(io.out_x + out, x);
+        f_st(io.out_y + out, y);
+    }
 }
+
+// ---- asynchronous staging of slot operands in shared memory (cp.async, SASS LDGSTS) ----
+// A lane does only 1 (forward) or 5 (backward) multiplications per slot, each an out-of-line call, and a call waits for
+// every register load still in flight — so nothing the hot loops need may be a pending register load. Descriptors and
+// operands are copied global -> shared ahead of use instead: thread t owns 16-byte chunk k of a stage at
+// (k * 128 + t) * 16 (conflict-free) and reads back only what it copied itself, so cp.async.wait_group is the only
+// synchronisation. Forward: descriptors four slots ahead, x coordinates two slots ahead (one multiplication per slot
+// hides little). Backward: descriptors two slots ahead, prefix product and both points one slot ahead.
+__device__ __forceinline__ uint32_t ba_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ba_cp16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+template <class F> __device__ __forceinline__ void ba_prefetch_l2(const F *p) {   // both 128-byte lines an element can touch
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p) + sizeof(F) - 16));
+}
+__device__ __forceinline__ void ba_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void ba_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t ba_chunk(int k) { return (uint32_t)((k * BA_THREADS + threadIdx.x) * 16); }
+template <class F> __device__ __forceinline__ void ba_cp_field(uint32_t base, int chunk0, const F *src) {
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(F) / 16); k++) ba_cp16(base + ba_chunk(chunk0 + k), reinterpret_cast<const uint4 *>(src) + k);
+}
+template <class F> __device__ __forceinline__ void ba_ld_stage(F &v, const unsigned char *base, int chunk0) {
+    uint4 *dst = reinterpret_cast<uint4 *>(&v);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(F) / 16); k++) dst[k] = *reinterpret_cast<const uint4 *>(base + ba_chunk(chunk0 + k));
+}
+#ifdef MSMB200_BA_TIMING   // developer builds only: per-block phase time stamps (clock64) of every round
+constexpr int BA_DBG_BLOCKS = 4096;
+static __device__ unsigned long long ba_dbg[BA_RMAX][BA_DBG_BLOCKS][4];
+#define BA_STAMP(k) do { if (threadIdx.x == 0 && blockIdx.x < BA_DBG_BLOCKS) ba_dbg[round][blockIdx.x][k] += clock64(); } while (0)
+#else
+#define BA_STAMP(k) do { } while (0)
+#endif
+template <class F> struct ba_smem {
+    static constexpr int FCH = (int)(sizeof(F) / 16);        // 16-byte chunks per field element
+    static constexpr int FWD_DESC = 4, FWD_STAGES = 3;       // descriptor ring / data stages (x1, x2, descriptor copy)
+    static constexpr int BWD_DESC = 2, BWD_STAGES = 2;       // data stage: prefix product, x1, x2, y1, y2, descriptor copy
+    // y staged as well: 68 KB per block (3 blocks per SM for Fp); otherwise y is prefetched into L2 one slot ahead and loaded
+    // directly where it is needed (44 KB, 4 blocks per SM). Fp2: staging y would leave one block per SM.
+    static constexpr bool STAGE_Y = sizeof(F) <= 48 && BA_STAGE_Y_FP;
+    static constexpr int FWD_STAGE_CH = 2 * FCH + 1, BWD_STAGE_CH = (STAGE_Y ? 5 : 3) * FCH + 1;
+    static constexpr int BWD_META = (STAGE_Y ? 5 : 3) * FCH;   // chunk of the descriptor copy inside a backward stage
+    static constexpr int FWD_CH = FWD_DESC + FWD_STAGES * FWD_STAGE_CH, BWD_CH = BWD_DESC + BWD_STAGES * BWD_STAGE_CH;
+    static constexpr int BYTES = (FWD_CH > BWD_CH ? FWD_CH : BWD_CH) * BA_THREADS * 16;
+};
+
+// Work distribution of one round. The kernel is PERSISTENT (`grid` = the co-resident blocks) and every WARP is an
+// independent worker: it takes batches of n slots per lane (32 n consecutive slots) from an atomic counter until the round
+// is exhausted — one inversion per lane per batch. In a round with several batches per warp the first batch of a warp is
+// shortened ((k % 3 + 1) / 3 of it, k = arrival order of its block on the SM), so the warps sharing a scheduler sit in
+// different phases: the forward pass is DRAM-bound (one multiplication per slot), the inversion leaves the multiplier
+// idle, the backward pass saturates it. Towards the end of the round the batches shrink to a third so that all warps
+// finish close together. Rounds with a single batch per warp run unstaggered.
+struct BaSched {
+    uint32_t *counter;      // slots per lane (in units of 32-slot rows) handed out so far; zeroed before the launch
+    uint32_t *sm_arrivals;  // per-SM block arrival count (never reset: only its value mod 3 matters)
+    uint32_t rows;          // ceil(nadds / 32)
+    uint32_t batch;         // rows per full batch
+    uint32_t stagger;       // 1: shortened first batches + shrinking tail
+};
+__device__ __forceinline__ uint32_t ba_smid() { uint32_t r; asm("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 
 template <class F, bool FIRST>
-static __global__ void __launch_bounds__(BA_THREADS) ba_round_kernel(const aff_t<F> *__restrict__ src, const uint32_t *__restrict__ sorted,
-                                                                     const uint2 *__restrict__ adesc, uint32_t nadds,
+static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_round_kernel(ba_io<F> io, const uint4 *__restrict__ adesc, uint32_t nadds,
                                                                      const uint2 *__restrict__ cdesc, uint32_t ncopies,
-                                                                     aff_t<F> *__restrict__ pts_out, aff_t<F> *__restrict__ bucket_sum,
-                                                                     uint4 *__restrict__ scratch, size_t scratch_stride, uint32_t B) {
-    // ---- copies (odd last elements, single-entry buckets): no arithmetic ----
+                                                                     uint4 *__restrict__ scratch, size_t scratch_stride, BaSched sched, uint32_t round) {
+    using SM = ba_smem<F>;
+    constexpr int FCH = SM::FCH;
+    constexpr uint32_t IDX = 0x7fffffffu;
+    extern __shared__ __align__(16) unsigned char ba_shared[];
+    __shared__ uint32_t sh_k;
+    if (threadIdx.x == 0) sh_k = sched.stagger ? atomicAdd(&sched.sm_arrivals[ba_smid()], 1u) % 3u : 2u;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, nwarps = gridDim.x * (BA_THREADS / 32), last = nadds ? nadds - 1 : 0;
+    const uint32_t sbase = ba_smem_addr(ba_shared);
+    bool first_batch = true;
+#pragma unroll 1
+    for (; nadds != 0;) {
+        uint32_t start = 0, n = 0;
+        if (lane == 0) {
+            n = sched.batch;
+            if (sched.stagger) {
+                if (first_batch) n = max(1u, (n * (sh_k + 1u)) / 3u);
+                const uint32_t seen = *(volatile uint32_t *)sched.counter;
+                const uint32_t left = seen < sched.rows ? sched.rows - seen : 0u;
+                if (left < nwarps * sched.batch) n = min(n, max((sched.batch + 2u) / 3u, left / nwarps));
+            }
+            start = atomicAdd(sched.counter, n);
+        }
+        first_batch = false;
+        start = __shfl_sync(0xffffffffu, start, 0);
+        n = __shfl_sync(0xffffffffu, n, 0);
+        if (start >= sched.rows) break;
+        const uint32_t niter = min(n, sched.rows - start);
+        const size_t tile0 = (size_t)start * 32 + lane;
+        auto slot_of = [&](uint32_t j) { return tile0 + (size_t)j * 32; };
+        auto desc_src = [&](uint32_t j) { const size_t s = slot_of(j); return adesc + (s < nadds ? s : last); };  // clamped: copies stay in bounds
+        BA_STAMP(0);
+        // ---- forward: denominators and their running product ----
+        F run;
+        f_set_one(run);
+        {
+            constexpr int ND = SM::FWD_DESC, NS = SM::FWD_STAGES, SCH = SM::FWD_STAGE_CH;
+            auto stage_ch = [&](uint32_t j) { return ND + (int)(j % NS) * SCH; };
+            auto issue_desc = [&](uint32_t j) { ba_cp16(sbase + ba_chunk((int)(j % ND)), desc_src(j)); };
+            auto issue_data = [&](uint32_t j) {   // needs the descriptor of slot j in the ring
+                const uint4 m = *reinterpret_cast<const uint4 *>(ba_shared + ba_chunk((int)(j % ND)));
+                const int c0 = stage_ch(j);
+                ba_cp_field(sbase, c0, ba_px<F, FIRST>(io, m.x & IDX));
+                ba_cp_field(sbase, c0 + FCH, ba_px<F, FIRST>(io, m.y & IDX));
+                *reinterpret_cast<uint4 *>(ba_shared + ba_chunk(c0 + 2 * FCH)) = m;
+            };
+#pragma unroll
+            for (uint32_t j = 0; j < (uint32_t)ND; j++) issue_desc(j);
+            ba_cp_commit();
+            ba_cp_wait<0>();
+            issue_data(0);
+            ba_cp_commit();
+            issue_data(1);
+            ba_cp_commit();
+#pragma unroll 1
+            for (uint32_t j = 0; j < niter; j++) {
+                ba_cp_wait<1>();            // everything committed before the previous iteration's group has landed
+                issue_data(j + 2);          // descriptor j + 2 arrived with the group of iteration j - 2
+                issue_desc(j + 4);
+                ba_cp_commit();
+                const size_t s = slot_of(j);
+                if (s < nadds) {
+                    const int c0 = stage_ch(j);
+                    F x1, d;
+                    ba_ld_stage(x1, ba_shared, c0);
+                    ba_ld_stage(d, ba_shared, c0 + FCH);
+                    const bool odd = f_is_zero(x1) || f_is_zero(d);
+                    f_sub(d, d, x1);
+                    int tag = BA_TAG_ADD;
+                    if (odd || f_is_zero(d)) {
+                        const uint4 m = *reinterpret_cast<const uint4 *>(ba_shared + ba_chunk(c0 + 2 * FCH));
+                        const ba_cold_t<F> c = ba_classify_cold(ba_px<F, FIRST>(io, m.x & IDX), ba_py<F, FIRST>(io, m.x & IDX), FIRST && (m.x >> 31),
+                                                                ba_px<F, FIRST>(io, m.y & IDX), ba_py<F, FIRST>(io, m.y & IDX), FIRST && (m.y >> 31));
+                        tag = c.tag;
+                        d = c.d;
+                    }
+                    if (tag <= BA_TAG_DBL) {
+                        ba_scratch_st(scratch, scratch_stride, s, run);
+                        f_mul(run, run, d);
+                    }
+                }
+            }
+            ba_cp_wait<0>();
+        }
+        BA_STAMP(1);
+        // ---- one inversion per lane (branch-free; every lane of the warp takes part) ----
+        F inv;
+        f_inv_warp(inv, run);
+        BA_STAMP(2);
+        // ---- backward: slopes and results ----
+        {
+            constexpr int ND = SM::BWD_DESC, NS = SM::BWD_STAGES, SCH = SM::BWD_STAGE_CH;
+            auto stage_ch = [&](uint32_t j) { return ND + (int)(j % NS) * SCH; };
+            auto issue_desc = [&](uint32_t j) { ba_cp16(sbase + ba_chunk((int)(j % ND)), desc_src(j)); };
+            auto issue_data = [&](uint32_t j) {
+                const uint4 m = *reinterpret_cast<const uint4 *>(ba_shared + ba_chunk((int)(j % ND)));
+                const int c0 = stage_ch(j);
+                const size_t s = min(slot_of(j), (size_t)last);
+#pragma unroll
+                for (int k = 0; k < FCH; k++) ba_cp16(sbase + ba_chunk(c0 + k), scratch + (size_t)k * scratch_stride + s);
+                ba_cp_field(sbase, c0 + FCH, ba_px<F, FIRST>(io, m.x & IDX));
+                ba_cp_field(sbase, c0 + 2 * FCH, ba_px<F, FIRST>(io, m.y & IDX));
+                if (SM::STAGE_Y) {
+                    ba_cp_field(sbase, c0 + 3 * FCH, ba_py<F, FIRST>(io, m.x & IDX));
+                    ba_cp_field(sbase, c0 + 4 * FCH, ba_py<F, FIRST>(io, m.y & IDX));
+                } else {
+                    ba_prefetch_l2(ba_py<F, FIRST>(io, m.x & IDX));
+                    ba_prefetch_l2(ba_py<F, FIRST>(io, m.y & IDX));
+                }
+                *reinterpret_cast<uint4 *>(ba_shared + ba_chunk(c0 + SM::BWD_META)) = m;
+            };
+            issue_desc(niter - 1);
+            if (niter >= 2) issue_desc(niter - 2);
+            ba_cp_commit();
+            ba_cp_wait<0>();
+            issue_data(niter - 1);
+            ba_cp_commit();
+#pragma unroll 1
+            for (uint32_t j = niter; j-- > 0;) {
+                ba_cp_wait<0>();            // operands of slot j and the descriptor of slot j - 1 have landed
+                if (j >= 1) issue_data(j - 1);
+                if (j >= 2) issue_desc(j - 2);
+                ba_cp_commit();
+                const size_t s = slot_of(j);
+                if (s >= nadds) continue;
+                const int c0 = stage_ch(j);
+                const uint4 m = *reinterpret_cast<const uint4 *>(ba_shared + ba_chunk(c0 + SM::BWD_META));
+                F lam, x1, x2, y1, t, d;
+                ba_ld_stage(t, ba_shared, c0);
+                f_mul(lam, inv, t);                // 1 / d when the slot is an addition or a doubling (unused otherwise)
+                ba_ld_stage(x1, ba_shared, c0 + FCH);
+                ba_ld_stage(x2, ba_shared, c0 + 2 * FCH);
+                f_sub(d, x2, x1);
+                int tag = BA_TAG_ADD;
+                if (f_is_zero(x1) || f_is_zero(x2) || f_is_zero(d)) {
+                    const ba_cold_t<F> c = ba_classify_cold(ba_px<F, FIRST>(io, m.x & IDX), ba_py<F, FIRST>(io, m.x & IDX), FIRST && (m.x >> 31),
+                                                            ba_px<F, FIRST>(io, m.y & IDX), ba_py<F, FIRST>(io, m.y & IDX), FIRST && (m.y >> 31));
+                    tag = c.tag;
+                    d = c.d;
+                }
+                if (tag <= BA_TAG_DBL) {
+                    if (j != 0) f_mul(inv, inv, d);
+                    if (SM::STAGE_Y) ba_ld_stage(y1, ba_shared, c0 + 3 * FCH);
+                    else f_ld(y1, ba_py<F, FIRST>(io, m.x & IDX));
+                    if (FIRST) f_cneg(y1, y1, (m.x >> 31) != 0);
+                    if (tag == BA_TAG_ADD) {
+                        if (SM::STAGE_Y) ba_ld_stage(t, ba_shared, c0 + 4 * FCH);
+                        else f_ld(t, ba_py<F, FIRST>(io, m.y & IDX));
+                        if (FIRST) f_cneg(t, t, (m.y >> 31) != 0);
+                        f_sub(t, t, y1);
+                    } else {
+                        f_sqr(t, x1);
+                        f_mul3(t, t);
+                    }
+                    f_mul(lam, lam, t);            // (y2 - y1) / (x2 - x1)   or   3 x1^2 / (2 y1)
+                    f_sqr(t, lam);
+                    f_sub(t, t, x1);
+                    f_sub(t, t, x2);               // x3 = lambda^2 - x1 - x2
+                    f_sub(x1, x1, t);
+                    f_mul(x1, x1, lam);
+                    f_sub(x1, x1, y1);             // y3 = lambda (x1 - x3) - y1
+                    ba_store_point(m.z, io, t, x1);
+                } else if (tag == BA_TAG_INF) {
+                    f_set_zero(t);
+                    ba_store_point(m.z, io, t, t);
+                } else {
+                    const bool cp = tag == BA_TAG_COPY_P;
+                    if (SM::STAGE_Y) ba_ld_stage(y1, ba_shared, c0 + (cp ? 3 : 4) * FCH);
+                    else f_ld(y1, ba_py<F, FIRST>(io, (cp ? m.x : m.y) & IDX));
+                    if (FIRST) f_cneg(y1, y1, ((cp ? m.x : m.y) >> 31) != 0);
+                    ba_store_point(m.z, io, cp ? x1 : x2, y1);
+                }
+            }
+            ba_cp_wait<0>();
+        }
+        BA_STAMP(3);
+    }
+    // ---- copies (odd last elements, single-entry buckets): no arithmetic; done last, in the
+    // shadow of the blocks that are still adding ----
     for (size_t ci = (size_t)blockIdx.x * BA_THREADS + threadIdx.x; ci < ncopies; ci += (size_t)gridDim.x * BA_THREADS) {
         const uint2 dsc = cdesc[ci];
-        ba_operands<F, FIRST> op(src, sorted, dsc.x, false);
         F x, y;
-        f_ld(x, &op.p->x);
-        f_ld(y, &op.p->y);
-        if (FIRST) f_cneg(y, y, op.sp);
-        ba_store_point(dsc.y, pts_out, bucket_sum, x, y);
-    }
-    const size_t tile0 = (size_t)blockIdx.x * B * BA_THREADS;
-    if (tile0 >= nadds) return;
-    // ---- forward: denominators and their running product ----
-    F run;
-    f_set_one(run);
-#pragma unroll 1
-    for (uint32_t j = 0; j < B; j++) {
-        const size_t s = tile0 + (size_t)j * BA_THREADS + threadIdx.x;
-        if (s < nadds) {
-            const uint2 dsc = adesc[s];
-            ba_operands<F, FIRST> op(src, sorted, dsc.x, true);
-            F x1, d;
-            f_ld(x1, &op.p->x);
-            f_ld(d, &op.q->x);
-            const bool odd = f_is_zero(x1) || f_is_zero(d);
-            f_sub(d, d, x1);
-            int tag = BA_TAG_ADD;
-            if (odd || f_is_zero(d)) tag = ba_classify_cold(op.p, op.sp, op.q, op.sq, d);
-            if (tag <= BA_TAG_DBL) {
-                ba_scratch_st(scratch, scratch_stride, s, run);
-                f_mul(run, run, d);
-            }
-        }
-    }
-    // ---- one inversion per lane (branch-free; every lane of the warp takes part) ----
-    F inv;
-    f_inv_warp(inv, run);
-    // ---- backward: slopes and results ----
-#pragma unroll 1
-    for (uint32_t j = B; j-- > 0;) {
-        const size_t s = tile0 + (size_t)j * BA_THREADS + threadIdx.x;
-        if (s >= nadds) continue;
-        const uint2 dsc = adesc[s];
-        ba_operands<F, FIRST> op(src, sorted, dsc.x, true);
-        F x1, x2, d;
-        f_ld(x1, &op.p->x);
-        f_ld(x2, &op.q->x);
-        const bool odd = f_is_zero(x1) || f_is_zero(x2);
-        f_sub(d, x2, x1);
-        int tag = BA_TAG_ADD;
-        if (odd || f_is_zero(d)) tag = ba_classify_cold(op.p, op.sp, op.q, op.sq, d);
-        F y1, lam, t;
-        if (tag <= BA_TAG_DBL) {
-            F pre;
-            ba_scratch_ld(pre, scratch, scratch_stride, s);
-            f_mul(lam, inv, pre);          // 1 / d
-            if (j != 0) f_mul(inv, inv, d);
-            f_ld(y1, &op.p->y);
-            if (FIRST) f_cneg(y1, y1, op.sp);
-            if (tag == BA_TAG_ADD) {
-                f_ld(t, &op.q->y);
-                if (FIRST) f_cneg(t, t, op.sq);
-                f_sub(t, t, y1);
-            } else {
-                f_sqr(t, x1);
-                f_mul3(t, t);
-            }
-            f_mul(lam, lam, t);            // (y2 - y1) / (x2 - x1)   or   3 x1^2 / (2 y1)
-            f_sqr(t, lam);
-            f_sub(t, t, x1);
-            f_sub(t, t, x2);               // x3 = lambda^2 - x1 - x2
-            f_sub(x1, x1, t);
-            f_mul(x1, x1, lam);
-            f_sub(x1, x1, y1);             // y3 = lambda (x1 - x3) - y1
-            ba_store_point(dsc.y, pts_out, bucket_sum, t, x1);
-        } else if (tag == BA_TAG_INF) {
-            f_set_zero(t);
-            ba_store_point(dsc.y, pts_out, bucket_sum, t, t);
-        } else {
-            const aff_t<F> *c = tag == BA_TAG_COPY_P ? op.p : op.q;
-            const bool sc = tag == BA_TAG_COPY_P ? op.sp : op.sq;
-            f_ld(t, &c->x);
-            f_ld(y1, &c->y);
-            if (FIRST) f_cneg(y1, y1, sc);
-            ba_store_point(dsc.y, pts_out, bucket_sum, t, y1);
-        }
+        f_ld(x, ba_px<F, FIRST>(io, dsc.x & IDX));
+        f_ld(y, ba_py<F, FIRST>(io, dsc.x & IDX));
+        if (FIRST) f_cneg(y, y, (dsc.x >> 31) != 0);
+        ba_store_point(dsc.y, io, x, y);
     }
 }
 

@@ -75,6 +75,12 @@ int measure_peaks(double *macs_per_s, double *fp_mul_per_s) {
     return MSMB200_OK;
 }
 
+#ifdef MSMB200_BA_TIMING
+extern "C" int msmb200_debug_ba_timing(unsigned long long *out) {
+    return cudaMemcpyFromSymbol(out, ba_dbg, sizeof(ba_dbg)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 static const GroupOps kOps = {
     sizeof(aff_t<fp_t>), sizeof(jac_t<fp_t>), sizeof(xyzz_t<fp_t>),
     msm_impl<fp_t, fpc_t>, generate_fix_points_impl<fpc_t>, table_build_impl<fpc_t>, sum_partials_impl<fpc_t>, tile_impl<fp_t, fpc_t>,

@@ -102,7 +102,7 @@ static int ba_accumulate(Ctx *c, const aff_t<F> *d_table, uint32_t *count, size_
     rd.aoff[Rs] = (uint32_t)a_total; rd.coff[Rs] = (uint32_t)c_total;
     const size_t ntiles = (nb + BA_TILE - 1) / BA_TILE, nbs = ntiles * BA_TILE, NR = 3 * (size_t)Rs;
     const size_t scratch_stride = ((size_t)T[0] + 31) & ~(size_t)31;
-    if (ensure(c, c->ba_tile_sums, ntiles * NR * 4) || ensure(c, c->ba_bases, NR * nbs * 4) || ensure(c, c->ba_adesc, (a_total + 1) * 8) ||
+    if (ensure(c, c->ba_tile_sums, ntiles * NR * 4) || ensure(c, c->ba_bases, NR * nbs * 4) || ensure(c, c->ba_adesc, (a_total + 1) * 16) ||
         ensure(c, c->ba_cdesc, (c_total + 1) * 8) || ensure(c, c->ba_heavy, (m / BA_HEAVY + 2) * 4) || ensure(c, c->pts_a, e_odd * sizeof(aff_t<F>)) ||
         ensure(c, c->pts_b, e_even * sizeof(aff_t<F>)) || ensure(c, c->ba_scratch, (scratch_stride + 1) * sizeof(F)) ||
         ensure(c, c->bucket_sum, nb * sizeof(aff_t<F>)) || ensure(c, c->sorted, (m + 2) * 4))
@@ -120,41 +120,63 @@ static int ba_accumulate(Ctx *c, const aff_t<F> *d_table, uint32_t *count, size_
     scatter_kernel<<<blocks_for(m, 256), 256, 0, st>>>((const uint32_t *)c->keys.p, (const uint32_t *)c->vals.p, m, bases + 2 * nbs,
                                                        (const uint32_t *)c->ranks.p, (uint32_t *)c->sorted.p);
     MSM_CUDA(c, cudaMemsetAsync(c->ba_heavy.p, 0, 4, st));
-    ba_emit_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, nb, bases, nbs, rd, (uint2 *)c->ba_adesc.p, (uint2 *)c->ba_cdesc.p, (uint32_t *)c->ba_heavy.p);
+    ba_emit_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(count, nb, bases, nbs, rd, (const uint32_t *)c->sorted.p, (uint4 *)c->ba_adesc.p, (uint2 *)c->ba_cdesc.p,
+                                                        (uint32_t *)c->ba_heavy.p, (uint4 *)c->bucket_sum.p, (uint32_t)(sizeof(aff_t<F>) / 16));
     if (T[3 * BA_RMAX] > BA_HEAVY)
-        ba_emit_heavy_kernel<<<(unsigned)std::min<size_t>(m / BA_HEAVY + 1, (size_t)c->sms * 2), 256, 0, st>>>(count, bases, nbs, rd, (uint2 *)c->ba_adesc.p,
-                                                                                                          (uint2 *)c->ba_cdesc.p, (const uint32_t *)c->ba_heavy.p);
+        ba_emit_heavy_kernel<<<(unsigned)std::min<size_t>(m / BA_HEAVY + 1, (size_t)c->sms * 2), 256, 0, st>>>(count, bases, nbs, rd, (const uint32_t *)c->sorted.p,
+                                                                                                          (uint4 *)c->ba_adesc.p, (uint2 *)c->ba_cdesc.p, (const uint32_t *)c->ba_heavy.p);
     c->launches += 8;
     MSM_CUDA(c, cudaEventRecord(c->ev[2], st));
     // ---- arithmetic rounds ----
     if (c->ba_resident <= 0) {
         int nbk = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, ba_round_kernel<F, false>, BA_THREADS, 0) != cudaSuccess || nbk < 1) nbk = 2;
+        MSM_CUDA(c, cudaFuncSetAttribute(ba_round_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba_smem<F>::BYTES));
+        MSM_CUDA(c, cudaFuncSetAttribute(ba_round_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba_smem<F>::BYTES));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, ba_round_kernel<F, false>, BA_THREADS, ba_smem<F>::BYTES) != cudaSuccess || nbk < 1) nbk = 2;
         c->ba_resident = nbk;
     }
-    const size_t wave = (size_t)c->sms * c->ba_resident;   // co-resident blocks
-    aff_t<F> *pts[2] = {(aff_t<F> *)c->pts_b.p, (aff_t<F> *)c->pts_a.p};  // round r writes pts[(r + 1) & 1]: round 0 -> pts_a (E_1)
+    const size_t wave = (size_t)c->sms * c->ba_resident;   // co-resident blocks: the round kernel is persistent
+    const size_t nwarps = wave * (BA_THREADS / 32);
+    if (ensure(c, c->ba_counters, (BA_RMAX + 1) * 4)) return MSMB200_ECUDA;
+    if (!c->ba_sm_arrivals.p) {
+        if (ensure(c, c->ba_sm_arrivals, 1024 * 4)) return MSMB200_ECUDA;
+        MSM_CUDA(c, cudaMemsetAsync(c->ba_sm_arrivals.p, 0, 1024 * 4, st));
+    }
+    MSM_CUDA(c, cudaMemsetAsync(c->ba_counters.p, 0, (BA_RMAX + 1) * 4, st));
+    // ping-pong point buffers between rounds, x[] and y[] separate: round r reads buffer r & 1 and writes buffer (r + 1) & 1
+    F *bx[2] = {(F *)c->pts_b.p, (F *)c->pts_a.p};
+    F *by[2] = {(F *)c->pts_b.p + e_even, (F *)c->pts_a.p + e_odd};
     for (uint32_t r = 0; r < Rs; r++) {
         const uint32_t A = T[3 * r], Cn = T[3 * r + 1];
-        // batch per lane: whole waves of equal blocks, at most ba_batch_max slots per lane
-        uint32_t B = 1;
-        if (A) {
-            const size_t per_wave = wave * BA_THREADS;
-            size_t w = 1;
-            while ((A + per_wave * w - 1) / (per_wave * w) > (size_t)c->ba_batch_max) w++;
-            B = (uint32_t)std::max<size_t>(1, (A + per_wave * w - 1) / (per_wave * w));
+        BaSched sched;
+        sched.rows = (A + 31) / 32;
+        const size_t share = (sched.rows + nwarps - 1) / nwarps;   // rows per warp if the round were split evenly
+        if (share > (size_t)c->ba_batch_max) {   // several batches per warp: equal full batches, staggered start, shrinking tail
+            const size_t nb_ = (share + c->ba_batch_max - 1) / c->ba_batch_max;
+            sched.batch = (uint32_t)((share + nb_ - 1) / nb_);
+            sched.stagger = c->ba_stagger ? 1u : 0u;
+        } else {
+            sched.batch = (uint32_t)std::max<size_t>(1, share);
+            sched.stagger = 0;
         }
-        if (c->ba_batch_fixed > 0) B = (uint32_t)c->ba_batch_fixed;
-        const size_t add_blocks = A ? ((size_t)A + (size_t)B * BA_THREADS - 1) / ((size_t)B * BA_THREADS) : 0;
-        const size_t copy_blocks = std::min<size_t>(blocks_for(Cn, BA_THREADS), wave);
-        const unsigned grid = (unsigned)std::max<size_t>(1, std::max(add_blocks, copy_blocks));
-        const uint2 *ad = (const uint2 *)c->ba_adesc.p + rd.aoff[r], *cd = (const uint2 *)c->ba_cdesc.p + rd.coff[r];
+        if (c->ba_batch_fixed > 0) sched.batch = (uint32_t)c->ba_batch_fixed;
+        sched.counter = (uint32_t *)c->ba_counters.p + r;
+        sched.sm_arrivals = (uint32_t *)c->ba_sm_arrivals.p;
+        const size_t batches = (sched.rows + sched.batch - 1) / sched.batch;
+        const size_t add_blocks = (batches + BA_THREADS / 32 - 1) / (BA_THREADS / 32);
+        const size_t copy_blocks = blocks_for(Cn, BA_THREADS);
+        const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(wave, std::max(add_blocks, copy_blocks)));
+        const uint4 *ad = (const uint4 *)c->ba_adesc.p + rd.aoff[r];
+        const uint2 *cd = (const uint2 *)c->ba_cdesc.p + rd.coff[r];
+        ba_io<F> io;
+        io.table = d_table;
+        io.in_x = bx[r & 1]; io.in_y = by[r & 1];
+        io.out_x = bx[(r + 1) & 1]; io.out_y = by[(r + 1) & 1];
+        io.bucket_sum = (aff_t<F> *)c->bucket_sum.p;
         if (r == 0)
-            ba_round_kernel<F, true><<<grid, BA_THREADS, 0, st>>>(d_table, (const uint32_t *)c->sorted.p, ad, A, cd, Cn, pts[1], (aff_t<F> *)c->bucket_sum.p,
-                                                                  (uint4 *)c->ba_scratch.p, scratch_stride, B);
+            ba_round_kernel<F, true><<<grid, BA_THREADS, ba_smem<F>::BYTES, st>>>(io, ad, A, cd, Cn, (uint4 *)c->ba_scratch.p, scratch_stride, sched, r);
         else
-            ba_round_kernel<F, false><<<grid, BA_THREADS, 0, st>>>(pts[r & 1], nullptr, ad, A, cd, Cn, pts[(r + 1) & 1], (aff_t<F> *)c->bucket_sum.p,
-                                                                   (uint4 *)c->ba_scratch.p, scratch_stride, B);
+            ba_round_kernel<F, false><<<grid, BA_THREADS, ba_smem<F>::BYTES, st>>>(io, ad, A, cd, Cn, (uint4 *)c->ba_scratch.p, scratch_stride, sched, r);
         c->launches += 1;
     }
     MSM_CUDA(c, cudaGetLastError());
