@@ -13,7 +13,7 @@ for spec in which:
     g = int(g)
     ctx = M.MsmContext(g, cfg); ctx.init_fix_point_list(); ctx.init_pippenger_CHES_q_over_5()
     sc = O.gen_scalars(1, ctx.n); cf, _ = O.closed_form(g, sc)
-    for accum, bmax, stag in ((2, 64, 1), (2, 110, 1), (2, 220, 1), (2, 110, 0)):
+    for accum, bmax, stag in ((1, 0, 0), (2, 64, 1), (2, 110, 1)):
         ctx.set_accumulator(accum)
         if bmax: ctx.set_tuning("ba_batch_max", bmax); ctx.set_tuning("ba_stagger", stag)
         for rep in range(3): r = ctx.msm(1, sc)
