@@ -137,6 +137,16 @@ int msmb200_msm_device(msmb200_ctx *ctx, int method, const void *scalars_dev, vo
 int msmb200_msm_partial_device(msmb200_ctx *ctx, int method, const void *scalars_dev, void *out_jacobian_dev);
 /* Sum `count` Jacobian partials (device memory, contiguous) and normalise: the G-1 dadds + blst_p1_to_affine. */
 int msmb200_sum_partials_device(msmb200_ctx *ctx, const void *partials_dev, int count, void *out_affine_host);
+/* Multi-GPU leg with ONE Horner pass and ONE inversion for the whole job: every rank stops after the bucket reduction and
+ * hands out its per-bit sums (layout[0] windows x layout[1] bit positions, blst_pNxyzz each: 192 B / 384 B) instead of a
+ * finalised point; after one all-gather, any rank sums entry by entry over the ranks, runs the Horner pass over the bit
+ * positions (bit k of window w weighs 2^(w * layout[2] + k)) and normalises. Replaces G x (xyzz_to_Jacobian + shift
+ * loop) + (G - 1) dadd + to_affine (src/multi_scalar.c:565-575). All ranks must use the same configuration.
+ * Precondition of the three *_device entry points: work is enqueued on the context's stream (msmb200_set_stream); the
+ * caller's collective must be ordered after it on the same stream or by an event. */
+int msmb200_msm_bits_layout(msmb200_ctx *ctx, int method, uint32_t layout[3]);
+int msmb200_msm_bits_device(msmb200_ctx *ctx, int method, const void *scalars_dev, void *out_bits_dev);
+int msmb200_combine_bits_device(msmb200_ctx *ctx, const void *gathered_dev, int world, const uint32_t layout[3], void *out_affine_host);
 /* blst_p1_affine_serialize / blst_p2_affine_serialize (src/e1.c:153-162, src/e2.c:194-203): 96 / 192 bytes. */
 int msmb200_affine_serialize(int group, const void *affine_host, unsigned char *out);
 
@@ -150,6 +160,11 @@ int msmb200_last_launches(msmb200_ctx *ctx);
 /* Live roofline denominators (register-only microbenchmarks): full 32x32+64-bit multiply-accumulates
  * per second with IMAD.WIDE.U32, and dependent-chain mul_mont_384 per second, on `device`. */
 int msmb200_measure_peaks(int device, double *imad_macs_per_s, double *fp_mul_per_s);
+/* Same run, all figures: out[0] = multiply-accumulates per second, out[1] = dependent mul_mont_384 per second,
+ * out[2] = multiply-accumulates per clock per SM (32 on B200: one IMAD.WIDE per 4 cycles per sub-partition, whatever the
+ * operands), out[3] = SM clock in MHz while the ~55 ms IMAD kernel ran. Both multiplicands of every IMAD.WIDE change
+ * each iteration (ptxas folds loop-invariant products into additions). */
+int msmb200_measure_peaks_ex(int device, double out[4]);
 
 /* ---- blst-named drop-ins (signatures of bindings/blst.h:238-240,:274-283,:299-304) ------------------
  * Exported under an msmb200_ prefix so the library can be linked next to libblst.a; build the reference

@@ -83,10 +83,14 @@ def lib():
         L.msmb200_msm_device.argtypes = [vp, ci, vp, vp]
         L.msmb200_msm_partial_device.argtypes = [vp, ci, vp, vp]
         L.msmb200_sum_partials_device.argtypes = [vp, vp, ci, vp]
+        L.msmb200_msm_bits_layout.argtypes = [vp, ci, vp]
+        L.msmb200_msm_bits_device.argtypes = [vp, ci, vp, vp]
+        L.msmb200_combine_bits_device.argtypes = [vp, vp, ci, vp, vp]
         L.msmb200_affine_serialize.argtypes = [ci, vp, vp]
         L.msmb200_last_timings.argtypes = [vp, vp]
         L.msmb200_last_launches.argtypes = [vp]
         L.msmb200_measure_peaks.argtypes = [ci, vp, vp]
+        L.msmb200_measure_peaks_ex.argtypes = [ci, vp]
         L.msmb200_test_field_op.argtypes = [ci, ci, ci, vp, vp, vp, sz]
         L.msmb200_test_point_op.argtypes = [ci, ci, ci, vp, vp, vp, vp, sz]
         L.msmb200_test_digits.argtypes = [vp, ci, vp, sz, vp, vp]
@@ -129,6 +133,15 @@ def measure_peaks(device=0):
     if rc:
         raise MsmB200Error("measure_peaks failed (%d)" % rc)
     return a.value, b.value
+
+
+def measure_peaks_ex(device=0):
+    """dict: IMAD.WIDE multiply-accumulates/s, dependent fp_mul/s, multiply-accumulates per clock per SM, SM clock (MHz)."""
+    out = (C.c_double * 4)()
+    rc = lib().msmb200_measure_peaks_ex(device, out)
+    if rc:
+        raise MsmB200Error("measure_peaks_ex failed (%d)" % rc)
+    return {"imad_wide_macs_per_s": out[0], "dependent_fp_mul_per_s": out[1], "macs_per_clk_per_sm": out[2], "sm_mhz_during_microbench": out[3]}
 
 
 def host_bucket_set(e, a):
@@ -289,6 +302,23 @@ class MsmContext:
     def sum_partials_device(self, partials_dev_ptr, count):
         out = np.zeros(AFF_BYTES[self.group], dtype=np.uint8)
         self._ck(lib().msmb200_sum_partials_device(self._h, C.c_void_p(partials_dev_ptr), count, _ptr(out)))
+        return out
+
+    def msm_bits_layout(self, method):
+        """(windows, bit positions per window, doublings between windows) of the per-bit sums, or None when this context
+        cannot hand them out (chunked reducer, bucket-range sharding, window layouts the digit splitting does not cover)."""
+        out = (C.c_uint32 * 3)()
+        if lib().msmb200_msm_bits_layout(self._h, method, out) != 0:
+            return None
+        return tuple(int(x) for x in out)
+
+    def msm_bits_device(self, method, scalars_dev_ptr, out_bits_dev_ptr):
+        self._ck(lib().msmb200_msm_bits_device(self._h, method, C.c_void_p(scalars_dev_ptr), C.c_void_p(out_bits_dev_ptr)))
+
+    def combine_bits_device(self, gathered_dev_ptr, world, layout):
+        out = np.zeros(AFF_BYTES[self.group], dtype=np.uint8)
+        lay = (C.c_uint32 * 3)(*layout)
+        self._ck(lib().msmb200_combine_bits_device(self._h, C.c_void_p(gathered_dev_ptr), world, lay, _ptr(out)))
         return out
 
     # -- introspection --

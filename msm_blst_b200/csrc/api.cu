@@ -579,6 +579,54 @@ int msmb200_msm_partial_device(msmb200_ctx *ctx, int method, const void *scalars
     MSM_CUDA(c, cudaSetDevice(c->device));
     return c->ops->msm(c, method, scalars_dev, out_jacobian_dev, false);
 }
+// layout of the per-bit sums of a method under this context: out[0] = windows, out[1] = bit positions per window,
+// out[2] = doublings between windows; builds the (cached) dense reduction plan when the method needs one
+int msmb200_msm_bits_layout(msmb200_ctx *ctx, int method, uint32_t out[3]) {
+    if (!ctx || !out) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    MSM_CUDA(c, cudaSetDevice(c->device));
+    if (c->reduce_mode == 1 || c->reduce_env == 1 || c->shard_world > 1) return ctx_fail(c, MSMB200_ESTATE, "per-bit partial sums need the digit-splitting reducer");
+    const ReducePlan *plan = nullptr;
+    uint32_t nw = 1, wbits = 0;
+    if (method == MSMB200_CHES || method == MSMB200_CHES_INTEGRAL) plan = &c->plan_ches;
+    else if (method == MSMB200_BGMW95) {
+        const size_t nbw = ((size_t)1 << (c->cfg.e_bgmw - 1)) + 1;
+        if (!c->plan_bgmw.valid || c->plan_bgmw.key_nbw != nbw || c->plan_bgmw_windows != 1) {
+            if (build_reduce_plan(c, c->plan_bgmw, nullptr, nbw, 1) != MSMB200_OK) return MSMB200_ECUDA;
+            c->plan_bgmw_windows = 1;
+        }
+        plan = &c->plan_bgmw;
+    } else if (method == MSMB200_PIPPENGER) {
+        nw = (uint32_t)c->pip_tiles; wbits = (uint32_t)c->pip_window;
+        const size_t nbw = ((size_t)1 << (c->pip_window - 1)) + 1;
+        if (!c->plan_pip.valid || c->plan_pip.key_nbw != nbw || c->plan_pip_windows != nw) {
+            if (build_reduce_plan(c, c->plan_pip, nullptr, nbw, nw) != MSMB200_OK) return MSMB200_ECUDA;
+            c->plan_pip_windows = nw;
+        }
+        plan = &c->plan_pip;
+    } else return ctx_fail(c, MSMB200_EINVAL, "unknown method");
+    if (!plan->valid || (nw > 1 && plan->nbits_w > wbits)) return ctx_fail(c, MSMB200_ESTATE, "per-bit partial sums unavailable for this layout");
+    out[0] = nw; out[1] = plan->nbits_w; out[2] = wbits;
+    return MSMB200_OK;
+}
+int msmb200_msm_bits_device(msmb200_ctx *ctx, int method, const void *scalars_dev, void *out_bits_dev) {
+    if (!ctx || !scalars_dev || !out_bits_dev) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    MSM_CUDA(c, cudaSetDevice(c->device));
+    c->bits_out = out_bits_dev;
+    int rc = c->ops->msm(c, method, scalars_dev, nullptr, false);
+    c->bits_out = nullptr;
+    return rc;
+}
+int msmb200_combine_bits_device(msmb200_ctx *ctx, const void *gathered_dev, int world, const uint32_t layout[3], void *out_affine_host) {
+    if (!ctx || !gathered_dev || world < 1 || !layout || !out_affine_host || layout[0] == 0 || layout[1] == 0) return MSMB200_EINVAL;
+    Ctx *c = C(ctx);
+    MSM_CUDA(c, cudaSetDevice(c->device));
+    int rc = c->ops->combine_bits(c, gathered_dev, world, layout[0], layout[1], layout[2]);
+    if (rc) return rc;
+    memcpy(out_affine_host, c->h_result, c->ops->aff_bytes);
+    return MSMB200_OK;
+}
 int msmb200_sum_partials_device(msmb200_ctx *ctx, const void *partials_dev, int count, void *out_affine_host) {
     if (!ctx || !partials_dev || count < 1 || !out_affine_host) return MSMB200_EINVAL;
     Ctx *c = C(ctx);
@@ -626,8 +674,17 @@ int msmb200_affine_serialize(int group, const void *affine_host, unsigned char *
 
 int msmb200_measure_peaks(int device, double *imad_macs_per_s, double *fp_mul_per_s) {
     if (!imad_macs_per_s || !fp_mul_per_s) return MSMB200_EINVAL;
+    double out[4];
+    int rc = msmb200_measure_peaks_ex(device, out);
+    if (rc) return rc;
+    *imad_macs_per_s = out[0];
+    *fp_mul_per_s = out[1];
+    return MSMB200_OK;
+}
+int msmb200_measure_peaks_ex(int device, double out[4]) {
+    if (!out) return MSMB200_EINVAL;
     if (cudaSetDevice(device) != cudaSuccess) return MSMB200_ECUDA;
-    return measure_peaks(imad_macs_per_s, fp_mul_per_s);
+    return measure_peaks(out);
 }
 
 // ---- parity-test hooks ------------------------------------------------------------------------------

@@ -85,6 +85,7 @@ struct Ctx {
     int shard_rank = 0, shard_world = 1;  // bucket-range sharding: this context owns 1/world of the reduction chunks
     int accum_mode = 0;  // 0 = default, 1 = XYZZ work items, 2 = batch-affine rounds
     void *h_result = nullptr;  // pinned staging for the result
+    void *bits_out = nullptr;  // device buffer for the per-bit XYZZ sums (msmb200_msm_bits_device) instead of a finalised point
     // host-to-host CHES calls: chunked upload on a second stream overlapped with the digit kernel (msmb200_msm)
     const void *h_scalars_pending = nullptr;
     cudaStream_t copy_stream = nullptr;
@@ -104,6 +105,8 @@ struct GroupOps {
     int (*generate_fix_points)(Ctx *, size_t first);
     int (*table_build)(Ctx *, int which);  // 0 CHES 3nh, 1 BGMW95
     int (*sum_partials)(Ctx *, const void *d_partials, int count);
+    // multi-GPU combine over all-gathered per-bit sums (world x nwindows x nbits_w XYZZ points): sum, Horner, to_affine
+    int (*combine_bits)(Ctx *, const void *d_gathered, int world, uint32_t nwindows, uint32_t nbits_w, uint32_t wbits);
     // generic tile: device arrays of bucket index (or value when v2i given) / sign / point index into d_table
     int (*tile)(Ctx *, const void *d_table, const int *d_bvals, const unsigned char *d_signs, const uint32_t *d_pidx,
                 size_t m, const int *d_v2i, const int *d_bucket_vals, size_t nbuckets, int d_max, const int *d_chunk_first, uint32_t vspan,
@@ -123,7 +126,7 @@ struct GroupOps {
     int (*table_io)(Ctx *, int dir, int serialized, const void *d_src, void *d_dst, size_t n, uint32_t *d_bad);
 };
 
-int measure_peaks(double *macs_per_s, double *fp_mul_per_s);
+int measure_peaks(double out[4]);
 const GroupOps *group_ops_g1();
 const GroupOps *group_ops_g2();
 

@@ -15,23 +15,28 @@ static int field_op_g(int field, int op, const void *a, const void *b, void *out
     return cudaGetLastError() == cudaSuccess ? 0 : MSMB200_ECUDA;
 }
 
-// Register-only microbenchmarks (same kernels as microbench.cu) that give bench.py its integer roofline
-// denominators live: 32x32+64 multiply-accumulates per second (IMAD.WIDE.U32, 8 independent accumulators per
-// thread, 32 warps per SM) and dependent-chain fp_mul throughput.
-static __global__ void peak_imad_wide_kernel(uint64_t *out, uint32_t a, uint32_t b, int iters) {
+// Register-only microbenchmarks (the kernels of microbench.cu) that give bench.py its integer roofline denominator live.
+// ptxas folds `acc += x * y` with loop-invariant x, y into one multiplication plus adds (the round-1 figure of
+// 61.5 MAC/clk/SM was that artefact), so both multiplicands here come from accumulators that change every iteration:
+// one IMAD.WIDE.U32 per multiply-accumulate, 8 independent chains per thread, 32 warps per SM. The kernel runs for tens
+// of milliseconds and reports its own cycle count, so the result is MACs per clock per SM plus the clock it ran at.
+static __global__ void peak_imad_wide_kernel(uint64_t *out, uint32_t a, int iters, long long *cyc) {
     uint64_t acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = threadIdx.x + k;
-    uint32_t x = a + threadIdx.x, y = b + blockIdx.x;
+    for (int k = 0; k < 8; k++) acc[k] = ((uint64_t)(threadIdx.x * 2654435761u + k) << 32) | (a * (k + 1) + threadIdx.x);
+    const long long t0 = clock64();
 #pragma unroll 1
     for (int i = 0; i < iters; i++) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(x), "r"(y));
+        for (int k = 0; k < 8; k++)
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"((uint32_t)acc[(k + 1) & 7]), "r"((uint32_t)(acc[(k + 3) & 7] >> 32)));
     }
+    const long long t1 = clock64();
     uint64_t s = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) s ^= acc[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 static __global__ void peak_fp_mul_kernel(fp_t *out, int iters) {
     int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -40,26 +45,34 @@ static __global__ void peak_fp_mul_kernel(fp_t *out, int iters) {
     fp_set_one(y);
     x.l[0] ^= tid; y.l[1] ^= tid * 2654435761u;
 #pragma unroll 1
-    for (int i = 0; i < iters; i++) { fp_mul_inline(x, x, y); fp_mul_inline(y, y, x); }
+    for (int i = 0; i < iters; i++) { fp_mul(x, x, y); fp_mul(y, y, x); }
     x.l[0] ^= y.l[0];
     out[tid] = x;
 }
-int measure_peaks(double *macs_per_s, double *fp_mul_per_s) {
+// out[0] = IMAD.WIDE multiply-accumulates per second, out[1] = dependent fp_mul per second (the out-of-line multiplier the
+// kernels call), out[2] = multiply-accumulates per clock per SM, out[3] = SM clock (MHz) during the IMAD kernel
+int measure_peaks(double out[4]) {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return MSMB200_ECUDA;
     void *buf = nullptr;
-    if (cudaMalloc(&buf, (size_t)sms * 8 * 256 * 48) != cudaSuccess) return MSMB200_ECUDA;
+    long long *d_cyc = nullptr;
+    if (cudaMalloc(&buf, (size_t)sms * 8 * 256 * 48) != cudaSuccess || cudaMalloc((void **)&d_cyc, (size_t)sms * 4 * sizeof(long long)) != cudaSuccess) return MSMB200_ECUDA;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const int it1 = 4096, it2 = 256;
-    float best1 = 1e30f, best2 = 1e30f, ms;
+    const int it1 = 300000, it2 = 256;   // ~55 ms of IMAD.WIDE at 32 MAC/clk/SM
+    float ms1 = 0, best2 = 1e30f, ms;
+    peak_imad_wide_kernel<<<sms * 4, 256>>>((uint64_t *)buf, 3u, 1000, d_cyc);   // warm-up
+    cudaEventRecord(e0);
+    peak_imad_wide_kernel<<<sms * 4, 256>>>((uint64_t *)buf, 5u, it1, d_cyc);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms1, e0, e1);
+    std::vector<long long> cyc((size_t)sms * 4);
+    cudaMemcpy(cyc.data(), d_cyc, cyc.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    double avg_cyc = 0;
+    for (long long v : cyc) avg_cyc += (double)v;
+    avg_cyc /= (double)cyc.size();
     for (int r = 0; r < 7; r++) {
-        cudaEventRecord(e0);
-        peak_imad_wide_kernel<<<sms * 4, 256>>>((uint64_t *)buf, 3u + r, 5u, it1);
-        cudaEventRecord(e1);
-        cudaEventSynchronize(e1);
-        cudaEventElapsedTime(&ms, e0, e1);
-        if (r >= 2 && ms < best1) best1 = ms;
         cudaEventRecord(e0);
         peak_fp_mul_kernel<<<sms * 8, 128>>>((fp_t *)buf, it2);
         cudaEventRecord(e1);
@@ -68,10 +81,12 @@ int measure_peaks(double *macs_per_s, double *fp_mul_per_s) {
         if (r >= 2 && ms < best2) best2 = ms;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(buf);
+    cudaFree(buf); cudaFree(d_cyc);
     if (cudaGetLastError() != cudaSuccess) return MSMB200_ECUDA;
-    *macs_per_s = 8.0 * it1 * (double)sms * 4 * 256 / (best1 * 1e-3);
-    *fp_mul_per_s = 2.0 * it2 * (double)sms * 8 * 128 / (best2 * 1e-3);
+    out[0] = 8.0 * it1 * (double)sms * 4 * 256 / (ms1 * 1e-3);
+    out[1] = 2.0 * it2 * (double)sms * 8 * 128 / (best2 * 1e-3);
+    out[2] = 8.0 * it1 * 4 * 256 / avg_cyc;      // 4 blocks of 256 threads per SM, all co-resident
+    out[3] = avg_cyc / (ms1 * 1e3);
     return MSMB200_OK;
 }
 
@@ -83,7 +98,7 @@ extern "C" int msmb200_debug_ba_timing(unsigned long long *out) {
 
 static const GroupOps kOps = {
     sizeof(aff_t<fp_t>), sizeof(jac_t<fp_t>), sizeof(xyzz_t<fp_t>),
-    msm_impl<fp_t, fpc_t>, generate_fix_points_impl<fpc_t>, table_build_impl<fpc_t>, sum_partials_impl<fpc_t>, tile_impl<fp_t, fpc_t>,
+    msm_impl<fp_t, fpc_t>, generate_fix_points_impl<fpc_t>, table_build_impl<fpc_t>, sum_partials_impl<fpc_t>, combine_bits_impl<fpc_t>, tile_impl<fp_t, fpc_t>,
     pippenger_impl<fp_t, fpc_t>, field_op_g, point_op_impl<fp_t, fpc_t>, digits_impl<fp_t>, resident_blocks_impl<fp_t, fpc_t>, wbits_precompute_impl<fpc_t>, table_io_impl<fpc_t>};
 const GroupOps *group_ops_g1() { return &kOps; }
 

@@ -11,9 +11,12 @@ namespace msmb200 {
 
 static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
-#ifndef MSMB200_DEFAULT_ACCUM
-#define MSMB200_DEFAULT_ACCUM 1
-#endif
+// Default accumulator (msmb200_set_accumulator(ctx, 0)): batch-affine rounds (2) once the problem is large enough that
+// its rounds are throughput-bound, XYZZ work items (1) below — measured crossover on B200 (profiles/r2_accum_sweep.log):
+// G1 between 2^19 and 2^20 points (6.8 M / 12.6 M entries), G2 around 2^16 points (1 M entries).
+template <class F> static inline int default_accumulator(size_t entries) {
+    return entries >= (sizeof(F) > 48 ? ((size_t)1 << 20) : ((size_t)1 << 23)) ? 2 : 1;
+}
 
 struct Layout {
     size_t m;            // number of (key, val) entries
@@ -212,19 +215,21 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     const size_t max_items = std::min(nb, m) + m / item_len + 1;
     const size_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
 
-    if (ensure(c, c->packed, nb * 8) || ensure(c, c->scanned, nb * 8) || ensure(c, c->tile_sums, (ntiles + 1) * 8) ||
-        ensure(c, c->seg_start, nb * 4) || ensure(c, c->item_start, nb * 4) || ensure(c, c->cursor, nb * 4) ||
-        ensure(c, c->sorted, (m + nb + 2) * 4) || ensure(c, c->maxcount, 16) || ensure(c, c->item_begin, max_items * 4) || ensure(c, c->item_cnt, max_items * 4) ||
-        ensure(c, c->order, max_items * 4) || ensure(c, c->len_hist, (item_len + 1) * 4) ||
-        ensure(c, c->len_start, (item_len + 1) * 4) || ensure(c, c->len_cursor, (item_len + 1) * 4) ||
-        ensure(c, c->partial, max_items * sizeof(xyzz_t<F>)) || ensure(c, c->heavy, (m / item_len + 2) * 4) || ensure(c, c->result, sizeof(jac_t<F>) + sizeof(aff_t<F>)))
+    int mode = c->accum_mode;
+    if (c->accum_env) mode = c->accum_env;
+    if (mode == 0) mode = default_accumulator<F>(m);
+    if (ensure(c, c->sorted, (m + 2) * 4) || ensure(c, c->result, sizeof(jac_t<F>) + sizeof(aff_t<F>))) return MSMB200_ECUDA;
+    if (mode != 2 &&   // workspace of the XYZZ work-item path only
+        (ensure(c, c->packed, nb * 8) || ensure(c, c->scanned, nb * 8) || ensure(c, c->tile_sums, (ntiles + 1) * 8) ||
+         ensure(c, c->seg_start, nb * 4) || ensure(c, c->item_start, nb * 4) || ensure(c, c->cursor, nb * 4) ||
+         ensure(c, c->maxcount, 16) || ensure(c, c->item_begin, max_items * 4) || ensure(c, c->item_cnt, max_items * 4) ||
+         ensure(c, c->order, max_items * 4) || ensure(c, c->len_hist, (item_len + 1) * 4) ||
+         ensure(c, c->len_start, (item_len + 1) * 4) || ensure(c, c->len_cursor, (item_len + 1) * 4) ||
+         ensure(c, c->partial, max_items * sizeof(xyzz_t<F>)) || ensure(c, c->heavy, (m / item_len + 2) * 4)))
         return MSMB200_ECUDA;
 
     uint32_t *count = (uint32_t *)c->count.p;
     // ---- sort by bucket ----
-    int mode = c->accum_mode;
-    if (c->accum_env) mode = c->accum_env;
-    if (mode == 0) mode = MSMB200_DEFAULT_ACCUM;
     const bool batch_affine = mode == 2;
     if (!batch_affine) {
         MSM_CUDA(c, cudaMemsetAsync(c->maxcount.p, 0, 4, st));
@@ -327,6 +332,12 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         coop(P.s2b, c->red_c.p, P.s2a.nlists, c->red_d.p);
         c->launches += 4;
         MSM_CUDA(c, cudaEventRecord(c->ev[4], st));
+        if (c->bits_out) {   // multi-GPU leg: hand out the per-bit sums; Horner and to_affine run once, after the all-gather
+            MSM_CUDA(c, cudaMemcpyAsync(c->bits_out, c->red_d.p, (size_t)nw * P.nbits_w * sizeof(xyzz_t<F>), cudaMemcpyDeviceToDevice, st));
+            MSM_CUDA(c, cudaEventRecord(c->ev[5], st));
+            MSM_CUDA(c, cudaGetLastError());
+            return MSMB200_OK;
+        }
         jac_t<F> *d_jac = d_out_jac ? (jac_t<F> *)d_out_jac : (jac_t<F> *)c->result.p;
         aff_t<F> *d_aff = (aff_t<F> *)((char *)c->result.p + sizeof(jac_t<F>));
         if (getenv("MSMB200_SERIAL_FINALIZE"))
@@ -342,6 +353,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         if (want_affine) MSM_CUDA(c, cudaStreamSynchronize(st));
         return MSMB200_OK;
     }
+    if (c->bits_out) return ctx_fail(c, MSMB200_ESTATE, "per-bit partial sums need the digit-splitting reducer");
     const uint32_t cpw = L.chunk_cnt ? L.chunk_cnt : L.nchunks;
     size_t nchunks = (size_t)cpw * L.nwindows;
     if (ensure(c, c->chunk_a, 2 * nchunks * sizeof(xyzz_t<F>)) || ensure(c, c->chunk_b, (2 * ((size_t)cpw / 4 + 2) * L.nwindows + 2) * sizeof(xyzz_t<F>)))
@@ -527,6 +539,22 @@ template <class F> static int sum_partials_impl(Ctx *c, const void *d_partials, 
         sum_partials_kernel<F><<<1, 32, 0, c->stream>>>((const jac_t<F> *)d_partials, count, d_aff);
     else
         sum_partials_coop_kernel<F><<<1, 32, 0, c->stream>>>((const jac_t<F> *)d_partials, count, (xyzz_t<F> *)c->red_c.p, d_aff);
+    MSM_CUDA(c, cudaMemcpyAsync(c->h_result, d_aff, sizeof(aff_t<F>), cudaMemcpyDeviceToHost, c->stream));
+    MSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MSMB200_OK;
+}
+
+// second half of the multi-GPU combine: per-entry sum over the ranks, one Horner pass, one inversion
+template <class F> static int combine_bits_impl(Ctx *c, const void *d_gathered, int world, uint32_t nwindows, uint32_t nbits_w, uint32_t wbits) {
+    using CT = typename coop_of<F>::type;
+    const uint32_t entries = nwindows * nbits_w;
+    if (ensure(c, c->result, sizeof(jac_t<F>) + sizeof(aff_t<F>)) || ensure(c, c->red_c, sizeof(xyzz_t<F>) + 64) ||
+        ensure(c, c->red_d, (size_t)entries * sizeof(xyzz_t<F>) + 64))
+        return MSMB200_ECUDA;
+    aff_t<F> *d_aff = (aff_t<F> *)((char *)c->result.p + sizeof(jac_t<F>));
+    sum_ranks_coop_kernel<F><<<blocks_for((size_t)entries * coop_group_lanes<CT>(), 128), 128, 0, c->stream>>>((const xyzz_t<F> *)d_gathered, entries, (uint32_t)world,
+                                                                                                         (xyzz_t<F> *)c->red_d.p);
+    bits_finalize_coop_kernel<F><<<1, 32, 0, c->stream>>>((const xyzz_t<F> *)c->red_d.p, nwindows, nbits_w, wbits, (xyzz_t<F> *)c->red_c.p, nullptr, d_aff);
     MSM_CUDA(c, cudaMemcpyAsync(c->h_result, d_aff, sizeof(aff_t<F>), cudaMemcpyDeviceToHost, c->stream));
     MSM_CUDA(c, cudaStreamSynchronize(c->stream));
     return MSMB200_OK;

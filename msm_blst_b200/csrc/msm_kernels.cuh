@@ -936,6 +936,29 @@ static __global__ void __launch_bounds__(32) sum_partials_coop_kernel(const jac_
     *out_aff = a;
 }
 
+// Multi-GPU combine, first half: entry e of the result = sum over the ranks of gathered[g * entries + e] (the per-bit
+// sums every rank contributes, all-gathered); one lane group per entry. The Horner pass + to_affine that follow run ONCE
+// (bits_finalize_coop_kernel) instead of once per rank plus a second inversion after the gather.
+template <class F>
+static __global__ void __launch_bounds__(128) sum_ranks_coop_kernel(const xyzz_t<F> *__restrict__ gathered, uint32_t entries, uint32_t world,
+                                                                    xyzz_t<F> *__restrict__ out) {
+    using C = typename coop_of<F>::type;
+    constexpr uint32_t GL = coop_group_lanes<C>();
+    const uint32_t gq = (blockIdx.x * blockDim.x + threadIdx.x) / GL;
+    const bool live = gq < entries;
+    C acc;
+    f_set_zero(acc);
+#pragma unroll 1
+    for (uint32_t g = 0; g < world; g++) {
+        C s;
+        f_set_zero(s);
+        if (live) dq_load(s, gathered + (size_t)g * entries + gq);
+        if (g == 0) acc = s;
+        else dq_add(acc, s);
+    }
+    if (live) dq_store(out + gq, acc);
+}
+
 // ------------------------------------------------------------------------------------------------
 // precomputation tables and fixed points
 // ------------------------------------------------------------------------------------------------

@@ -55,12 +55,41 @@ def all_gather_scalars(shard, full):
     return full
 
 
-def msm_sharded(ctx, method, scalars_dev, partial_buf):
+def _bind_stream(ctx, tensor):
+    """All three legs (MSM kernels, the collective, the combine) are ordered on ONE stream: the context is bound to
+    torch's current stream of the tensor's device, which is also the stream NCCL orders its collective after."""
+    if tensor.is_cuda:
+        cur = torch.cuda.current_stream(tensor.device).cuda_stream
+        if getattr(ctx, "_bound_stream", None) != cur:
+            ctx.set_stream(cur)
+            ctx._bound_stream = cur
+
+
+def msm_sharded(ctx, method, scalars_dev, partial_buf=None):
     """Run this rank's shard on its GPU and combine: returns the affine result (numpy uint8) on every rank.
 
-    ctx: msm_blst_b200.MsmContext for this rank's shard; scalars_dev: torch uint8 CUDA tensor (n_shard x 32);
-    partial_buf: torch uint8 CUDA tensor of JAC_BYTES.
+    ctx: msm_blst_b200.MsmContext for this rank's shard (same configuration on every rank); scalars_dev: torch uint8 CUDA
+    tensor (n_shard x 32). Every rank stops after its bucket reduction and contributes its per-bit XYZZ sums (a few KB);
+    after ONE all-gather the entries are summed over the ranks and a single Horner pass + inversion finishes the job
+    (msmb200_msm_bits_device / msmb200_combine_bits_device). Contexts that cannot hand out per-bit sums fall back to
+    Jacobian partials (partial_buf: torch uint8 CUDA tensor of JAC_BYTES, allocated on demand).
+    Stream ordering: the context is bound to torch's current stream, so the MSM, the NCCL collective and the combine are
+    ordered without host synchronisation.
     """
+    from .api import JAC_BYTES, XYZZ_BYTES
+    _bind_stream(ctx, scalars_dev)
+    cache = ctx.__dict__.setdefault("_bits_cache", {})
+    if method not in cache:
+        lay = ctx.msm_bits_layout(method)
+        buf = torch.zeros(lay[0] * lay[1] * XYZZ_BYTES[ctx.group], dtype=torch.uint8, device=scalars_dev.device) if lay else None
+        cache[method] = (lay, buf)
+    lay, buf = cache[method]
+    if lay is not None:
+        ctx.msm_bits_device(method, scalars_dev.data_ptr(), buf.data_ptr())
+        gathered = all_gather_partials(buf)
+        return ctx.combine_bits_device(gathered.data_ptr(), gathered.shape[0], lay)
+    if partial_buf is None:
+        partial_buf = torch.zeros(JAC_BYTES[ctx.group], dtype=torch.uint8, device=scalars_dev.device)
     ctx.msm_partial_device(method, scalars_dev.data_ptr(), partial_buf.data_ptr())
     gathered = all_gather_partials(partial_buf)
     return ctx.sum_partials_device(gathered.data_ptr(), gathered.shape[0])

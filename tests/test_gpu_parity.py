@@ -825,6 +825,54 @@ def test_table_save_load_round_trip_and_serialized_bytes(M, group, tmp_path):
     c4.close()
 
 
+@pytest.mark.parametrize("group", [1, 2])
+def test_sharded_per_bit_sums_combine_to_full_result(M, group):
+    """The multi-GPU leg that runs ONE Horner pass and ONE inversion for the whole job: G = 3 shards as contexts on one
+    GPU, each stops after its bucket reduction and writes its per-bit XYZZ sums (msmb200_msm_bits_device); the gathered
+    sums are added entry by entry over the ranks, shifted and normalised once (msmb200_combine_bits_device). All four
+    methods (blst-Pippenger has 32 windows at n = 2^10), result == closed form; also through distributed.msm_sharded's
+    single-rank path."""
+    import torch
+
+    from msm_blst_b200 import distributed as D
+
+    n, world = 1000, 3
+    sc = O.gen_scalars(44, n)
+    exp, _ = O.closed_form(group, sc)
+    ctxs = []
+    for r in range(world):
+        lo, hi = D.shard_range(n, r, world)
+        ctx = M.MsmContext(group, "10", npoints=hi - lo, first=lo)
+        ctx.init_fix_point_list()
+        ctx.init_pippenger_CHES_q_over_5()
+        ctx.init_pippenger_BGMW95()
+        ctxs.append((ctx, torch.from_numpy(sc[lo:hi].view(np.uint8).copy()).cuda()))
+    for method in (1, 2, 3, 4):
+        lays = {ctx.msm_bits_layout(method) for ctx, _ in ctxs}
+        if method == 4 and lays != {None} and len(lays) > 1:
+            continue  # shards of different sizes choose different Pippenger windows: nothing to combine entry by entry
+        if lays == {None}:
+            continue
+        assert len(lays) == 1
+        lay = lays.pop()
+        per = lay[0] * lay[1] * O.XYZZ_BYTES[group] if hasattr(O, "XYZZ_BYTES") else lay[0] * lay[1] * (192 if group == 1 else 384)
+        gathered = torch.zeros((world, per), dtype=torch.uint8, device="cuda")
+        for r, (ctx, d_sc) in enumerate(ctxs):
+            ctx.msm_bits_device(method, d_sc.data_ptr(), gathered[r].data_ptr())
+        torch.cuda.synchronize()
+        got = ctxs[1][0].combine_bits_device(gathered.data_ptr(), world, lay)
+        assert (got == exp).all(), (method, lay)
+    # one rank: msm_sharded without a process group is not possible; the combine with world = 1 must equal msm_device
+    ctx, d_sc = ctxs[0]
+    lay = ctx.msm_bits_layout(1)
+    buf = torch.zeros(lay[0] * lay[1] * (192 if group == 1 else 384), dtype=torch.uint8, device="cuda")
+    ctx.msm_bits_device(1, d_sc.data_ptr(), buf.data_ptr())
+    torch.cuda.synchronize()
+    assert (ctx.combine_bits_device(buf.data_ptr(), 1, lay) == ctx.msm_device(1, d_sc.data_ptr())).all()
+    for ctx, _ in ctxs:
+        ctx.close()
+
+
 # ---------------------------------------------------------------- bucket-range sharding (tables replicated)
 @pytest.mark.parametrize("group", [1, 2])
 def test_bucket_range_shards_sum_to_full_result(M, group):
