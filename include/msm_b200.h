@@ -55,6 +55,11 @@ typedef struct {
  * makefile:15-18): "8".."21", "16_beta", "17_beta", "20_beta". */
 int msmb200_config_lookup(const char *name, msmb200_config *out);
 
+/* Parameter search (main_bucket_set_construction.cpp: construct_bucket_set :39-72, check_bucket_set_validity :74-113,
+ * max_gap_in_bucket_set :115-122) for ANY even radix q (not only the 17 shipped configurations) and leading term a:
+ * out[0] = valid (both checks), out[1] = |B|, out[2] = largest gap d, out[3] = leading-digit check (every top digit
+ * 0..a+1 is m*b), out[4] = first digit in [0, q] that is neither m*b nor q - m*b (-1 when all are covered). Host only. */
+int msmb200_host_bucket_set_check(long q, long a, long out[5]);
 /* Host-only parameter construction (no CUDA needed), the run-time form of construct_bucket_set
  * (auxiliaryfunc.h:257-288) and of the DIGIT_CONVERSION_HASH_TABLE fill (main_p1.cpp:140-152).
  * msmb200_host_bucket_set returns |B| (fills out[] when cap >= |B|). msmb200_host_digit_table writes q+1
@@ -117,7 +122,8 @@ int msmb200_download(msmb200_ctx *ctx, int which, size_t first, size_t count, vo
 /* Table persistence (the reference rebuilds its tables on every run, main_p1.cpp:615-617). which: 0 fixed
  * points, 1 CHES 3nh table, 2 BGMW95 table. format 0: the in-memory blst_pN_affine layout (Montgomery limbs); format 1:
  * blst_pN_affine_serialize of every entry (src/e1.c:153-162, src/e2.c:194-203: 96 / 192 bytes big-endian, infinity
- * 0x40), readable by blst_pN_deserialize. A 72-byte header records group, configuration, npoints and entry count;
+ * 0x40), readable by blst_pN_deserialize. An 80-byte header records group, configuration, npoints, entry count and a checksum of the
+ * fixed points the array belongs to (a table is only accepted next to the points it was built from);
  * load checks it against the context and validates EVERY entry on the device like blst_pN_deserialize does
  * (flags, coordinates < p, y^2 = x^3 + B) before marking the array usable. */
 int msmb200_table_save(msmb200_ctx *ctx, int which, const char *path, int format);
@@ -184,6 +190,21 @@ void msmb200_blst_p2_tile_pippenger_d_CHES(void *ret_jacobian, const void *const
                                            const int scalars[], const unsigned char booth_signs[], void *buckets,
                                            int bucket_set_ascend[], int bucket_value_to_its_index[],
                                            size_t bucket_set_size, int d_max);
+/* blst_p{1,2}_construct_nh_scalars_nh_points (bindings/blst.h:274-276, src/multi_scalar.c:748-775), literally: in place on
+ * the caller's host arrays (standard q-ary digits in, bucket values out; booth signs out; host pointers into the caller's
+ * 3nh table out; the alpha carry crosses slots exactly like the reference's sequential pass), computed on the device. */
+void msmb200_blst_p1_construct_nh_scalars_nh_points(int nh_scalars[], unsigned char booth_signs[], void *nh_points_ptr[], size_t npoints,
+                                                    void *precomputation_points_list_3nh, const void *digit_conversion_hash_table);
+void msmb200_blst_p2_construct_nh_scalars_nh_points(int nh_scalars[], unsigned char booth_signs[], void *nh_points_ptr[], size_t npoints,
+                                                    void *precomputation_points_list_3nh, const void *digit_conversion_hash_table);
+/* Optional: mirror the caller's host precomputation table (PRECOMPUTATION_POINTS_LIST_3nh / _BGMW95, `entries` affine
+ * points) in HBM now. The tile shims translate points[k] to (points[k] - host_table) / sizeof(affine) on the device and
+ * gather from the mirror, so a call uploads 13 bytes per entry instead of n*h points. Without this call the shims learn
+ * the table from the pointer range of the first call (the drivers only ever pass pointers into one table). A table that
+ * is rebuilt in place is noticed (probe of sampled entries) and uploaded again. */
+int msmb200_blst_register_table(int group, const void *host_table, size_t entries);
+/* Wall time in ms (host to host, lock to return) of the group's most recent blst-named shim call. */
+double msmb200_blst_last_call_ms(int group);
 void msmb200_blst_p1_tile_pippenger_BGMW95(void *ret_jacobian, const void *const points[], size_t npoints,
                                            const int scalars[], const unsigned char booth_signs[], void *buckets,
                                            size_t q_exponent);
@@ -191,12 +212,12 @@ void msmb200_blst_p2_tile_pippenger_BGMW95(void *ret_jacobian, const void *const
                                            const int scalars[], const unsigned char booth_signs[], void *buckets,
                                            size_t q_exponent);
 
-/* blst_p1s_add / blst_p2s_add (bindings/blst.h:224,:364; src/bulk_addition.c:145-164): Jacobian sum of npoints affine
- * points (pointer-array convention as above). SURVEY §8f rank 1: the library's other consumer of bulk addition. */
 /* blst_p1s_to_affine / blst_p2s_to_affine (bindings/blst.h:222,:362; src/multi_scalar.c:17-59): batched normalisation of
  * npoints Jacobian points (pointer-array convention as above) into dst[npoints]; SURVEY §8f rank 3. */
 void msmb200_blst_p1s_to_affine(void *dst_affine, const void *const points[], size_t npoints);
 void msmb200_blst_p2s_to_affine(void *dst_affine, const void *const points[], size_t npoints);
+/* blst_p1s_add / blst_p2s_add (bindings/blst.h:224,:364; src/bulk_addition.c:145-164): Jacobian sum of npoints affine
+ * points (pointer-array convention as above). SURVEY §8f rank 1: the library's other consumer of bulk addition. */
 void msmb200_blst_p1s_add(void *ret_jacobian, const void *const points[], size_t npoints);
 void msmb200_blst_p2s_add(void *ret_jacobian, const void *const points[], size_t npoints);
 

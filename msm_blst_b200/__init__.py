@@ -13,6 +13,7 @@ from .api import (  # noqa: F401
     build_library,
     config_lookup,
     host_bucket_set,
+    host_bucket_set_check,
     host_digit_table,
     lib,
     measure_peaks,
@@ -21,6 +22,6 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "LIB_PATH", "MsmB200Error", "MsmContext", "affine_serialize", "build_library", "config_lookup", "host_bucket_set", "host_digit_table", "lib", "measure_peaks",
+    "LIB_PATH", "MsmB200Error", "MsmContext", "affine_serialize", "build_library", "config_lookup", "host_bucket_set", "host_bucket_set_check", "host_digit_table", "lib", "measure_peaks",
     "test_field_op", "test_point_op",
 ]

@@ -58,6 +58,7 @@ def lib():
         L.msmb200_host_bucket_set.argtypes = [ci, ci, vp, C.c_long]
         L.msmb200_host_bucket_set.restype = C.c_long
         L.msmb200_host_digit_table.argtypes = [ci, ci, vp]
+        L.msmb200_host_bucket_set_check.argtypes = [C.c_long, C.c_long, vp]
         L.msmb200_pippenger_window_size.argtypes = [sz]
         L.msmb200_pippenger_window_size.restype = sz
         L.msmb200_ctx_create.argtypes = [C.POINTER(vp), ci, C.POINTER(_Config), sz, ci]
@@ -111,6 +112,12 @@ def lib():
             f = getattr(L, "msmb200_blst_p%d_tile_pippenger_BGMW95" % g)
             f.argtypes = [vp, vp, sz, vp, vp, vp, sz]
             f.restype = None
+            f = getattr(L, "msmb200_blst_p%d_construct_nh_scalars_nh_points" % g)
+            f.argtypes = [vp, vp, vp, sz, vp, vp]
+            f.restype = None
+        L.msmb200_blst_register_table.argtypes = [ci, vp, sz]
+        L.msmb200_blst_last_call_ms.argtypes = [ci]
+        L.msmb200_blst_last_call_ms.restype = C.c_double
         _lib = L
     return _lib
 
@@ -151,6 +158,14 @@ def host_bucket_set(e, a):
     out = np.empty(n, dtype=np.int32)
     lib().msmb200_host_bucket_set(e, a, _ptr(out), n)
     return out
+
+
+def host_bucket_set_check(q, a):
+    """check_bucket_set_validity + max_gap of the reference's parameter tool for radix q and leading term a (host only)."""
+    out = (C.c_long * 5)()
+    if lib().msmb200_host_bucket_set_check(int(q), int(a), out) != 0:
+        raise MsmB200Error("host_bucket_set_check(%d, %d): arguments out of range" % (q, a))
+    return {"valid": bool(out[0]), "size": int(out[1]), "max_gap": int(out[2]), "leading_ok": bool(out[3]), "first_uncovered": int(out[4])}
 
 
 def host_digit_table(e, a):

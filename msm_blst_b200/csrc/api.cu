@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include "engine.hpp"
 
@@ -204,7 +205,8 @@ static int ctx_init_common(Ctx *c, int group, int device) {
     return MSMB200_OK;
 }
 
-static void ctx_free(Ctx *c) {
+// releases everything the context owns; the memory of *c itself belongs to whoever allocated it
+static void ctx_release(Ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
@@ -223,7 +225,7 @@ static void ctx_free(Ctx *c) {
     for (auto &e : c->ev_chunk) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
-    delete c;
+    c->stream = nullptr;
 }
 
 // lazily created context used by the context-free blst-named shims
@@ -231,6 +233,20 @@ static std::mutex g_shim_mu;
 // the blst functions are re-entrant; the shims share one lazily created context per group, so calls of the
 // same group are serialised (the GPU runs one MSM at a time anyway)
 static std::mutex g_shim_call_mu[3];
+// a shim call = the lock plus a wall-clock stamp (msmb200_blst_last_call_ms: what one drop-in call cost, host to host)
+static double g_shim_last_ms[3] = {0, 0, 0};
+struct ShimCall {
+    std::lock_guard<std::mutex> lock;
+    int group;
+    std::chrono::steady_clock::time_point t0;
+    explicit ShimCall(int g) : lock(g_shim_call_mu[g]), group(g), t0(std::chrono::steady_clock::now()) {}
+    double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+    void lap(const char *what) const {   // MSMB200_SHIM_TRACE=1: where a drop-in call spends its time (stderr)
+        static const bool on = getenv("MSMB200_SHIM_TRACE") != nullptr;
+        if (on) fprintf(stderr, "msm_b200 shim[g%d] %-28s %9.3f ms\n", group, what, ms());
+    }
+    ~ShimCall() { g_shim_last_ms[group] = ms(); lap("return"); }
+};
 static Ctx *g_shim[3] = {nullptr, nullptr, nullptr};
 static Ctx *shim_ctx(int group) {
     std::lock_guard<std::mutex> lk(g_shim_mu);
@@ -265,6 +281,14 @@ long msmb200_host_bucket_set(int e, int a, int *out, long cap) {
     std::vector<int> B = build_bucket_set(1 << e, a);
     if (out && cap >= (long)B.size()) memcpy(out, B.data(), B.size() * sizeof(int));
     return (long)B.size();
+}
+int msmb200_host_bucket_set_check(long q, long a, long out[5]) {
+    if (q < 16 || q > ((long)1 << 26) || (q & 1) || a < 0 || a + 1 > q / 2 || !out) return MSMB200_EINVAL;
+    const std::vector<int> B = build_bucket_set((int)q, (int)a);
+    const BucketSetCheck r = check_bucket_set(B, q, a);
+    out[0] = r.leading_ok && r.cover_ok ? 1 : 0;
+    out[1] = r.size; out[2] = r.max_gap; out[3] = r.leading_ok ? 1 : 0; out[4] = r.first_uncovered;
+    return MSMB200_OK;
 }
 int msmb200_host_digit_table(int e, int a, int *out_triples) {
     if (e < 4 || e > 24 || a < 0 || !out_triples) return MSMB200_EINVAL;
@@ -322,13 +346,14 @@ int msmb200_ctx_create(msmb200_ctx **out, int group, const msmb200_config *cfg, 
     c->cfg = *cfg;
     c->n = npoints;
     int rc = ctx_init_common(c, group, device);
-    if (rc) { g_create_err = c->err; ctx_free(c); return rc; }
+    if (rc) { g_create_err = c->err; ctx_release(c); delete x; return rc; }
     // CHES parameters
     c->q = 1 << cfg->e;
     c->bucket_set = build_bucket_set(c->q, cfg->a);
     if (cfg->bsize && (size_t)cfg->bsize != c->bucket_set.size()) {
         g_create_err = "bucket set size differs from configured B_SIZE";
-        ctx_free(c);
+        ctx_release(c);
+        delete x;
         return MSMB200_EINVAL;
     }
     int gap = 0;
@@ -336,12 +361,12 @@ int msmb200_ctx_create(msmb200_ctx **out, int group, const msmb200_config *cfg, 
     std::vector<uint32_t> dtab = build_digit_table(c->q, c->bucket_set);
     bool covered = gap <= cfg->d;
     for (uint32_t v : dtab) covered = covered && v != DT_INVALID;
-    if (!covered) { g_create_err = "bucket set does not cover all digits / max gap exceeds d"; ctx_free(c); return MSMB200_EINVAL; }
+    if (!covered) { g_create_err = "bucket set does not cover all digits / max gap exceeds d"; ctx_release(c); delete x; return MSMB200_EINVAL; }
     std::vector<int> v2i(c->q / 2 + 1, 0);
     for (size_t i = 0; i < c->bucket_set.size(); i++) v2i[c->bucket_set[i]] = (int)i;
     c->pip_window = (int)pippenger_window_size(npoints);
     c->pip_tiles = 255 / c->pip_window + 1;
-#define CREATE_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { g_create_err = std::string(#call) + ": " + cudaGetErrorString(e__); ctx_free(c); return MSMB200_ECUDA; } } while (0)
+#define CREATE_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { g_create_err = std::string(#call) + ": " + cudaGetErrorString(e__); ctx_release(c); delete x; return MSMB200_ECUDA; } } while (0)
     CREATE_CUDA(cudaMalloc(&c->d_bucket_vals, c->bucket_set.size() * sizeof(int)));
     CREATE_CUDA(cudaMalloc(&c->d_v2i, v2i.size() * sizeof(int)));
     CREATE_CUDA(cudaMalloc(&c->d_dtab, dtab.size() * sizeof(uint32_t)));
@@ -356,16 +381,15 @@ int msmb200_ctx_create(msmb200_ctx **out, int group, const msmb200_config *cfg, 
     CREATE_CUDA(cudaMemcpy(c->d_dtab, dtab.data(), dtab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 #undef CREATE_CUDA
     rc = build_reduce_plan(c, c->plan_ches, c->bucket_set.data(), c->bucket_set.size(), 1);
-    if (rc) { g_create_err = c->err; ctx_free(c); return rc; }
+    if (rc) { g_create_err = c->err; ctx_release(c); delete x; return rc; }
     *out = x;
     return MSMB200_OK;
 }
 
 void msmb200_ctx_destroy(msmb200_ctx *ctx) {
     if (!ctx) return;
-    Ctx *c = new Ctx(std::move(ctx->c));  // ctx_free deletes a heap Ctx
+    ctx_release(&ctx->c);
     delete ctx;
-    ctx_free(c);
 }
 
 int msmb200_set_stream(msmb200_ctx *ctx, void *cuda_stream) {
@@ -455,7 +479,19 @@ struct TableFileHeader {
     uint32_t version, group, format, which;
     int32_t cfg[8];      // n_exp, e, h, a, d, bsize, e_bgmw, h_bgmw
     uint64_t npoints, entries;
+    uint64_t points_digest;  // version 2: checksum of the fixed points the array belongs to (a table of OTHER points must not load)
 };
+// checksum of the context's fixed points (device computation, 8 bytes read back)
+static int points_digest(Ctx *c, uint64_t *out) {
+    unsigned long long *d = nullptr;
+    MSM_CUDA(c, cudaMalloc((void **)&d, 8));
+    cudaMemsetAsync(d, 0, 8, c->stream);
+    int rc = c->ops->checksum(c, c->d_points, c->n * c->ops->aff_bytes, d);
+    if (!rc && (cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess))
+        rc = ctx_fail(c, MSMB200_ECUDA, "points digest");
+    cudaFree(d);
+    return rc;
+}
 static int table_slot(Ctx *c, int which, void ***slot, size_t *entries, bool **have) {
     if (which == 0) { *slot = &c->d_points; *entries = c->n; *have = &c->have_points; }
     else if (which == 1) { *slot = &c->d_table_ches; *entries = c->n * (size_t)c->cfg.h * 3; *have = &c->have_ches; }
@@ -475,7 +511,8 @@ int msmb200_table_save(msmb200_ctx *ctx, int which, const char *path, int format
     if (!f) return ctx_fail(c, MSMB200_EINVAL, std::string("cannot open ") + path);
     TableFileHeader h{};
     memcpy(h.magic, "MSMB200T", 8);
-    h.version = 1; h.group = (uint32_t)c->group; h.format = (uint32_t)format; h.which = (uint32_t)which;
+    h.version = 2; h.group = (uint32_t)c->group; h.format = (uint32_t)format; h.which = (uint32_t)which;
+    if (c->have_points && points_digest(c, &h.points_digest)) { fclose(f); return MSMB200_ECUDA; }
     const int32_t cf[8] = {c->cfg.n_exp, c->cfg.e, c->cfg.h, c->cfg.a, c->cfg.d, c->cfg.bsize, c->cfg.e_bgmw, c->cfg.h_bgmw};
     memcpy(h.cfg, cf, sizeof(cf));
     h.npoints = c->n; h.entries = entries;
@@ -508,20 +545,30 @@ int msmb200_table_load(msmb200_ctx *ctx, int which, const char *path) {
     FILE *f = fopen(path, "rb");
     if (!f) return ctx_fail(c, MSMB200_EINVAL, std::string("cannot open ") + path);
     TableFileHeader h{};
-    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "MSMB200T", 8) != 0 || h.version != 1 || h.format > 1) { fclose(f); return ctx_fail(c, MSMB200_EINVAL, "not a table file"); }
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "MSMB200T", 8) != 0 || h.version != 2 || h.format > 1) { fclose(f); return ctx_fail(c, MSMB200_EINVAL, "not a table file (or written by an older version)"); }
     // the table depends on the group, the points (n) and the radix / length of its method; the points on group and n only
     bool match = h.group == (uint32_t)c->group && h.which == (uint32_t)which && h.npoints == c->n && h.entries == entries;
     if (which == 1) match = match && h.cfg[1] == c->cfg.e && h.cfg[2] == c->cfg.h;
     if (which == 2) match = match && h.cfg[6] == c->cfg.e_bgmw && h.cfg[7] == c->cfg.h_bgmw;
     if (!match) { fclose(f); return ctx_fail(c, MSMB200_EINVAL, "table file was written for another group / size / configuration"); }
+    if (which != 0) {  // a precomputation table belongs to the points it was built from: they must be here and be the same
+        uint64_t dig = 0;
+        if (!c->have_points) { fclose(f); return ctx_fail(c, MSMB200_ESTATE, "load or generate the fixed points before their table"); }
+        if (points_digest(c, &dig)) { fclose(f); return MSMB200_ECUDA; }
+        if (dig != h.points_digest) { fclose(f); return ctx_fail(c, MSMB200_EINVAL, "table file was built from other fixed points"); }
+    }
     const size_t ab = c->ops->aff_bytes, chunk = (size_t)1 << 20;
-    if (!*slot) MSM_CUDA(c, cudaMalloc(slot, entries * ab));
+    if (!*slot && cudaMalloc(slot, entries * ab) != cudaSuccess) { fclose(f); *slot = nullptr; return ctx_fail(c, MSMB200_ECUDA, "cudaMalloc"); }
     *have = false;
     if (which == 0) c->have_ches = c->have_bgmw = false;
     std::vector<unsigned char> host(std::min(entries, chunk) * ab);
     void *d_stage = nullptr;
     uint32_t *d_bad = nullptr, bad = 0;
-    if (cudaMalloc(&d_stage, std::min(entries, chunk) * ab) != cudaSuccess || cudaMalloc((void **)&d_bad, 4) != cudaSuccess) { fclose(f); return ctx_fail(c, MSMB200_ECUDA, "cudaMalloc"); }
+    if (cudaMalloc(&d_stage, std::min(entries, chunk) * ab) != cudaSuccess || cudaMalloc((void **)&d_bad, 4) != cudaSuccess) {
+        if (d_stage) cudaFree(d_stage);
+        fclose(f);
+        return ctx_fail(c, MSMB200_ECUDA, "cudaMalloc");
+    }
     cudaMemsetAsync(d_bad, 0, 4, c->stream);
     bool ok = true;
     for (size_t off = 0; ok && off < entries; off += chunk) {
@@ -770,37 +817,15 @@ static void shim_fail(Ctx *c, const char *what) {
     fprintf(stderr, "msm_b200: %s failed: %s\n", what, c->err.c_str());
     abort();  // void blst signature: no error channel, and never a CPU fallback
 }
-static void shim_mult_pippenger(int group, void *ret, const void *const points[], size_t npoints, const unsigned char *const scalars[],
-                                size_t nbits, int tile_bit0 = -1, int tile_window = 0) {
-    // tile_bit0 >= 0: blst_pNs_tile_pippenger — one window of tile_window bits starting at bit tile_bit0 (not shifted)
-    Ctx *c = shim_ctx(group);
-    std::lock_guard<std::mutex> call_lock(g_shim_call_mu[group]);
-    size_t ab = c->ops->aff_bytes, jb = c->ops->jac_bytes;
-    if (npoints == 0 || nbits == 0 || nbits > 255) { memset(ret, 0, jb); return; }
-    if (tile_bit0 >= 0 && (tile_window < 1 || tile_window > 24 || (size_t)tile_bit0 >= nbits)) { memset(ret, 0, jb); return; }
-    cudaSetDevice(c->device);
-    std::vector<unsigned char> hp, hs;
-    gather_ptr_array(hp, points, npoints, ab, ab);
-    gather_ptr_array(hs, (const void *const *)scalars, npoints, (nbits + 7) / 8, 32);
-    void *dp = nullptr, *ds = nullptr, *dj = nullptr;
-    if (cudaMalloc(&dp, hp.size()) != cudaSuccess || cudaMalloc(&ds, hs.size()) != cudaSuccess || cudaMalloc(&dj, jb) != cudaSuccess) {
-        c->err = "cudaMalloc"; shim_fail(c, "blst_pNs_mult_pippenger");
-    }
-    cudaMemcpyAsync(dp, hp.data(), hp.size(), cudaMemcpyHostToDevice, c->stream);
-    cudaMemcpyAsync(ds, hs.data(), hs.size(), cudaMemcpyHostToDevice, c->stream);
-    if (c->ops->pippenger(c, dp, npoints, ds, (int)nbits, dj, false, 0, tile_bit0, tile_window)) shim_fail(c, "blst_pNs_mult_pippenger");
-    cudaMemcpyAsync(ret, dj, jb, cudaMemcpyDeviceToHost, c->stream);
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pNs_mult_pippenger"); }
-    cudaFree(dp); cudaFree(ds); cudaFree(dj);
-}
 // blst_pNs_mult_wbits_precompute / blst_pNs_mult_wbits (bindings/blst.h:228-236,:368-376; src/multi_scalar.c:81-261): the
 // library's fixed-window table MSM. The table lives in HOST memory in the reference's layout (the caller owns it), so
 // the shim uploads it per call; it is gathered by the same accumulate kernel as the CHES / BGMW95 tables.
 static void shim_wbits_precompute(int group, void *table, size_t wbits, const void *const points[], size_t npoints) {
     Ctx *c = shim_ctx(group);
-    std::lock_guard<std::mutex> call_lock(g_shim_call_mu[group]);
+    ShimCall call_lock(group);
     size_t ab = c->ops->aff_bytes;
-    if (npoints == 0 || wbits == 0 || wbits > 16) return;
+    if (npoints == 0 || wbits == 0) return;
+    if (wbits > 16) { c->err = "wbits > 16 is not supported"; shim_fail(c, "blst_pNs_mult_wbits_precompute"); }
     cudaSetDevice(c->device);
     std::vector<unsigned char> hp;
     gather_ptr_array(hp, points, npoints, ab, ab);
@@ -815,11 +840,12 @@ static void shim_wbits_precompute(int group, void *table, size_t wbits, const vo
 }
 static void shim_mult_wbits(int group, void *ret, const void *table, size_t wbits, size_t npoints, const unsigned char *const scalars[], size_t nbits) {
     Ctx *c = shim_ctx(group);
-    std::lock_guard<std::mutex> call_lock(g_shim_call_mu[group]);
+    ShimCall call_lock(group);
     size_t ab = c->ops->aff_bytes, jb = c->ops->jac_bytes;
-    if (npoints == 0 || nbits == 0 || nbits > 255 || wbits == 0 || wbits > 16 || ((double)npoints * (double)((size_t)1 << (wbits - 1))) >= 2147483648.0) {
-        memset(ret, 0, jb);
-        return;
+    if (npoints == 0 || nbits == 0 || wbits == 0) { memset(ret, 0, jb); return; }
+    if (nbits > 256 || wbits > 16 || ((double)npoints * (double)((size_t)1 << (wbits - 1))) >= 2147483648.0) {
+        c->err = "nbits > 256, wbits > 16 or npoints * 2^(wbits-1) >= 2^31 is not supported";
+        shim_fail(c, "blst_pNs_mult_wbits");
     }
     cudaSetDevice(c->device);
     std::vector<unsigned char> hs;
@@ -836,56 +862,282 @@ static void shim_mult_wbits(int group, void *ret, const void *table, size_t wbit
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pNs_mult_wbits"); }
     cudaFree(dt); cudaFree(ds); cudaFree(dj);
 }
+// State of the literal shims that work on the CALLER's host arrays (one per group, guarded by g_shim_call_mu):
+//  * the host precomputation table the drivers' pointer arrays point into (main_p1.cpp:219,:224,:330,:345,:365), mirrored in
+//    HBM: registered explicitly (msmb200_blst_register_table) or learned from the pointer range of the first call, so
+//    that later calls translate pointers to indices on the device instead of gathering and uploading n*h points;
+//  * the bucket set / index map / reduction plan of the last CHES tile call and the dense plan of the last BGMW95 call;
+//  * the {m, b, alpha} digit table of blst_pN_construct_nh_scalars_nh_points; grow-only device staging buffers.
+// A host table mirrored in HBM. The allocation keeps MIRROR_SLACK entries of room on both sides: a table learned from the
+// pointers of one call starts at the lowest pointer seen, and a later call may reach an entry or two further out.
+constexpr size_t MIRROR_SLACK = 8;
+struct Mirror {
+    const unsigned char *base = nullptr; size_t entries = 0; unsigned char *d = nullptr; uint64_t probe = 0, used = 0;
+    unsigned char *d_alloc = nullptr; size_t cap = 0, before = 0;   // allocation, its capacity in entries, entries of room before `d`
+};
+struct ShimState {
+    Mirror mir[4]; uint64_t tick = 0;   // CHES table, BGMW95 table, the fixed points, one spare; least recently used is replaced
+    const int *bs_key = nullptr; size_t bs_n = 0; int bs_last = -1, bs_mid = -1, bs_d = 0;
+    DevBuf d_bs, d_v2i, d_cf; uint32_t vspan = 0, nchunks = 0; ReducePlan plan; size_t dense_n = 0; ReducePlan dense_plan; uint32_t dense_vspan = 0, dense_chunks = 0;
+    const void *tri_key = nullptr; size_t tri_n = 0; DevBuf d_tri;
+    DevBuf sc, sg, pi, ptrs, jac, aux, pts, in;
+    unsigned char *h_stage = nullptr; size_t h_stage_bytes = 0;   // pinned staging for gathered host data
+};
+static ShimState g_state[3];
+static uint64_t probe_table(const unsigned char *base, size_t entries, size_t ab) {  // a few entries, to notice a table rebuilt in place
+    uint64_t h = 0;
+    for (size_t k : {(size_t)0, entries / 3, entries / 2, entries - 1}) {
+        uint64_t w[4];
+        memcpy(w, base + k * ab + ab - 32, 32);
+        h = (h ^ w[0] ^ (w[3] << 1)) * 0x9E3779B97F4A7C15ull + w[1] + w[2];
+    }
+    return h;
+}
+// mirror [base, base + entries): grow a mirror that overlaps the range and has the room, refresh the one with this base,
+// else take the least recently used slot
+static Mirror *shim_upload_table(Ctx *c, ShimState &S, const unsigned char *base, size_t entries) {
+    const size_t ab = c->ops->aff_bytes;
+    const unsigned char *end = base + entries * ab;
+    for (Mirror &k : S.mir) {
+        if (!k.base || !k.d || (k.base == base && k.entries == entries)) continue;
+        const unsigned char *kend = k.base + k.entries * ab;
+        if (end <= k.base || base >= kend || (size_t)(k.base > base ? k.base - base : base - k.base) % ab) continue;
+        const size_t add_lo = base < k.base ? (size_t)(k.base - base) / ab : 0, add_hi = end > kend ? (size_t)(end - kend) / ab : 0;
+        if (add_lo > k.before || k.before + k.entries + add_hi > k.cap) continue;
+        if (probe_table(k.base, k.entries, ab) != k.probe) continue;   // stale: let the caller replace it as a whole
+        if (add_lo && cudaMemcpyAsync(k.d - add_lo * ab, base, add_lo * ab, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return nullptr;
+        if (add_hi && cudaMemcpyAsync(k.d + k.entries * ab, kend, add_hi * ab, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return nullptr;
+        k.d -= add_lo * ab; k.before -= add_lo; k.base -= add_lo * ab; k.entries += add_lo + add_hi;
+        k.probe = probe_table(k.base, k.entries, ab); k.used = ++S.tick;
+        return &k;
+    }
+    Mirror *m = nullptr;
+    for (Mirror &k : S.mir) if (k.base == base) m = &k;
+    if (!m) { m = &S.mir[0]; for (Mirror &k : S.mir) if (k.used < m->used) m = &k; }
+    if (m->d_alloc && m->cap < entries + 2 * MIRROR_SLACK) { cudaFree(m->d_alloc); m->d_alloc = nullptr; }
+    m->base = nullptr; m->d = nullptr;
+    if (!m->d_alloc) {
+        if (cudaMalloc((void **)&m->d_alloc, (entries + 2 * MIRROR_SLACK) * ab) != cudaSuccess) { m->d_alloc = nullptr; cudaGetLastError(); return nullptr; }
+        m->cap = entries + 2 * MIRROR_SLACK;
+    }
+    m->before = MIRROR_SLACK;
+    m->d = m->d_alloc + MIRROR_SLACK * ab;
+    if (cudaMemcpyAsync(m->d, base, entries * ab, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { m->d = nullptr; return nullptr; }
+    m->base = base; m->entries = entries; m->probe = probe_table(base, entries, ab); m->used = ++S.tick;
+    return m;
+}
+static bool pinned_stage(ShimState &S, size_t bytes) {
+    if (S.h_stage_bytes >= bytes) return true;
+    if (S.h_stage) cudaFreeHost(S.h_stage);
+    S.h_stage = nullptr; S.h_stage_bytes = 0;
+    if (cudaMallocHost((void **)&S.h_stage, bytes + bytes / 4) != cudaSuccess) { cudaGetLastError(); return false; }
+    S.h_stage_bytes = bytes + bytes / 4;
+    return true;
+}
+// points[0 .. npoints) are host pointers (already uploaded to S.ptrs). Returns the device array the indices written to S.pi
+// refer to: a mirrored host table when every pointer lies inside one (registered, or learned from the range the pointers
+// span - the drivers only ever pass pointers into one table per call), else the points gathered on the host and uploaded.
+static const void *shim_resolve_points(Ctx *c, ShimState &S, const void *const points[], size_t npoints, const char *what) {
+    const size_t ab = c->ops->aff_bytes;
+    ShimAux x;
+    x.ptrs = (unsigned long long *)S.ptrs.p; x.m = npoints; x.entry_bytes = (unsigned)ab; x.pidx = (uint32_t *)S.pi.p; x.bad = (uint32_t *)S.aux.p;
+    const unsigned char *p0 = (const unsigned char *)points[0], *p1 = (const unsigned char *)points[npoints - 1];
+    for (int attempt = 0; attempt < 2; attempt++) {
+        for (Mirror &m : S.mir) {
+            if (!m.base || !m.d || p0 < m.base || p0 >= m.base + m.entries * ab || p1 < m.base || p1 >= m.base + m.entries * ab) continue;
+            if (probe_table(m.base, m.entries, ab) != m.probe) {   // rebuilt in place: upload again
+                if (!shim_upload_table(c, S, m.base, m.entries)) break;
+            }
+            uint32_t bad = 0;
+            cudaMemsetAsync(S.aux.p, 0, 4, c->stream);
+            x.base = (unsigned long long)(uintptr_t)m.base; x.entries = m.entries;
+            if (c->ops->shim_aux(c, 1, x)) shim_fail(c, what);
+            cudaMemcpyAsync(&bad, S.aux.p, 4, cudaMemcpyDeviceToHost, c->stream);
+            if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, what); }
+            if (bad == 0) { m.used = ++S.tick; return m.d; }
+        }
+        if (attempt == 0) {  // learn the table from the range the pointers span
+            unsigned long long mm[2] = {~0ull, 0ull};
+            cudaMemcpyAsync((char *)S.aux.p + 16, mm, 16, cudaMemcpyHostToDevice, c->stream);
+            ShimAux y = x;
+            y.pidx = (uint32_t *)((char *)S.aux.p + 16);
+            if (c->ops->shim_aux(c, 3, y)) shim_fail(c, what);
+            cudaMemcpyAsync(mm, (char *)S.aux.p + 16, 16, cudaMemcpyDeviceToHost, c->stream);
+            if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, what); }
+            const unsigned long long span = mm[1] - mm[0];
+            // a sparse set of pointers (far fewer points than the range holds) is not a table worth mirroring
+            if (span % ab != 0 || span / ab + 1 > ((size_t)1 << 31) || span / ab + 1 > 64 * npoints + 4096 ||
+                !shim_upload_table(c, S, (const unsigned char *)(uintptr_t)mm[0], span / ab + 1))
+                break;
+        }
+    }
+    // pointers into unrelated buffers: the general (slow) path of the blst convention
+    if (!pinned_stage(S, npoints * (ab + 4)) || ensure(c, S.pts, npoints * ab)) { c->err = "staging memory"; shim_fail(c, what); }
+    uint32_t *pidx = (uint32_t *)(S.h_stage + npoints * ab);
+    for (size_t k = 0; k < npoints; k++) { memcpy(S.h_stage + k * ab, points[k], ab); pidx[k] = (uint32_t)k; }
+    cudaMemcpyAsync(S.pts.p, S.h_stage, npoints * ab, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(S.pi.p, pidx, npoints * 4, cudaMemcpyHostToDevice, c->stream);
+    cudaStreamSynchronize(c->stream);  // the staging buffer is reused by the next call
+    return S.pts.p;
+}
+static void shim_mult_pippenger(int group, void *ret, const void *const points[], size_t npoints, const unsigned char *const scalars[],
+                                size_t nbits, int tile_bit0 = -1, int tile_window = 0) {
+    // tile_bit0 >= 0: blst_pNs_tile_pippenger — one window of tile_window bits starting at bit tile_bit0 (not shifted)
+    Ctx *c = shim_ctx(group);
+    ShimCall call_lock(group);
+    ShimState &S = g_state[group];
+    const char *what = "blst_pNs_mult_pippenger";
+    size_t ab = c->ops->aff_bytes, jb = c->ops->jac_bytes;
+    if (npoints == 0 || nbits == 0) { memset(ret, 0, jb); return; }
+    if (nbits > 256) { c->err = "nbits > 256 is not supported"; shim_fail(c, what); }
+    if (tile_bit0 >= 0 && (tile_window < 1 || tile_window > 24 || (size_t)tile_bit0 >= nbits)) { memset(ret, 0, jb); return; }
+    cudaSetDevice(c->device);
+    const size_t sb = (nbits + 7) / 8;
+    if (!pinned_stage(S, npoints * (ab + 32)) || ensure(c, S.sc, npoints * 32) || ensure(c, S.jac, jb)) { c->err = "staging memory"; shim_fail(c, what); }
+    // scalars: blst's convention (an array of pointers, or one pointer followed by NULL for a contiguous array) -> 32-byte rows
+    unsigned char *hs = S.h_stage;
+    {
+        const unsigned char *cur = nullptr;
+        size_t pi = 0;
+        for (size_t i = 0; i < npoints; i++) {
+            if (i == 0) cur = scalars[pi++];
+            else if (scalars[pi] != nullptr) cur = scalars[pi++];
+            else cur += sb;
+            memcpy(hs + i * 32, cur, sb);
+            if (sb < 32) memset(hs + i * 32 + sb, 0, 32 - sb);
+        }
+    }
+    cudaMemcpyAsync(S.sc.p, hs, npoints * 32, cudaMemcpyHostToDevice, c->stream);
+    // points: one contiguous host array (the fixed-base case: FIX_POINTS_LIST, main_p1.cpp:416-418) is mirrored in HBM once
+    // and found again by address; anything else is gathered and uploaded per call
+    bool contiguous = true;
+    const unsigned char *p0 = (const unsigned char *)points[0];
+    if (npoints > 1 && points[1] != nullptr)
+        for (size_t k = 1; k < npoints && contiguous; k++) contiguous = (const unsigned char *)points[k] == p0 + k * ab;
+    const void *d_points = nullptr;
+    if (contiguous && npoints >= 64) {
+        for (Mirror &m : S.mir)
+            if (m.base && m.d && p0 >= m.base && p0 + npoints * ab <= m.base + m.entries * ab && (size_t)(p0 - m.base) % ab == 0 &&
+                probe_table(m.base, m.entries, ab) == m.probe) {
+                m.used = ++S.tick;
+                d_points = m.d + (p0 - m.base);
+            }
+        if (!d_points) {
+            Mirror *m = shim_upload_table(c, S, p0, npoints);
+            if (m) d_points = m->d + (p0 - m->base);
+        }
+    }
+    if (!d_points) {
+        unsigned char *hp = S.h_stage + npoints * 32;
+        if (ensure(c, S.pts, npoints * ab)) shim_fail(c, what);
+        const unsigned char *cur = nullptr;
+        size_t pi = 0;
+        for (size_t i = 0; i < npoints; i++) {
+            if (i == 0) cur = (const unsigned char *)points[pi++];
+            else if (points[pi] != nullptr) cur = (const unsigned char *)points[pi++];
+            else cur += ab;
+            memcpy(hp + i * ab, cur, ab);
+        }
+        cudaMemcpyAsync(S.pts.p, hp, npoints * ab, cudaMemcpyHostToDevice, c->stream);
+        d_points = S.pts.p;
+    }
+    call_lock.lap("pippenger: inputs staged");
+    if (c->ops->pippenger(c, d_points, npoints, S.sc.p, (int)nbits, S.jac.p, false, 0, tile_bit0, tile_window)) shim_fail(c, what);
+    call_lock.lap("pippenger: enqueued");
+    cudaMemcpyAsync(ret, S.jac.p, jb, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, what); }
+}
 static void shim_tile(int group, void *ret, const void *const points[], size_t npoints, const int scalars[], const unsigned char signs[],
                       const int *bucket_set_ascend, const int *v2i, size_t nbuckets, int d_max) {
     Ctx *c = shim_ctx(group);
-    std::lock_guard<std::mutex> call_lock(g_shim_call_mu[group]);
-    size_t ab = c->ops->aff_bytes, jb = c->ops->jac_bytes;
+    ShimCall call_lock(group);
+    ShimState &S = g_state[group];
+    const size_t jb = c->ops->jac_bytes;
+    if (npoints == 0) { memset(ret, 0, jb); return; }
     cudaSetDevice(c->device);
-    // points[k] are arbitrary host pointers (main_p1.cpp:219,:224 point into the 3nh table): gather them
-    std::vector<unsigned char> hp(npoints * ab);
-    std::vector<uint32_t> pidx(npoints);
-    for (size_t k = 0; k < npoints; k++) { memcpy(&hp[k * ab], points[k], ab); pidx[k] = (uint32_t)k; }
-    size_t v2i_len = bucket_set_ascend ? (size_t)bucket_set_ascend[nbuckets - 1] + 1 : 0;
-    void *dp = nullptr, *dsc = nullptr, *dsg = nullptr, *dpi = nullptr, *dj = nullptr, *dbs = nullptr, *dv = nullptr, *dcf = nullptr;
-    uint32_t vspan, nchunks;
-    std::vector<int> cf;
+    const char *what = "blst_pN_tile_pippenger";
+    if (ensure(c, S.sc, npoints * 4) || ensure(c, S.sg, npoints) || ensure(c, S.pi, npoints * 4) || ensure(c, S.ptrs, npoints * 8) || ensure(c, S.jac, jb) ||
+        ensure(c, S.aux, 64))
+        shim_fail(c, what);
+    cudaMemcpyAsync(S.sc.p, scalars, npoints * 4, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(S.sg.p, signs, npoints, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(S.ptrs.p, points, npoints * 8, cudaMemcpyHostToDevice, c->stream);
+    const void *d_table = shim_resolve_points(c, S, points, npoints, what);
+    call_lock.lap("tile: inputs on the device");
+    // ---- bucket set, index map and reduction plan: cached across calls ----
+    const ReducePlan *plan = nullptr;
+    const int *d_bs = nullptr, *d_v = nullptr, *d_cf = nullptr;
+    uint32_t vspan = 0, nchunks = 0;
     if (bucket_set_ascend) {
-        vspan = pick_vspan_host((size_t)bucket_set_ascend[nbuckets - 1], 1);
-        cf = build_chunk_first(bucket_set_ascend, nbuckets, vspan, &nchunks);
+        const int last = bucket_set_ascend[nbuckets - 1], mid = bucket_set_ascend[nbuckets / 2];
+        if (!(S.bs_key == bucket_set_ascend && S.bs_n == nbuckets && S.bs_last == last && S.bs_mid == mid && S.plan.valid)) {
+            S.vspan = pick_vspan_host((size_t)last, 1);
+            std::vector<int> cf = build_chunk_first(bucket_set_ascend, nbuckets, S.vspan, &S.nchunks);
+            if (ensure(c, S.d_bs, nbuckets * 4) || ensure(c, S.d_v2i, ((size_t)last + 1) * 4) || ensure(c, S.d_cf, cf.size() * 4)) shim_fail(c, what);
+            cudaMemcpyAsync(S.d_bs.p, bucket_set_ascend, nbuckets * 4, cudaMemcpyHostToDevice, c->stream);
+            cudaMemcpyAsync(S.d_v2i.p, v2i, ((size_t)last + 1) * 4, cudaMemcpyHostToDevice, c->stream);
+            cudaMemcpyAsync(S.d_cf.p, cf.data(), cf.size() * 4, cudaMemcpyHostToDevice, c->stream);
+            cudaStreamSynchronize(c->stream);
+            if (build_reduce_plan(c, S.plan, bucket_set_ascend, nbuckets, 1)) shim_fail(c, what);
+            S.bs_key = bucket_set_ascend; S.bs_n = nbuckets; S.bs_last = last; S.bs_mid = mid;
+        }
+        plan = &S.plan; d_bs = (const int *)S.d_bs.p; d_v = (const int *)S.d_v2i.p; d_cf = (const int *)S.d_cf.p; vspan = S.vspan; nchunks = S.nchunks;
     } else {
-        vspan = pick_vspan_host(nbuckets - 1, 1);
-        nchunks = (uint32_t)((nbuckets - 1 + vspan - 1) / vspan);
+        if (S.dense_n != nbuckets || !S.dense_plan.valid) {
+            S.dense_vspan = pick_vspan_host(nbuckets - 1, 1);
+            S.dense_chunks = (uint32_t)((nbuckets - 1 + S.dense_vspan - 1) / S.dense_vspan);
+            if (build_reduce_plan(c, S.dense_plan, nullptr, nbuckets, 1)) shim_fail(c, what);
+            S.dense_n = nbuckets;
+        }
+        plan = &S.dense_plan; vspan = S.dense_vspan; nchunks = S.dense_chunks;
     }
-    bool ok = cudaMalloc(&dp, hp.size()) == cudaSuccess && cudaMalloc(&dsc, npoints * 4) == cudaSuccess && cudaMalloc(&dsg, npoints) == cudaSuccess &&
-              cudaMalloc(&dpi, npoints * 4) == cudaSuccess && cudaMalloc(&dj, jb) == cudaSuccess;
-    if (ok && bucket_set_ascend) ok = cudaMalloc(&dbs, nbuckets * 4) == cudaSuccess && cudaMalloc(&dv, v2i_len * 4) == cudaSuccess && cudaMalloc(&dcf, cf.size() * 4) == cudaSuccess;
-    if (!ok) { c->err = "cudaMalloc"; shim_fail(c, "blst_pN_tile_pippenger"); }
-    cudaMemcpyAsync(dp, hp.data(), hp.size(), cudaMemcpyHostToDevice, c->stream);
-    cudaMemcpyAsync(dsc, scalars, npoints * 4, cudaMemcpyHostToDevice, c->stream);
-    cudaMemcpyAsync(dsg, signs, npoints, cudaMemcpyHostToDevice, c->stream);
-    cudaMemcpyAsync(dpi, pidx.data(), npoints * 4, cudaMemcpyHostToDevice, c->stream);
-    if (bucket_set_ascend) {
-        cudaMemcpyAsync(dbs, bucket_set_ascend, nbuckets * 4, cudaMemcpyHostToDevice, c->stream);
-        cudaMemcpyAsync(dv, v2i, v2i_len * 4, cudaMemcpyHostToDevice, c->stream);
-        cudaMemcpyAsync(dcf, cf.data(), cf.size() * 4, cudaMemcpyHostToDevice, c->stream);
+    if (c->ops->tile(c, d_table, (const int *)S.sc.p, (const unsigned char *)S.sg.p, (const uint32_t *)S.pi.p, npoints, d_v, d_bs, nbuckets, d_max, d_cf, vspan,
+                     nchunks, plan, S.jac.p))
+        shim_fail(c, what);
+    cudaMemcpyAsync(ret, S.jac.p, jb, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, what); }
+}
+// blst_pN_construct_nh_scalars_nh_points (bindings/blst.h:274-276, src/multi_scalar.c:748-775), in place on the caller's
+// arrays like the reference: digits in / bucket values out, signs out, host pointers into the caller's 3nh table out.
+static void shim_construct_nh(int group, int nh_scalars[], unsigned char booth_signs[], void *nh_points_ptr[], size_t npoints, const void *table,
+                              const void *triples) {
+    Ctx *c = shim_ctx(group);
+    ShimCall call_lock(group);
+    ShimState &S = g_state[group];
+    if (npoints == 0) return;
+    cudaSetDevice(c->device);
+    const char *what = "blst_pN_construct_nh_scalars_nh_points";
+    if (ensure(c, S.in, npoints * 4) || ensure(c, S.sc, npoints * 4) || ensure(c, S.sg, npoints) || ensure(c, S.ptrs, npoints * 8) || ensure(c, S.aux, 64))
+        shim_fail(c, what);
+    cudaMemcpyAsync(S.in.p, nh_scalars, npoints * 4, cudaMemcpyHostToDevice, c->stream);
+    // the digit table has q + 1 entries; its length is not an argument: size the upload by the largest digit (+1 for a carry)
+    ShimAux x;
+    x.in = (const int *)S.in.p; x.m = npoints; x.out_b = (int *)S.aux.p;
+    int maxd = 0;
+    cudaMemsetAsync(S.aux.p, 0, 4, c->stream);
+    if (c->ops->shim_aux(c, 2, x)) shim_fail(c, what);
+    cudaMemcpyAsync(&maxd, S.aux.p, 4, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, what); }
+    const size_t need = (size_t)maxd + 2;
+    if (S.tri_key != triples || S.tri_n < need) {
+        if (ensure(c, S.d_tri, need * 12)) shim_fail(c, what);
+        cudaMemcpyAsync(S.d_tri.p, triples, need * 12, cudaMemcpyHostToDevice, c->stream);
+        S.tri_key = triples; S.tri_n = need;
     }
-    ReducePlan plan;  // rebuilt per call: the shim is a compatibility path, the context API caches its plans
-    if (build_reduce_plan(c, plan, bucket_set_ascend, nbuckets, 1)) shim_fail(c, "blst_pN_tile_pippenger");
-    if (c->ops->tile(c, dp, (const int *)dsc, (const unsigned char *)dsg, (const uint32_t *)dpi, npoints, (const int *)dv, (const int *)dbs, nbuckets,
-                     d_max, (const int *)dcf, vspan, nchunks, &plan, dj))
-        shim_fail(c, "blst_pN_tile_pippenger");
-    cudaMemcpyAsync(ret, dj, jb, cudaMemcpyDeviceToHost, c->stream);
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, "blst_pN_tile_pippenger"); }
-    cudaFree(dp); cudaFree(dsc); cudaFree(dsg); cudaFree(dpi); cudaFree(dj); cudaFree(dbs); cudaFree(dv); cudaFree(dcf);
-    free_reduce_plan(plan);
+    x.out_b = (int *)S.sc.p; x.signs = (unsigned char *)S.sg.p; x.ptrs = (unsigned long long *)S.ptrs.p; x.triples = (const int *)S.d_tri.p;
+    x.base = (unsigned long long)(uintptr_t)table; x.entry_bytes = (unsigned)c->ops->aff_bytes;
+    if (c->ops->shim_aux(c, 0, x)) shim_fail(c, what);
+    cudaMemcpyAsync(nh_scalars, S.sc.p, npoints * 4, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(booth_signs, S.sg.p, npoints, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(nh_points_ptr, S.ptrs.p, npoints * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = cudaGetErrorString(cudaGetLastError()); shim_fail(c, what); }
 }
 
 // blst_pNs_add (src/bulk_addition.c:145-164): sum of npoints affine points. One bucket holding every point, so the
 // work is exactly the bucket-accumulation stage (batch-affine rounds or XYZZ work items + block combine).
 static void shim_points_add(int group, void *ret, const void *const points[], size_t npoints) {
     Ctx *c = shim_ctx(group);
-    std::lock_guard<std::mutex> call_lock(g_shim_call_mu[group]);
+    ShimCall call_lock(group);
     size_t ab = c->ops->aff_bytes, jb = c->ops->jac_bytes;
     if (npoints == 0) { memset(ret, 0, jb); return; }
     cudaSetDevice(c->device);
@@ -961,6 +1213,24 @@ void msmb200_blst_p1_tile_pippenger_d_CHES(void *ret, const void *const points[]
 void msmb200_blst_p2_tile_pippenger_d_CHES(void *ret, const void *const points[], size_t npoints, const int scalars[], const unsigned char booth_signs[],
                                            void *, int bucket_set_ascend[], int bucket_value_to_its_index[], size_t bucket_set_size, int d_max) {
     shim_tile(2, ret, points, npoints, scalars, booth_signs, bucket_set_ascend, bucket_value_to_its_index, bucket_set_size, d_max);
+}
+void msmb200_blst_p1_construct_nh_scalars_nh_points(int nh_scalars[], unsigned char booth_signs[], void *nh_points_ptr[], size_t npoints,
+                                                    void *precomputation_points_list_3nh, const void *digit_conversion_hash_table) {
+    shim_construct_nh(1, nh_scalars, booth_signs, nh_points_ptr, npoints, precomputation_points_list_3nh, digit_conversion_hash_table);
+}
+void msmb200_blst_p2_construct_nh_scalars_nh_points(int nh_scalars[], unsigned char booth_signs[], void *nh_points_ptr[], size_t npoints,
+                                                    void *precomputation_points_list_3nh, const void *digit_conversion_hash_table) {
+    shim_construct_nh(2, nh_scalars, booth_signs, nh_points_ptr, npoints, precomputation_points_list_3nh, digit_conversion_hash_table);
+}
+double msmb200_blst_last_call_ms(int group) { return group == 1 || group == 2 ? g_shim_last_ms[group] : -1.0; }
+int msmb200_blst_register_table(int group, const void *host_table, size_t entries) {
+    if ((group != 1 && group != 2) || !host_table || entries == 0 || entries > ((size_t)1 << 31)) return MSMB200_EINVAL;
+    Ctx *c = shim_ctx(group);
+    ShimCall call_lock(group);
+    cudaSetDevice(c->device);
+    if (!shim_upload_table(c, g_state[group], (const unsigned char *)host_table, entries) || cudaStreamSynchronize(c->stream) != cudaSuccess)
+        return ctx_fail(c, MSMB200_ECUDA, "uploading the host table failed");
+    return MSMB200_OK;
 }
 void msmb200_blst_p1_tile_pippenger_BGMW95(void *ret, const void *const points[], size_t npoints, const int scalars[], const unsigned char booth_signs[],
                                            void *, size_t q_exponent) {

@@ -97,6 +97,12 @@ struct Ctx {
     int launches = 0;
 };
 
+struct ShimAux {
+    const int *in = nullptr; int *out_b = nullptr; unsigned char *signs = nullptr; unsigned long long *ptrs = nullptr; size_t m = 0;
+    const int *triples = nullptr; unsigned long long base = 0; unsigned entry_bytes = 0; unsigned long long entries = 0;
+    uint32_t *pidx = nullptr, *bad = nullptr;
+};
+
 struct GroupOps {
     size_t aff_bytes, jac_bytes, xyzz_bytes;
     // method 1..4; scalars in device memory; writes Jacobian partial to d_out_jac (device) and/or affine to
@@ -113,6 +119,9 @@ struct GroupOps {
                 uint32_t nchunks, const ReducePlan *plan, void *d_out_jac);
     int (*pippenger)(Ctx *, const void *d_points, size_t npoints, const void *d_scalars, int nbits, void *d_out_jac,
                      bool want_affine, int wbits_table, int tile_bit0, int tile_window);
+    // device halves of the literal shims on the caller's arrays: what 0 = construct_nh on {m, b, alpha} triples, 1 = host
+    // pointers -> table indices (*bad counts pointers outside the table), 2 = max of an int array, 3 = min / max pointer
+    int (*shim_aux)(Ctx *, int what, const ShimAux &x);
     int (*field_op)(int field, int op, const void *a, const void *b, void *out, size_t n);
     int (*point_op)(int op, const void *a, const void *b, const unsigned char *flags, void *out, size_t n);
     int (*digits)(Ctx *, int kind, const void *d_scalars, size_t n, uint32_t *d_keys, uint32_t *d_vals);
@@ -124,6 +133,8 @@ struct GroupOps {
     // table persistence: dir 0 = affine entries -> blst_pN_affine_serialize bytes; dir 1 = bytes (serialized != 0) or raw
     // Montgomery entries (serialized == 0) -> validated affine entries, *d_bad += number of invalid entries
     int (*table_io)(Ctx *, int dir, int serialized, const void *d_src, void *d_dst, size_t n, uint32_t *d_bad);
+    // *d_out += position-weighted 64-bit checksum of `bytes` bytes of device memory (bytes a multiple of 8)
+    int (*checksum)(Ctx *, const void *d_src, size_t bytes, unsigned long long *d_out);
 };
 
 int measure_peaks(double out[4]);

@@ -99,7 +99,7 @@ extern "C" int msmb200_debug_ba_timing(unsigned long long *out) {
 static const GroupOps kOps = {
     sizeof(aff_t<fp_t>), sizeof(jac_t<fp_t>), sizeof(xyzz_t<fp_t>),
     msm_impl<fp_t, fpc_t>, generate_fix_points_impl<fpc_t>, table_build_impl<fpc_t>, sum_partials_impl<fpc_t>, combine_bits_impl<fpc_t>, tile_impl<fp_t, fpc_t>,
-    pippenger_impl<fp_t, fpc_t>, field_op_g, point_op_impl<fp_t, fpc_t>, digits_impl<fp_t>, resident_blocks_impl<fp_t, fpc_t>, wbits_precompute_impl<fpc_t>, table_io_impl<fpc_t>};
+    pippenger_impl<fp_t, fpc_t>, shim_aux_impl, field_op_g, point_op_impl<fp_t, fpc_t>, digits_impl<fp_t>, resident_blocks_impl<fp_t, fpc_t>, wbits_precompute_impl<fpc_t>, table_io_impl<fpc_t>, checksum_impl};
 const GroupOps *group_ops_g1() { return &kOps; }
 
 }  // namespace msmb200

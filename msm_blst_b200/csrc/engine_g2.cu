@@ -14,7 +14,7 @@ template <> const uint32_t *generator_words<fp2_t>() { return (const uint32_t *)
 static const GroupOps kOps = {
     sizeof(aff_t<fp2_t>), sizeof(jac_t<fp2_t>), sizeof(xyzz_t<fp2_t>),
     msm_impl<fp2_t, fp2_t>, generate_fix_points_impl<fp2_t>, table_build_impl<fp2_t>, sum_partials_impl<fp2_t>, combine_bits_impl<fp2_t>, tile_impl<fp2_t, fp2_t>,
-    pippenger_impl<fp2_t, fp2_t>, nullptr, point_op_impl<fp2_t, fp2_t>, digits_impl<fp2_t>, resident_blocks_impl<fp2_t, fp2_t>, wbits_precompute_impl<fp2_t>, table_io_impl<fp2_t>};
+    pippenger_impl<fp2_t, fp2_t>, shim_aux_impl, nullptr, point_op_impl<fp2_t, fp2_t>, digits_impl<fp2_t>, resident_blocks_impl<fp2_t, fp2_t>, wbits_precompute_impl<fp2_t>, table_io_impl<fp2_t>, checksum_impl};
 const GroupOps *group_ops_g2() { return &kOps; }
 
 }  // namespace msmb200

@@ -532,6 +532,17 @@ static int tile_impl(Ctx *c, const void *d_table, const int *d_bvals, const unsi
     return run_buckets<F, FC>(c, L, (const aff_t<F> *)d_table, d_out_jac, false);
 }
 
+// device halves of the literal shims that work on the caller's host arrays (api.cu)
+static int shim_aux_impl(Ctx *c, int what, const ShimAux &x) {
+    cudaStream_t st = c->stream;
+    if (what == 0) construct_nh_triples_kernel<<<blocks_for(x.m, 256), 256, 0, st>>>(x.in, x.out_b, x.signs, x.ptrs, x.m, x.triples, x.base, x.entry_bytes);
+    else if (what == 1) ptrs_to_index_kernel<<<blocks_for(x.m, 256), 256, 0, st>>>(x.ptrs, x.m, x.base, x.entry_bytes, x.entries, x.pidx, x.bad);
+    else if (what == 2) max_int_kernel<<<blocks_for(x.m, 256), 256, 0, st>>>(x.in, x.m, x.out_b);
+    else minmax_ptr_kernel<<<blocks_for(x.m, 256), 256, 0, st>>>(x.ptrs, x.m, (unsigned long long *)x.pidx);
+    MSM_CUDA(c, cudaGetLastError());
+    return MSMB200_OK;
+}
+
 template <class F> static int sum_partials_impl(Ctx *c, const void *d_partials, int count) {
     if (ensure(c, c->result, sizeof(jac_t<F>) + sizeof(aff_t<F>)) || ensure(c, c->red_c, sizeof(xyzz_t<F>) + 64)) return MSMB200_ECUDA;
     aff_t<F> *d_aff = (aff_t<F> *)((char *)c->result.p + sizeof(jac_t<F>));
@@ -654,6 +665,12 @@ template <class F> static int wbits_precompute_impl(Ctx *c, const void *d_points
 template <class F> static int table_io_impl(Ctx *c, int dir, int serialized, const void *d_src, void *d_dst, size_t n, uint32_t *d_bad) {
     if (dir == 0) table_serialize_kernel<F><<<blocks_for(n, 128), 128, 0, c->stream>>>((const aff_t<F> *)d_src, n, (uint32_t *)d_dst);
     else table_deserialize_kernel<F><<<blocks_for(n, 128), 128, 0, c->stream>>>((const uint32_t *)d_src, n, serialized, (aff_t<F> *)d_dst, d_bad);
+    MSM_CUDA(c, cudaGetLastError());
+    return MSMB200_OK;
+}
+
+static int checksum_impl(Ctx *c, const void *d_src, size_t bytes, unsigned long long *d_out) {
+    checksum_kernel<<<c->sms * 4, 256, 0, c->stream>>>((const unsigned long long *)d_src, bytes / 8, d_out);
     MSM_CUDA(c, cudaGetLastError());
     return MSMB200_OK;
 }

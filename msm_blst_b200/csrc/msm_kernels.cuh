@@ -109,6 +109,54 @@ static __global__ void construct_nh_kernel(int *__restrict__ flat, unsigned char
         pidx[k] = (uint32_t)(3 * k + ((ent >> 22) & 3u));
     }
 }
+// Literal blst_pN_construct_nh_scalars_nh_points (src/multi_scalar.c:748-775) on the caller's own arrays: the digit table is
+// the reference's array of {m, b, alpha} triples (bindings/blst.h:253); slot k becomes the bucket VALUE b, booth_signs[k] =
+// alpha, alpha carries into slot k + 1, and the output "pointer" is the HOST address table_base + (3k + m - 1) * entry size,
+// exactly what the reference stores. The reference is one sequential pass over all slots (it does not know where a scalar
+// ends); here every slot finds its own carry-in: it walks back to the nearest slot whose alpha does not depend on ITS
+// carry-in (alpha(H[d]) == alpha(H[d + 1]) — every scalar's small top digit is one) and replays forward from there.
+__device__ __forceinline__ int tri_alpha(const int *__restrict__ triples, int d) { return triples[3 * (size_t)d + 2]; }
+static __global__ void construct_nh_triples_kernel(const int *__restrict__ in, int *__restrict__ out_b, unsigned char *__restrict__ signs,
+                                                   unsigned long long *__restrict__ ptrs, size_t m, const int *__restrict__ triples,
+                                                   unsigned long long table_base, unsigned entry_bytes) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    long long j = (long long)k - 1;
+    int carry = 0;
+    while (j >= 0) {
+        const int d = in[j], a0 = tri_alpha(triples, d), a1 = tri_alpha(triples, d + 1);
+        if (a0 == a1) { carry = a0; break; }
+        j--;
+    }
+    for (long long t = j + 1; t < (long long)k; t++) carry = tri_alpha(triples, in[t] + carry);
+    const int d = in[k] + carry;
+    const int mm = triples[3 * (size_t)d], b = triples[3 * (size_t)d + 1], alpha = triples[3 * (size_t)d + 2];
+    out_b[k] = b;
+    signs[k] = (unsigned char)alpha;
+    ptrs[k] = table_base + (unsigned long long)(3 * k + (size_t)mm - 1) * entry_bytes;
+}
+// largest value of an int array (sizes the upload of the caller's digit table) / lowest and highest host pointer
+static __global__ void max_int_kernel(const int *__restrict__ v, size_t m, int *__restrict__ out) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int x = k < m ? v[k] : 0;
+    x = __reduce_max_sync(0xffffffffu, x);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, x);
+}
+static __global__ void minmax_ptr_kernel(const unsigned long long *__restrict__ p, size_t m, unsigned long long *__restrict__ out /* [min, max] */) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    atomicMin(&out[0], p[k]);
+    atomicMax(&out[1], p[k]);
+}
+// host pointers into a registered table -> table indices; anything outside the table raises *bad
+static __global__ void ptrs_to_index_kernel(const unsigned long long *__restrict__ ptrs, size_t m, unsigned long long base, unsigned entry_bytes,
+                                            unsigned long long entries, uint32_t *__restrict__ pidx, uint32_t *__restrict__ bad) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const unsigned long long off = ptrs[k] - base, idx = off / entry_bytes;
+    if (ptrs[k] < base || idx >= entries || off % entry_bytes) { atomicAdd(bad, 1u); pidx[k] = 0; return; }
+    pidx[k] = (uint32_t)idx;
+}
 // Front half of blst_p1_tile_pippenger_d_CHES (src/multi_scalar.c:437-461): booth_idx =
 // bucket_value_to_its_index[scalars[k]], skip when 0. Also serves the literal blst-named shim.
 static __global__ void tile_lookup_kernel(const int *__restrict__ bvals, const unsigned char *__restrict__ signs,
@@ -1212,6 +1260,15 @@ static __global__ void __launch_bounds__(128) table_serialize_kernel(const aff_t
 #pragma unroll
         for (int w = 0; w < 12; w++) o[12 * k + w] = be[w];
     }
+}
+// position-weighted 64-bit checksum of an array of 64-bit words (table files bind to the fixed points they were built from)
+static __global__ void checksum_kernel(const unsigned long long *__restrict__ w, size_t n, unsigned long long *__restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc += w[i] * (0x9E3779B97F4A7C15ull * (i + 1) | 1ull);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 // which entries fail is not needed: the count of bad entries (flags, range, curve equation) is accumulated
 template <class F>

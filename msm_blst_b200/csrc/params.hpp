@@ -56,6 +56,31 @@ inline std::vector<int> build_bucket_set(int q, int ah) {
     return B;
 }
 
+// Parameter-search side of the construction: check_bucket_set_validity + max_gap_in_bucket_set of the
+// reference's tool (main_bucket_set_construction.cpp:74-113, :115-122) on bitmaps instead of std::set.
+//   leading: every top digit 0..ah+1 is m*b with b in B, m in {1,2,3}            (:80-90)
+//   cover:   every digit 0..q is m*b or q - m*b with m*b <= q                     (:92-110)
+struct BucketSetCheck { bool leading_ok, cover_ok; long size, max_gap, first_uncovered; };
+inline BucketSetCheck check_bucket_set(const std::vector<int> &B, long q, long ah) {
+    BucketSetCheck r{true, true, (long)B.size(), 0, -1};
+    std::vector<uint8_t> lead((size_t)ah + 2, 0), cov((size_t)q + 1, 0);
+    lead[0] = 1;
+    cov[0] = 1;
+    for (size_t j = 0; j < B.size(); ++j) {
+        const long b = B[j];
+        if (j + 1 < B.size() && B[j + 1] - b > r.max_gap) r.max_gap = B[j + 1] - b;
+        for (long m = 1; m <= 3; ++m) {
+            const long v = m * b;
+            if (v <= ah + 1) lead[(size_t)v] = 1;
+            if (v <= q) { cov[(size_t)v] = 1; cov[(size_t)(q - v)] = 1; }
+        }
+    }
+    for (long d = 0; d <= ah + 1; ++d) r.leading_ok = r.leading_ok && lead[(size_t)d];
+    for (long d = 0; d <= q; ++d)
+        if (!cov[(size_t)d]) { r.cover_ok = false; if (r.first_uncovered < 0) r.first_uncovered = d; }
+    return r;
+}
+
 // Packed digit table: entry d in [0, q] -> bucket index (bits 0..21) | (m-1) << 22 | alpha << 24.
 // Same precedence as the reference's two passes (later writes win: alpha = 0 preferred, then the largest m).
 constexpr uint32_t DT_IDX_MASK = (1u << 22) - 1;

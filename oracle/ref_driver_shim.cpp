@@ -9,9 +9,26 @@
 // The driver source is #included by absolute path where it lies under /root/reference (never copied);
 // its configuration is whatever ches_config_files/config_file.h holds there (config 10: n = 2^10).
 // Built by oracle/Makefile into oracle/_ref/refdrv_p{1,2}.so (git-ignored).
+// Variants built by oracle/Makefile from this same file:
+//   refdrv_p{1,2}.so            the driver on the compiled reference (libblst_ref.so)                    [the oracle pin]
+//   refdrv_p{1,2}_dropin.so     the driver with its five MSM imports re-pointed (-D...=msmb200_...) at libmsm_b200.so, so
+//                               the reference's OWN glue runs on the CUDA shims with seeded scalars      [drop-in test]
+//   refdrv_p1_dropin_c<N>.so    the same for configuration N: REF_MAIN names the driver inside a symlink farm
+//                               (oracle/_ref/drv<N>/) whose ches_config_files/config_file.h links to the reference's
+//                               config_file_n_exp_<N>.h - what the reference makefile does with cp (makefile:15-18)
 #include <cstring>
+#include <chrono>
 #define main msmref_unused_main
+#ifdef REF_MAIN
+#include REF_MAIN
 #if GROUP == 1
+typedef blst_p1_affine ref_affine_t;
+#define REF_SERIALIZE blst_p1_affine_serialize
+#else
+typedef blst_p2_affine ref_affine_t;
+#define REF_SERIALIZE blst_p2_affine_serialize
+#endif
+#elif GROUP == 1
 #include "/root/reference/main_p1.cpp"
 typedef blst_p1_affine ref_affine_t;
 #define REF_SERIALIZE blst_p1_affine_serialize
@@ -35,16 +52,22 @@ void refdrv_init() {
     init_pippenger_CHES_q_over_5();
     init_pippenger_BGMW95();
 }
+// the fixed points only (the tables then come from refdrv_set_tables)
+void refdrv_init_points() { init_fix_point_list(); }
+size_t refdrv_table_entries(int which) { return which == 0 ? (size_t)3 * N_POINTS * h_LEN_SCALAR : (size_t)h_BGMW95 * N_POINTS; }
 const void *refdrv_fix_points() { return FIX_POINTS_LIST; }
 const void *refdrv_table(int which) { return which == 0 ? (const void *)PRECOMPUTATION_POINTS_LIST_3nh : (const void *)PRECOMPUTATION_POINTS_LIST_BGMW95; }
 const int *refdrv_bucket_set() { return BUCKET_SET; }
 const int *refdrv_hash() { return (const int *)DIGIT_CONVERSION_HASH_TABLE; }
+static double g_last_ms = 0;
+double refdrv_last_ms() { return g_last_ms; }   // wall time of the driver method of the last refdrv_msm call
 // scalars: N_POINTS x 4 u64 LE limbs. out_struct: affine struct (Montgomery limbs); out_bytes: serialised
 int refdrv_msm(int method, const uint64_t *scalars, void *out_struct, unsigned char *out_bytes) {
     uint256_t *arr = new uint256_t[N_POINTS];
     for (size_t i = 0; i < N_POINTS; i++)
         for (int k = 0; k < 4; k++) arr[i].data[k] = scalars[4 * i + k];
     ref_affine_t r;
+    const auto t0 = std::chrono::steady_clock::now();
     switch (method) {
     case 1: r = pippenger_variant_q_over_5_CHES(arr); break;
     case 2: r = pippenger_variant_q_over_5_CHES_integral_scalar_conversion(arr); break;
@@ -52,6 +75,7 @@ int refdrv_msm(int method, const uint64_t *scalars, void *out_struct, unsigned c
     case 4: r = pippenger_blst_built_in(arr); break;
     default: delete[] arr; return -1;
     }
+    g_last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     delete[] arr;
     if (out_struct) memcpy(out_struct, &r, sizeof(r));
     if (out_bytes) REF_SERIALIZE(out_bytes, &r);

@@ -56,6 +56,64 @@ def test_host_bucket_set_sizes_all_configs(product_lib, golden):
         assert int(np.diff(B).max()) == 6 and B[0] == 0 and B[1] == 1
 
 
+def _py_bucket_set(q, ah):
+    """Independent restatement of construct_bucket_set (reference main_bucket_set_construction.cpp:39-72) with Python sets."""
+    def w(i, p):
+        c = 0
+        while i % p == 0:
+            i //= p
+            c += 1
+        return c
+    B = {0, 1} | {i for i in range(2, q // 2 + 1) if (w(i, 2) + w(i, 3)) % 2 == 0}
+    for i in range(q // 4, q // 2):
+        if i in B and (q - 2 * i) in B:
+            B.discard(q - 2 * i)
+    for i in range(q // 6, q // 4):
+        if i in B and (q - 3 * i) in B:
+            B.discard(q - 3 * i)
+    B |= {i for i in range(1, ah + 2) if (w(i, 2) + w(i, 3)) % 2 == 0}
+    return sorted(B)
+
+
+def _py_check(B, q, ah):
+    """check_bucket_set_validity (:74-113) and max_gap_in_bucket_set (:115-122)."""
+    lead = {0} | {m * b for b in B for m in (1, 2, 3) if m * b <= ah + 1}
+    cov = {0}
+    for b in B:
+        for m in (1, 2, 3):
+            if m * b <= q:
+                cov |= {m * b, q - m * b}
+    missing = sorted(set(range(q + 1)) - cov)
+    return lead == set(range(ah + 2)), not missing, (missing[0] if missing else -1), max(y - x for x, y in zip(B, B[1:]))
+
+
+def test_parameter_search_check_all_reference_configs(product_lib, golden):
+    """the validity / max-gap check of the reference's parameter tool on all 17 shipped (e, a) pairs."""
+    for key, size in golden["kat_appc"]["bsize"].items():
+        e, a = map(int, key.split(","))
+        r = product_lib.host_bucket_set_check(1 << e, a)
+        assert r == {"valid": True, "size": size, "max_gap": 6, "leading_ok": True, "first_uncovered": -1}, (key, r)
+
+
+def test_parameter_search_check_other_radices(product_lib):
+    """Radices and leading terms the reference does not ship (including non powers of two and sets that FAIL the check),
+    against an independent Python restatement of construct_bucket_set + check_bucket_set_validity."""
+    seen_invalid = 0
+    for q in (16, 32, 64, 100, 1000, 1024, 3 * 512, 1 << 13, 10000):
+        for a in (0, 3, 7, 40, 231):
+            if a + 1 > q // 2:
+                continue
+            B = _py_bucket_set(q, a)
+            lead, cover, first, gap = _py_check(B, q, a)
+            r = product_lib.host_bucket_set_check(q, a)
+            assert (r["size"], r["max_gap"], r["leading_ok"], r["first_uncovered"], r["valid"]) == (len(B), gap, lead, first, lead and cover), (q, a, r)
+            seen_invalid += not r["valid"]
+    with pytest.raises(product_lib.MsmB200Error):
+        product_lib.host_bucket_set_check(15, 1)
+    assert product_lib.host_bucket_set_check(1 << 13, 231)["valid"]
+    print("invalid parameter pairs found:", seen_invalid)
+
+
 def test_no_cpu_fallback(product_lib):
     """Without a CUDA device every compute entry point returns an error; with one, bad arguments do."""
     import torch

@@ -133,8 +133,8 @@ ALL_CONFIGS = ["8", "9", "10", "11", "12", "13", "14", "15", "16", "16_beta", "1
 @pytest.mark.parametrize("cfgname", ALL_CONFIGS)
 def test_g1_size_sweep_all_reference_configs(M, cfgname):
     """BASELINE configs[4]: every ches_config_files/config_file_n_exp_*.h row (n = 2^8 .. 2^21 incl. the _beta rows),
-    G1, CHES and its integral-scalar-conversion variant, plus BGMW95 (r - a trick rows included) up to n = 2^19;
-    checked against the closed form of the synthetic points."""
+    G1, all four methods (CHES, its integral-scalar-conversion variant, BGMW95 with the r - a trick rows, blst's Pippenger);
+    checked against the closed form of the synthetic points. At n = 2^16 the device-resident entry point is checked too."""
     ctx = M.MsmContext(1, cfgname)
     ctx.init_fix_point_list()
     ctx.init_pippenger_CHES_q_over_5()
@@ -142,15 +142,20 @@ def test_g1_size_sweep_all_reference_configs(M, cfgname):
     exp, _ = O.closed_form(1, sc)
     assert (ctx.msm(1, sc) == exp).all()
     assert (ctx.msm(2, sc) == exp).all()
-    if ctx.cfg.n_exp <= 19:
-        ctx.init_pippenger_BGMW95()
-        assert (ctx.msm(3, sc) == exp).all()
-        assert (ctx.msm(4, sc) == exp).all()
+    ctx.init_pippenger_BGMW95()
+    assert (ctx.msm(3, sc) == exp).all()
+    assert (ctx.msm(4, sc) == exp).all()
+    if ctx.cfg.n_exp == 16:
+        import torch
+
+        d_sc = torch.from_numpy(sc.view(np.uint8).copy()).cuda()
+        for m in (1, 2, 3, 4):
+            assert (ctx.msm_device(m, d_sc.data_ptr()) == exp).all(), m
     ctx.close()
 
 
-@pytest.mark.parametrize("cfgname", ["8", "11", "13", "15", "16", "16_beta", "17"])
-def test_g2_size_sweep(M, cfgname):
+@pytest.mark.parametrize("cfgname", ALL_CONFIGS)
+def test_g2_size_sweep_all_reference_configs(M, cfgname):
     ctx = M.MsmContext(2, cfgname)
     ctx.init_fix_point_list()
     ctx.init_pippenger_CHES_q_over_5()

@@ -422,6 +422,163 @@ def test_blst_tile_shims_ches_and_bgmw95(M, group):
     assert (M.test_point_op(group, 5, ret) == exp).all()
 
 
+@pytest.mark.parametrize("group", [1, 2])
+def test_blst_construct_nh_shim_vs_compiled_reference(M, group):
+    """msmb200_blst_pN_construct_nh_scalars_nh_points against the compiled reference's blst_pN_construct_nh_scalars_nh_points
+    (src/multi_scalar.c:748-775) on the same standard q-ary digits (main_p1.cpp:257-263): bucket values, booth signs and the
+    host POINTERS into the caller's 3nh table must be identical, including carries that run through several slots."""
+    if not O.has_ref():
+        pytest.skip("compiled reference not present")
+    cfgname, n = "10", 300
+    cfg = O.config(cfgname)
+    e, h, q = cfg["e"], cfg["h"], 1 << cfg["e"]
+    ab = O.AFF_BYTES[group]
+    oc = O.OracleCtx(group, cfgname, n=n)
+    H = np.ascontiguousarray(oc.hash_table())  # (q + 1) x {m, b, alpha}, the reference's digit_decomposition layout
+    ints = O.scalars_to_ints(O.gen_scalars(41, n))
+    ints[0] = 0
+    ints[1] = 1
+    ints[2] = (1 << (e * (h - 1))) - 1          # every lower digit q - 1: a carry chain through h - 1 slots
+    ints[3] = O.R_ORDER - 1 if hasattr(O, "R_ORDER") else ints[3]
+    npts = n * h
+    digits = np.zeros(npts + 2, dtype=np.int32)  # + 2 slots of slack for the reference's prefetch (main_p1.cpp:254-256)
+    for i, s in enumerate(ints):
+        for j in range(h):
+            digits[i * h + j] = (s >> (e * j)) & (q - 1)
+    table = np.zeros((3 * npts, ab), dtype=np.uint8)  # only its address matters
+    out = {}
+    for name, lib, prefix in (("ref", O.blst_ref(), "blst_p%d" % group), ("cuda", M.lib(), "msmb200_blst_p%d" % group)):
+        sc = digits.copy()
+        sg = np.full(npts, 7, dtype=np.uint8)
+        pp = np.zeros(npts, dtype=np.uint64)
+        f = getattr(lib, prefix + "_construct_nh_scalars_nh_points")
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        f.restype = None
+        f(O.ptr(sc), O.ptr(sg), O.ptr(pp), npts, O.ptr(table), O.ptr(H))
+        out[name] = (sc[:npts], sg, pp)
+    assert (out["ref"][0] == out["cuda"][0]).all()
+    assert (out["ref"][1] == out["cuda"][1]).all()
+    assert (out["ref"][2] == out["cuda"][2]).all()
+    assert out["cuda"][1].max() == 1 and (out["cuda"][2] >= table.ctypes.data).all()
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_blst_tile_shims_use_the_registered_table(M, group):
+    """msmb200_blst_register_table: the host table is mirrored in HBM once, tile calls then upload pointers only (13 bytes per
+    entry); a table changed in place is noticed and uploaded again; pointers outside the table take the gather path."""
+    n, cfgname = 128, "10"
+    cfg = O.config(cfgname)
+    ab, jb = O.AFF_BYTES[group], O.JAC_BYTES[group]
+    hb = cfg["h_bgmw"]
+    oc = O.OracleCtx(group, cfgname, n=n, threads=4)
+    oc.init_fix_points()
+    oc.build_table(1)
+    tb = np.ascontiguousarray(oc.table(1)).reshape(-1, ab)
+    assert M.lib().msmb200_blst_register_table(group, O.ptr(tb), tb.shape[0]) == 0
+    tile = getattr(M.lib(), "msmb200_blst_p%d_tile_pippenger_BGMW95" % group)
+
+    def run(table, sc, rows=None):
+        rows = range(n) if rows is None else rows
+        npts = len(rows) * hb
+        scal = np.zeros(npts, dtype=np.int32)
+        signs = np.zeros(npts, dtype=np.uint8)
+        ptrs = (C.c_void_p * npts)()
+        for t, i in enumerate(rows):
+            d, _ = oc.digits(1, sc[i])
+            for j in range(hb):
+                scal[t * hb + j] = abs(int(d[j]))
+                signs[t * hb + j] = 1 if d[j] < 0 else 0
+                ptrs[t * hb + j] = table.ctypes.data + (i * hb + j) * ab
+        ret = np.zeros(jb, dtype=np.uint8)
+        tile(O.ptr(ret), ptrs, npts, O.ptr(scal), O.ptr(signs), None, cfg["e_bgmw"])
+        return M.test_point_op(group, 5, ret)
+
+    sc = O.gen_scalars(61, n)
+    exp, _ = O.closed_form(group, sc)
+    assert (run(tb, sc) == exp).all()
+    assert (run(tb, sc) == exp).all()           # second call: table already resident
+    # the same buffer now holds the table of OTHER points (rows 3.. then 0..2): the mirror must follow
+    perm = np.roll(np.arange(n), -3)
+    tb[:] = tb.reshape(n, hb, ab)[perm].reshape(-1, ab)
+    sc2 = sc[perm]
+    assert (run(tb, sc2) == exp).all()
+    # pointers into a different buffer (a copy): learned / gathered, still right
+    other = tb.copy()
+    assert (run(other, sc2) == exp).all()
+    assert M.lib().msmb200_blst_last_call_ms(group) > 0
+
+
+def _dropin_driver(group, suffix=""):
+    import os
+
+    path = os.path.join(O.REF_DIR, "refdrv_p%d_dropin%s.so" % (group, suffix))
+    if not os.path.exists(path):
+        pytest.skip("%s not built (needs /root/reference at build time)" % os.path.basename(path))
+    lib = C.CDLL(path)
+    lib.refdrv_msm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.refdrv_last_ms.restype = C.c_double
+    fd = os.dup(1)  # the driver's init reports progress on std::cout
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        lib.refdrv_init()
+    finally:
+        os.dup2(fd, 1)
+        os.close(fd)
+        os.close(devnull)
+    return lib
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_reference_driver_glue_on_the_cuda_shims_vs_golden(M, golden, group):
+    """The UNMODIFIED main_p{1,2}.cpp (config 10) as a library whose five MSM imports are re-pointed at libmsm_b200.so
+    (oracle/Makefile: refdrv_pN_dropin.so): its own init, digit conversions and pointer arrays, the CUDA shims underneath,
+    on the SEEDED scalars of the golden vectors - each of its four methods must print the reference's own result."""
+    lib = _dropin_driver(group)
+    gd = golden["c10"][str(group)]
+    for seed in (1, 2, 3):
+        sc = O.gen_scalars(seed, 1 << 10)
+        for method in (1, 2, 3, 4):
+            ob = np.zeros(O.SER_BYTES[group], dtype=np.uint8)
+            assert lib.refdrv_msm(method, O.ptr(sc), None, O.ptr(ob)) == 0
+            assert ob.tobytes().hex() == gd["msm"][str(seed)], (seed, method)
+
+
+@pytest.mark.parametrize("cfgname", ["13", "16"])
+def test_reference_driver_glue_other_configs_and_shim_cost(M, cfgname):
+    """The drop-in driver at configuration 13 (always) and 16 (MSMB200_SLOW_TESTS=1: its CPU table build takes about a
+    minute): results against the oracle's closed form; the time one tile-shim call costs (pointers translated on the device
+    against the mirrored table) next to the context API's host-to-host time for the same MSM."""
+    import os
+    import time
+
+    if cfgname == "16" and not os.environ.get("MSMB200_SLOW_TESTS"):
+        pytest.skip("set MSMB200_SLOW_TESTS=1 (the reference's CPU table build at n = 2^16 takes about a minute)")
+    lib = _dropin_driver(1, "_c" + cfgname)
+    n = 1 << int(cfgname)
+    ctx = M.MsmContext(1, cfgname)
+    ctx.init_fix_point_list()
+    ctx.init_pippenger_CHES_q_over_5()
+    ctx.init_pippenger_BGMW95()
+    report = {}
+    for seed in (11, 12):
+        sc = O.gen_scalars(seed, n)
+        exp = O.serialize(1, O.closed_form(1, sc)[0])
+        for method in (1, 2, 3, 4):
+            ob = np.zeros(O.SER_BYTES[1], dtype=np.uint8)
+            assert lib.refdrv_msm(method, O.ptr(sc), None, O.ptr(ob)) == 0
+            assert ob.tobytes() == exp, (seed, method)
+            t0 = time.perf_counter()
+            got = ctx.msm(method, sc)
+            api_ms = (time.perf_counter() - t0) * 1e3
+            assert O.serialize(1, got) == exp
+            report[method] = (lib.refdrv_last_ms(), M.lib().msmb200_blst_last_call_ms(1), api_ms)
+    for method, (drv, shim, api) in report.items():
+        print("config %s method %d: driver method %.2f ms (reference glue on the host included), last shim call %.2f ms, "
+              "context API host-to-host %.2f ms" % (cfgname, method, drv, shim, api))
+    ctx.close()
+
+
 # ---------------------------------------------------------------- multi-GPU path emulated on one device
 @pytest.mark.parametrize("group", [1, 2])
 def test_sharded_partials_sum_to_full_result(M, group):
@@ -766,7 +923,7 @@ def test_table_save_load_round_trip_and_serialized_bytes(M, group, tmp_path):
     msmb200_affine_serialize); a fresh context loads points and both tables from disk and reproduces the MSM; a
     corrupted entry and a file written for another configuration are rejected."""
     ab = O.AFF_BYTES[group]
-    HDR = 72  # magic, version, group, format, which, configuration, npoints, entries
+    HDR = 80  # magic, version, group, format, which, configuration, npoints, entries, digest of the fixed points
     ctx = M.MsmContext(group, "10")
     ctx.init_fix_point_list()
     ctx.init_pippenger_CHES_q_over_5()
@@ -823,6 +980,17 @@ def test_table_save_load_round_trip_and_serialized_bytes(M, group, tmp_path):
     with pytest.raises(M.MsmB200Error):
         c4.table_load(2, files[(1, 0)])
     c4.close()
+    # same group / size / configuration but OTHER fixed points (the shard that starts at point 1024): the table is refused,
+    # and so is a table offered before any points are present
+    c5 = M.MsmContext(group, "10", first=1024)
+    with pytest.raises(M.MsmB200Error):
+        c5.table_load(1, files[(1, 0)])
+    c5.init_fix_point_list()
+    with pytest.raises(M.MsmB200Error):
+        c5.table_load(1, files[(1, 0)])
+    with pytest.raises(M.MsmB200Error):
+        c5.table_load(2, files[(2, 1)])
+    c5.close()
 
 
 @pytest.mark.parametrize("group", [1, 2])
