@@ -214,7 +214,7 @@ static void ctx_release(Ctx *c) {
                       &c->item_start, &c->cursor, &c->item_begin, &c->item_cnt, &c->order, &c->len_hist, &c->len_start, &c->len_cursor,
                       &c->partial, &c->chunk_a, &c->chunk_b, &c->result, &c->flat, &c->signs, &c->pidx, &c->heavy, &c->light, &c->medium,
                       &c->ba_totals, &c->ba_tile_sums, &c->ba_bases, &c->ba_adesc, &c->ba_cdesc, &c->ba_heavy, &c->pts_a, &c->pts_b, &c->ba_scratch,
-                      &c->bucket_sum, &c->iota, &c->ba_counters, &c->ba_sm_arrivals, &c->maxcount, &c->red_a, &c->red_b, &c->red_c, &c->red_d};
+                      &c->bucket_sum, &c->iota, &c->ba_counters, &c->ba_sm_arrivals, &c->ba_lane_totals, &c->maxcount, &c->red_a, &c->red_b, &c->red_c, &c->red_d};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     free_reduce_plan(c->plan_ches); free_reduce_plan(c->plan_bgmw); free_reduce_plan(c->plan_pip);
     void *ptrs[] = {c->d_bucket_vals, c->d_v2i, c->d_dtab, c->d_chunk_first, c->d_points, c->d_table_ches, c->d_table_bgmw};
@@ -425,6 +425,8 @@ int msmb200_set_tuning(msmb200_ctx *ctx, const char *key, int value) {
     if (k == "ba_batch_max") c->ba_batch_max = std::max(1, value);
     else if (k == "ba_batch") c->ba_batch_fixed = value;
     else if (k == "ba_stagger") c->ba_stagger = value;
+    else if (k == "ba_split") c->ba_split = value;
+    else if (k == "ba_batch_max_split") c->ba_batch_max_split = std::max(1, value);
     else if (k == "item_len") c->item_len_fixed = value;
     else return ctx_fail(c, MSMB200_EINVAL, "unknown tuning key " + k);
     return MSMB200_OK;

@@ -29,17 +29,24 @@ constexpr int BA_RMAX = 32;                   // rounds: counts are < 2^32
 constexpr uint32_t BA_FINAL = 0x80000000u;    // output descriptor: bucket_sum[b] instead of the next round's buffer
 constexpr uint32_t BA_HEAVY = 2048;           // buckets with more entries are planned by a whole block
 constexpr int BA_THREADS = 128;
+enum { BA_FWD = 0, BA_BWD = 1, BA_FUSED = 2 };   // what one launch of ba_round_kernel does (see there)
 // resident blocks per SM the round kernel is compiled for (register budget 65536 / (128 x blocks) per thread)
 #ifndef BA_MIN_BLOCKS_FP
-#define BA_MIN_BLOCKS_FP 3
-#endif
-#ifndef BA_STAGE_Y_FP
-#define BA_STAGE_Y_FP 1
+#define BA_MIN_BLOCKS_FP 4
 #endif
 #ifndef BA_MIN_BLOCKS_FP2
 #define BA_MIN_BLOCKS_FP2 2
 #endif
-template <class F> struct ba_cfg { static constexpr int MIN_BLOCKS = sizeof(F) > 48 ? BA_MIN_BLOCKS_FP2 : BA_MIN_BLOCKS_FP; };
+#ifndef BA_MIN_BLOCKS_FWD_FP
+#define BA_MIN_BLOCKS_FWD_FP 4
+#endif
+#ifndef BA_MIN_BLOCKS_FWD_FP2
+#define BA_MIN_BLOCKS_FWD_FP2 2
+#endif
+template <class F> struct ba_cfg {
+    static constexpr int MIN_BLOCKS = sizeof(F) > 48 ? BA_MIN_BLOCKS_FP2 : BA_MIN_BLOCKS_FP;
+    static constexpr int MIN_BLOCKS_FWD = sizeof(F) > 48 ? BA_MIN_BLOCKS_FWD_FP2 : BA_MIN_BLOCKS_FWD_FP;   // forward-only launch
+};
 
 // filled by the host once the per-round totals are known
 struct BaRounds {
@@ -356,6 +363,32 @@ template <class F> __device__ __forceinline__ void ba_ld_stage(F &v, const unsig
 #pragma unroll
     for (int k = 0; k < (int)(sizeof(F) / 16); k++) dst[k] = *reinterpret_cast<const uint4 *>(base + ba_chunk(chunk0 + k));
 }
+
+// ---- round 0: warp-cooperative gather of table entries ----
+// Measured on B200 (profiles/r2_gather_microbench.json): the memory system serves about 41 G REQUESTS per second that miss
+// L2, whatever their size (32 .. 128 bytes of one line), and always fetches the whole 128-byte line from DRAM. A lane
+// that pulls its own entry with 16-byte copies makes one request per 32-byte sector (3-4 per 96-byte entry, twice per
+// round): 12.4 M slots x ~11 requests = 3.3 ms, the whole duration of round 0. Here the lanes of a warp fetch each
+// other's operands instead: NCH consecutive lanes copy the NCH consecutive 16-byte chunks of ONE entry, so the piece of
+// a line an entry occupies travels as one request. The owner's descriptor is read from the shared-memory ring (copied
+// there by the owner; visible after cp.async.wait_group + __syncwarp), the chunks land in the owner's stage.
+template <class F, int NCH>
+__device__ __forceinline__ void ba_coop_gather(const aff_t<F> *__restrict__ table, const unsigned char *shared, uint32_t sbase, int desc_chunk, int first_chunk,
+                                               int dst_p, int dst_q) {
+    constexpr int EPI = 32 / NCH;                 // entries per warp instruction
+    constexpr int NI = (64 + EPI - 1) / EPI;      // 32 slots x 2 operands
+    const uint32_t lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u, sub = lane / NCH, c = lane % NCH;
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+        const uint32_t e = (uint32_t)i * EPI + sub;
+        if (sub < (uint32_t)EPI && e < 64u) {
+            const uint32_t o = e >> 1, which = e & 1u;
+            const uint32_t idx = *reinterpret_cast<const uint32_t *>(shared + ((size_t)desc_chunk * BA_THREADS + wbase + o) * 16 + which * 4) & 0x7fffffffu;
+            const uint4 *src = reinterpret_cast<const uint4 *>(table + idx) + first_chunk + c;
+            ba_cp16(sbase + (uint32_t)((((which ? dst_q : dst_p) + (int)c) * BA_THREADS + (int)(wbase + o)) * 16), src);
+        }
+    }
+}
 #ifdef MSMB200_BA_TIMING   // developer builds only: per-block phase time stamps (clock64) of every round
 constexpr int BA_DBG_BLOCKS = 4096;
 static __device__ unsigned long long ba_dbg[BA_RMAX][BA_DBG_BLOCKS][4];
@@ -366,14 +399,13 @@ static __device__ unsigned long long ba_dbg[BA_RMAX][BA_DBG_BLOCKS][4];
 template <class F> struct ba_smem {
     static constexpr int FCH = (int)(sizeof(F) / 16);        // 16-byte chunks per field element
     static constexpr int FWD_DESC = 4, FWD_STAGES = 3;       // descriptor ring / data stages (x1, x2, descriptor copy)
-    static constexpr int BWD_DESC = 2, BWD_STAGES = 2;       // data stage: prefix product, x1, x2, y1, y2, descriptor copy
-    // y staged as well: 68 KB per block (3 blocks per SM for Fp); otherwise y is prefetched into L2 one slot ahead and loaded
-    // directly where it is needed (44 KB, 4 blocks per SM). Fp2: staging y would leave one block per SM.
-    static constexpr bool STAGE_Y = sizeof(F) <= 48 && BA_STAGE_Y_FP;
-    static constexpr int FWD_STAGE_CH = 2 * FCH + 1, BWD_STAGE_CH = (STAGE_Y ? 5 : 3) * FCH + 1;
-    static constexpr int BWD_META = (STAGE_Y ? 5 : 3) * FCH;   // chunk of the descriptor copy inside a backward stage
-    static constexpr int FWD_CH = FWD_DESC + FWD_STAGES * FWD_STAGE_CH, BWD_CH = BWD_DESC + BWD_STAGES * BWD_STAGE_CH;
+    static constexpr int FWD_STAGE_CH = 2 * FCH + 1;
+    static constexpr int BWD_DESC = 3, BWD_X_CH = 3 * FCH;   // descriptor ring; one x stage: prefix product, x1, x2 (two stages), one y stage: y1, y2
+    static constexpr int FWD_CH = FWD_DESC + FWD_STAGES * FWD_STAGE_CH, BWD_CH = BWD_DESC + 2 * BWD_X_CH + 2 * FCH;
+    // Fp: 25 / 27 chunks of 2 KB -> 54 KB per block, 4 blocks (16 warps) per SM; Fp2: 43 / 51 chunks -> 102 KB, 2 blocks
     static constexpr int BYTES = (FWD_CH > BWD_CH ? FWD_CH : BWD_CH) * BA_THREADS * 16;
+    static constexpr int BYTES_FWD = FWD_CH * BA_THREADS * 16, BYTES_BWD = BWD_CH * BA_THREADS * 16;
+    static constexpr int bytes(int phase) { return phase == BA_FWD ? BYTES_FWD : phase == BA_BWD ? BYTES_BWD : BYTES; }
 };
 
 // Work distribution of one round. The kernel is PERSISTENT (`grid` = the co-resident blocks) and every WARP is an
@@ -392,10 +424,16 @@ struct BaSched {
 };
 __device__ __forceinline__ uint32_t ba_smid() { uint32_t r; asm("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 
-template <class F, bool FIRST>
-static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_round_kernel(ba_io<F> io, const uint4 *__restrict__ adesc, uint32_t nadds,
+// PHASE: BA_FUSED = forward, inversion and backward pass of a batch by the same warp (phases of different warps overlap);
+// BA_FWD / BA_BWD = the round as TWO launches: the forward pass alone is bound by DRAM (one multiplication per slot, two
+// random 48-byte reads), inversion + backward pass by the multiplier, so each launch runs against ONE limit with every
+// resident warp in the same regime. Uniform batches (batch k = rows [k * batch, (k + 1) * batch)), lane totals handed over
+// in `totals[k * 32 + lane]`.
+template <class F, bool FIRST, int PHASE>
+static __global__ void __launch_bounds__(BA_THREADS, (PHASE == BA_FWD ? ba_cfg<F>::MIN_BLOCKS_FWD : ba_cfg<F>::MIN_BLOCKS)) ba_round_kernel(ba_io<F> io, const uint4 *__restrict__ adesc, uint32_t nadds,
                                                                      const uint2 *__restrict__ cdesc, uint32_t ncopies,
-                                                                     uint4 *__restrict__ scratch, size_t scratch_stride, BaSched sched, uint32_t round) {
+                                                                     uint4 *__restrict__ scratch, size_t scratch_stride, BaSched sched, uint32_t round,
+                                                                     F *__restrict__ totals) {
     using SM = ba_smem<F>;
     constexpr int FCH = SM::FCH;
     constexpr uint32_t IDX = 0x7fffffffu;
@@ -411,7 +449,7 @@ static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_r
         uint32_t start = 0, n = 0;
         if (lane == 0) {
             n = sched.batch;
-            if (sched.stagger) {
+            if (PHASE == BA_FUSED && sched.stagger) {
                 if (first_batch) n = max(1u, (n * (sh_k + 1u)) / 3u);
                 const uint32_t seen = *(volatile uint32_t *)sched.counter;
                 const uint32_t left = seen < sched.rows ? sched.rows - seen : 0u;
@@ -431,21 +469,25 @@ static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_r
         // ---- forward: denominators and their running product ----
         F run;
         f_set_one(run);
-        {
+        if (PHASE != BA_BWD) {
             constexpr int ND = SM::FWD_DESC, NS = SM::FWD_STAGES, SCH = SM::FWD_STAGE_CH;
             auto stage_ch = [&](uint32_t j) { return ND + (int)(j % NS) * SCH; };
             auto issue_desc = [&](uint32_t j) { ba_cp16(sbase + ba_chunk((int)(j % ND)), desc_src(j)); };
             auto issue_data = [&](uint32_t j) {   // needs the descriptor of slot j in the ring
                 const uint4 m = *reinterpret_cast<const uint4 *>(ba_shared + ba_chunk((int)(j % ND)));
                 const int c0 = stage_ch(j);
-                ba_cp_field(sbase, c0, ba_px<F, FIRST>(io, m.x & IDX));
-                ba_cp_field(sbase, c0 + FCH, ba_px<F, FIRST>(io, m.y & IDX));
+                if (FIRST) ba_coop_gather<F, FCH>(io.table, ba_shared, sbase, (int)(j % ND), 0, c0, c0 + FCH);   // x = chunks 0 .. FCH - 1 of an entry
+                else {
+                    ba_cp_field(sbase, c0, ba_px<F, FIRST>(io, m.x & IDX));
+                    ba_cp_field(sbase, c0 + FCH, ba_px<F, FIRST>(io, m.y & IDX));
+                }
                 *reinterpret_cast<uint4 *>(ba_shared + ba_chunk(c0 + 2 * FCH)) = m;
             };
 #pragma unroll
             for (uint32_t j = 0; j < (uint32_t)ND; j++) issue_desc(j);
             ba_cp_commit();
             ba_cp_wait<0>();
+            if (FIRST) __syncwarp();        // round 0: the lanes read each other's descriptors and fill each other's stages
             issue_data(0);
             ba_cp_commit();
             issue_data(1);
@@ -453,6 +495,7 @@ static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_r
 #pragma unroll 1
             for (uint32_t j = 0; j < niter; j++) {
                 ba_cp_wait<1>();            // everything committed before the previous iteration's group has landed
+                if (FIRST) __syncwarp();
                 issue_data(j + 2);          // descriptor j + 2 arrived with the group of iteration j - 2
                 issue_desc(j + 4);
                 ba_cp_commit();
@@ -481,91 +524,161 @@ static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_r
             ba_cp_wait<0>();
         }
         BA_STAMP(1);
+        const size_t total_at = ((size_t)(start / sched.batch)) * 32 + lane;   // uniform batches in the split launches
+        if (PHASE == BA_FWD) {
+            f_st(totals + total_at, run);
+            continue;
+        }
+        if (PHASE == BA_BWD) f_ld(run, totals + total_at);
         // ---- one inversion per lane (branch-free; every lane of the warp takes part) ----
         F inv;
         f_inv_warp(inv, run);
         BA_STAMP(2);
         // ---- backward: slopes and results ----
         {
-            constexpr int ND = SM::BWD_DESC, NS = SM::BWD_STAGES, SCH = SM::BWD_STAGE_CH;
-            auto stage_ch = [&](uint32_t j) { return ND + (int)(j % NS) * SCH; };
+            // shared-memory plan: descriptor ring of 3 (slots j, j - 1 live; j - 2 arriving), TWO stages of {prefix product,
+            // x1, x2} and ONE stage of {y1, y2}: the y coordinates of slot j - 1 are requested in the middle of slot j, right
+            // after slot j has taken its own into registers — three multiplications before they are needed.
+            constexpr int ND = SM::BWD_DESC, XCH = SM::BWD_X_CH, X0 = ND, Y0 = ND + 2 * XCH;
+            auto xstage = [&](uint32_t j) { return X0 + (int)(j & 1u) * XCH; };
+            auto desc_at = [&](uint32_t j) { return *reinterpret_cast<const uint4 *>(ba_shared + ba_chunk((int)(j % ND))); };
             auto issue_desc = [&](uint32_t j) { ba_cp16(sbase + ba_chunk((int)(j % ND)), desc_src(j)); };
-            auto issue_data = [&](uint32_t j) {
-                const uint4 m = *reinterpret_cast<const uint4 *>(ba_shared + ba_chunk((int)(j % ND)));
-                const int c0 = stage_ch(j);
+            auto issue_x = [&](uint32_t j) {   // needs the descriptor of slot j in the ring
+                const uint4 m = desc_at(j);
+                const int c0 = xstage(j);
                 const size_t s = min(slot_of(j), (size_t)last);
 #pragma unroll
                 for (int k = 0; k < FCH; k++) ba_cp16(sbase + ba_chunk(c0 + k), scratch + (size_t)k * scratch_stride + s);
-                ba_cp_field(sbase, c0 + FCH, ba_px<F, FIRST>(io, m.x & IDX));
-                ba_cp_field(sbase, c0 + 2 * FCH, ba_px<F, FIRST>(io, m.y & IDX));
-                if (SM::STAGE_Y) {
-                    ba_cp_field(sbase, c0 + 3 * FCH, ba_py<F, FIRST>(io, m.x & IDX));
-                    ba_cp_field(sbase, c0 + 4 * FCH, ba_py<F, FIRST>(io, m.y & IDX));
-                } else {
-                    ba_prefetch_l2(ba_py<F, FIRST>(io, m.x & IDX));
-                    ba_prefetch_l2(ba_py<F, FIRST>(io, m.y & IDX));
+                if (FIRST) ba_coop_gather<F, FCH>(io.table, ba_shared, sbase, (int)(j % ND), 0, c0 + FCH, c0 + 2 * FCH);
+                else {
+                    ba_cp_field(sbase, c0 + FCH, ba_px<F, FIRST>(io, m.x & IDX));
+                    ba_cp_field(sbase, c0 + 2 * FCH, ba_px<F, FIRST>(io, m.y & IDX));
                 }
-                *reinterpret_cast<uint4 *>(ba_shared + ba_chunk(c0 + SM::BWD_META)) = m;
+            };
+            auto issue_y = [&](uint32_t j) {
+                if (FIRST) { ba_coop_gather<F, FCH>(io.table, ba_shared, sbase, (int)(j % ND), FCH, Y0, Y0 + FCH); return; }
+                const uint4 m = desc_at(j);
+                ba_cp_field(sbase, Y0, ba_py<F, FIRST>(io, m.x & IDX));
+                ba_cp_field(sbase, Y0 + FCH, ba_py<F, FIRST>(io, m.y & IDX));
             };
             issue_desc(niter - 1);
             if (niter >= 2) issue_desc(niter - 2);
             ba_cp_commit();
             ba_cp_wait<0>();
-            issue_data(niter - 1);
+            issue_x(niter - 1);
+            issue_y(niter - 1);
             ba_cp_commit();
 #pragma unroll 1
             for (uint32_t j = niter; j-- > 0;) {
                 ba_cp_wait<0>();            // operands of slot j and the descriptor of slot j - 1 have landed
-                if (j >= 1) issue_data(j - 1);
+                if (FIRST) __syncwarp();    // round 0: ... for every lane of the warp (cooperative gather)
+                if (j >= 1) issue_x(j - 1);
                 if (j >= 2) issue_desc(j - 2);
                 ba_cp_commit();
                 const size_t s = slot_of(j);
-                if (s >= nadds) continue;
-                const int c0 = stage_ch(j);
-                const uint4 m = *reinterpret_cast<const uint4 *>(ba_shared + ba_chunk(c0 + SM::BWD_META));
+                const int c0 = xstage(j);
+                const uint4 m = desc_at(j);
                 F lam, x1, x2, y1, t, d;
+                // The single y stage is refilled for slot j - 1 once slot j has taken its y coordinates into registers.
+                if (FIRST) {
+                    // Round 0 fills the stages cooperatively: EVERY lane (also one past the end of the round) reads both y
+                    // coordinates, the warp synchronises, and only then the refill is issued.
+                    const bool live = s < nadds;
+                    int tag = BA_TAG_INF;
+                    if (live) {
+                        ba_ld_stage(t, ba_shared, c0);
+                        f_mul(lam, inv, t);            // 1 / d when the slot is an addition or a doubling (unused otherwise)
+                        ba_ld_stage(x1, ba_shared, c0 + FCH);
+                        ba_ld_stage(x2, ba_shared, c0 + 2 * FCH);
+                        f_sub(d, x2, x1);
+                        tag = BA_TAG_ADD;
+                        if (f_is_zero(x1) || f_is_zero(x2) || f_is_zero(d)) {
+                            const ba_cold_t<F> c = ba_classify_cold(ba_px<F, FIRST>(io, m.x & IDX), ba_py<F, FIRST>(io, m.x & IDX), (m.x >> 31) != 0,
+                                                                    ba_px<F, FIRST>(io, m.y & IDX), ba_py<F, FIRST>(io, m.y & IDX), (m.y >> 31) != 0);
+                            tag = c.tag;
+                            d = c.d;
+                        }
+                        if (tag <= BA_TAG_DBL && j != 0) f_mul(inv, inv, d);
+                    }
+                    ba_ld_stage(y1, ba_shared, Y0);
+                    ba_ld_stage(t, ba_shared, Y0 + FCH);
+                    __syncwarp();
+                    if (j >= 1) issue_y(j - 1);
+                    ba_cp_commit();
+                    if (!live) continue;
+                    f_cneg(y1, y1, (m.x >> 31) != 0);
+                    f_cneg(t, t, (m.y >> 31) != 0);
+                    if (tag <= BA_TAG_DBL) {
+                        if (tag == BA_TAG_ADD) {
+                            f_sub(t, t, y1);
+                        } else {
+                            f_sqr(t, x1);
+                            f_mul3(t, t);
+                        }
+                        f_mul(lam, lam, t);            // (y2 - y1) / (x2 - x1)   or   3 x1^2 / (2 y1)
+                        f_sqr(t, lam);
+                        f_sub(t, t, x1);
+                        f_sub(t, t, x2);               // x3 = lambda^2 - x1 - x2
+                        f_sub(x1, x1, t);
+                        f_mul(x1, x1, lam);
+                        f_sub(x1, x1, y1);             // y3 = lambda (x1 - x3) - y1
+                        ba_store_point(m.z, io, t, x1);
+                    } else if (tag == BA_TAG_INF) {
+                        f_set_zero(t);
+                        ba_store_point(m.z, io, t, t);
+                    } else if (tag == BA_TAG_COPY_P) {
+                        ba_store_point(m.z, io, x1, y1);
+                    } else {
+                        ba_store_point(m.z, io, x2, t);
+                    }
+                    continue;
+                }
+                // later rounds: every lane copies for itself and reads only what its slot's case needs
+                auto next_y = [&]() {       // exactly once per iteration, once the y stage has been read (or is not needed)
+                    if (j >= 1) issue_y(j - 1);
+                    ba_cp_commit();
+                };
+                if (s >= nadds) { next_y(); continue; }
                 ba_ld_stage(t, ba_shared, c0);
-                f_mul(lam, inv, t);                // 1 / d when the slot is an addition or a doubling (unused otherwise)
+                f_mul(lam, inv, t);
                 ba_ld_stage(x1, ba_shared, c0 + FCH);
                 ba_ld_stage(x2, ba_shared, c0 + 2 * FCH);
                 f_sub(d, x2, x1);
                 int tag = BA_TAG_ADD;
                 if (f_is_zero(x1) || f_is_zero(x2) || f_is_zero(d)) {
-                    const ba_cold_t<F> c = ba_classify_cold(ba_px<F, FIRST>(io, m.x & IDX), ba_py<F, FIRST>(io, m.x & IDX), FIRST && (m.x >> 31),
-                                                            ba_px<F, FIRST>(io, m.y & IDX), ba_py<F, FIRST>(io, m.y & IDX), FIRST && (m.y >> 31));
+                    const ba_cold_t<F> c = ba_classify_cold(ba_px<F, FIRST>(io, m.x & IDX), ba_py<F, FIRST>(io, m.x & IDX), false,
+                                                            ba_px<F, FIRST>(io, m.y & IDX), ba_py<F, FIRST>(io, m.y & IDX), false);
                     tag = c.tag;
                     d = c.d;
                 }
                 if (tag <= BA_TAG_DBL) {
                     if (j != 0) f_mul(inv, inv, d);
-                    if (SM::STAGE_Y) ba_ld_stage(y1, ba_shared, c0 + 3 * FCH);
-                    else f_ld(y1, ba_py<F, FIRST>(io, m.x & IDX));
-                    if (FIRST) f_cneg(y1, y1, (m.x >> 31) != 0);
+                    ba_ld_stage(y1, ba_shared, Y0);
                     if (tag == BA_TAG_ADD) {
-                        if (SM::STAGE_Y) ba_ld_stage(t, ba_shared, c0 + 4 * FCH);
-                        else f_ld(t, ba_py<F, FIRST>(io, m.y & IDX));
-                        if (FIRST) f_cneg(t, t, (m.y >> 31) != 0);
+                        ba_ld_stage(t, ba_shared, Y0 + FCH);
+                        next_y();
                         f_sub(t, t, y1);
                     } else {
+                        next_y();
                         f_sqr(t, x1);
                         f_mul3(t, t);
                     }
-                    f_mul(lam, lam, t);            // (y2 - y1) / (x2 - x1)   or   3 x1^2 / (2 y1)
+                    f_mul(lam, lam, t);
                     f_sqr(t, lam);
                     f_sub(t, t, x1);
-                    f_sub(t, t, x2);               // x3 = lambda^2 - x1 - x2
+                    f_sub(t, t, x2);
                     f_sub(x1, x1, t);
                     f_mul(x1, x1, lam);
-                    f_sub(x1, x1, y1);             // y3 = lambda (x1 - x3) - y1
+                    f_sub(x1, x1, y1);
                     ba_store_point(m.z, io, t, x1);
                 } else if (tag == BA_TAG_INF) {
+                    next_y();
                     f_set_zero(t);
                     ba_store_point(m.z, io, t, t);
                 } else {
                     const bool cp = tag == BA_TAG_COPY_P;
-                    if (SM::STAGE_Y) ba_ld_stage(y1, ba_shared, c0 + (cp ? 3 : 4) * FCH);
-                    else f_ld(y1, ba_py<F, FIRST>(io, (cp ? m.x : m.y) & IDX));
-                    if (FIRST) f_cneg(y1, y1, ((cp ? m.x : m.y) >> 31) != 0);
+                    ba_ld_stage(y1, ba_shared, Y0 + (cp ? 0 : FCH));
+                    next_y();
                     ba_store_point(m.z, io, cp ? x1 : x2, y1);
                 }
             }
@@ -575,6 +688,7 @@ static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_r
     }
     // ---- copies (odd last elements, single-entry buckets): no arithmetic; done last, in the
     // shadow of the blocks that are still adding ----
+    if (PHASE == BA_FWD) return;
     for (size_t ci = (size_t)blockIdx.x * BA_THREADS + threadIdx.x; ci < ncopies; ci += (size_t)gridDim.x * BA_THREADS) {
         const uint2 dsc = cdesc[ci];
         F x, y;

@@ -132,20 +132,30 @@ static int ba_accumulate(Ctx *c, const aff_t<F> *d_table, uint32_t *count, size_
     MSM_CUDA(c, cudaEventRecord(c->ev[2], st));
     // ---- arithmetic rounds ----
     if (c->ba_resident <= 0) {
-        int nbk = 0;
-        MSM_CUDA(c, cudaFuncSetAttribute(ba_round_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba_smem<F>::BYTES));
-        MSM_CUDA(c, cudaFuncSetAttribute(ba_round_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba_smem<F>::BYTES));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, ba_round_kernel<F, false>, BA_THREADS, ba_smem<F>::BYTES) != cudaSuccess || nbk < 1) nbk = 2;
-        c->ba_resident = nbk;
+        auto resident = [&](auto kern, int bytes) {
+            int nbk = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, kern, BA_THREADS, bytes) != cudaSuccess || nbk < 1) nbk = 2;
+            return nbk;
+        };
+#define BA_SMEM_ATTR(FIRST_, PHASE_) MSM_CUDA(c, cudaFuncSetAttribute(ba_round_kernel<F, FIRST_, PHASE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba_smem<F>::bytes(PHASE_)))
+        BA_SMEM_ATTR(true, BA_FUSED); BA_SMEM_ATTR(false, BA_FUSED); BA_SMEM_ATTR(true, BA_FWD); BA_SMEM_ATTR(false, BA_FWD); BA_SMEM_ATTR(true, BA_BWD); BA_SMEM_ATTR(false, BA_BWD);
+#undef BA_SMEM_ATTR
+        c->ba_resident = resident(ba_round_kernel<F, false, BA_FUSED>, ba_smem<F>::bytes(BA_FUSED));
+        c->ba_resident_fwd = resident(ba_round_kernel<F, false, BA_FWD>, ba_smem<F>::bytes(BA_FWD));
+        c->ba_resident_bwd = resident(ba_round_kernel<F, false, BA_BWD>, ba_smem<F>::bytes(BA_BWD));
     }
-    const size_t wave = (size_t)c->sms * c->ba_resident;   // co-resident blocks: the round kernel is persistent
+    const bool split = c->ba_split != 0;
+    const size_t wave = (size_t)c->sms * (split ? c->ba_resident_bwd : c->ba_resident);   // co-resident blocks: the round kernel is persistent
+    const size_t wave_fwd = (size_t)c->sms * c->ba_resident_fwd;
     const size_t nwarps = wave * (BA_THREADS / 32);
-    if (ensure(c, c->ba_counters, (BA_RMAX + 1) * 4)) return MSMB200_ECUDA;
+    const int batch_max = split ? c->ba_batch_max_split : c->ba_batch_max;
+    if (ensure(c, c->ba_counters, 2 * (BA_RMAX + 1) * 4)) return MSMB200_ECUDA;
     if (!c->ba_sm_arrivals.p) {
         if (ensure(c, c->ba_sm_arrivals, 1024 * 4)) return MSMB200_ECUDA;
         MSM_CUDA(c, cudaMemsetAsync(c->ba_sm_arrivals.p, 0, 1024 * 4, st));
     }
-    MSM_CUDA(c, cudaMemsetAsync(c->ba_counters.p, 0, (BA_RMAX + 1) * 4, st));
+    MSM_CUDA(c, cudaMemsetAsync(c->ba_counters.p, 0, 2 * (BA_RMAX + 1) * 4, st));
+    if (split && ensure(c, c->ba_lane_totals, ((((size_t)T[0] + 31) / 32) + 1) * 32 * sizeof(F))) return MSMB200_ECUDA;   // at most one lane row per slot row
     // ping-pong point buffers between rounds, x[] and y[] separate: round r reads buffer r & 1 and writes buffer (r + 1) & 1
     F *bx[2] = {(F *)c->pts_b.p, (F *)c->pts_a.p};
     F *by[2] = {(F *)c->pts_b.p + e_even, (F *)c->pts_a.p + e_odd};
@@ -154,10 +164,10 @@ static int ba_accumulate(Ctx *c, const aff_t<F> *d_table, uint32_t *count, size_
         BaSched sched;
         sched.rows = (A + 31) / 32;
         const size_t share = (sched.rows + nwarps - 1) / nwarps;   // rows per warp if the round were split evenly
-        if (share > (size_t)c->ba_batch_max) {   // several batches per warp: equal full batches, staggered start, shrinking tail
-            const size_t nb_ = (share + c->ba_batch_max - 1) / c->ba_batch_max;
+        if (share > (size_t)batch_max) {   // several batches per warp: equal full batches (fused: staggered start, shrinking tail)
+            const size_t nb_ = (share + batch_max - 1) / batch_max;
             sched.batch = (uint32_t)((share + nb_ - 1) / nb_);
-            sched.stagger = c->ba_stagger ? 1u : 0u;
+            sched.stagger = !split && c->ba_stagger ? 1u : 0u;
         } else {
             sched.batch = (uint32_t)std::max<size_t>(1, share);
             sched.stagger = 0;
@@ -176,11 +186,25 @@ static int ba_accumulate(Ctx *c, const aff_t<F> *d_table, uint32_t *count, size_
         io.in_x = bx[r & 1]; io.in_y = by[r & 1];
         io.out_x = bx[(r + 1) & 1]; io.out_y = by[(r + 1) & 1];
         io.bucket_sum = (aff_t<F> *)c->bucket_sum.p;
-        if (r == 0)
-            ba_round_kernel<F, true><<<grid, BA_THREADS, ba_smem<F>::BYTES, st>>>(io, ad, A, cd, Cn, (uint4 *)c->ba_scratch.p, scratch_stride, sched, r);
-        else
-            ba_round_kernel<F, false><<<grid, BA_THREADS, ba_smem<F>::BYTES, st>>>(io, ad, A, cd, Cn, (uint4 *)c->ba_scratch.p, scratch_stride, sched, r);
-        c->launches += 1;
+        uint4 *scr = (uint4 *)c->ba_scratch.p;
+        F *lt = (F *)c->ba_lane_totals.p;
+#define BA_LAUNCH(FIRST_, PHASE_, GRID_, SCHED_) \
+    ba_round_kernel<F, FIRST_, PHASE_><<<GRID_, BA_THREADS, ba_smem<F>::bytes(PHASE_), st>>>(io, ad, A, cd, Cn, scr, scratch_stride, SCHED_, r, lt)
+        if (split && A != 0) {
+            BaSched sf = sched;
+            sf.counter = (uint32_t *)c->ba_counters.p + (BA_RMAX + 1) + r;
+            const unsigned grid_f = (unsigned)std::max<size_t>(1, std::min<size_t>(wave_fwd, add_blocks));
+            if (r == 0) { BA_LAUNCH(true, BA_FWD, grid_f, sf); BA_LAUNCH(true, BA_BWD, grid, sched); }
+            else { BA_LAUNCH(false, BA_FWD, grid_f, sf); BA_LAUNCH(false, BA_BWD, grid, sched); }
+            c->launches += 2;
+        } else if (split) {   // copies only
+            if (r == 0) BA_LAUNCH(true, BA_BWD, grid, sched); else BA_LAUNCH(false, BA_BWD, grid, sched);
+            c->launches += 1;
+        } else {
+            if (r == 0) BA_LAUNCH(true, BA_FUSED, grid, sched); else BA_LAUNCH(false, BA_FUSED, grid, sched);
+            c->launches += 1;
+        }
+#undef BA_LAUNCH
     }
     MSM_CUDA(c, cudaGetLastError());
     return MSMB200_OK;

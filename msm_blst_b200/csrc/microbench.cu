@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
+#include <string>
 #include <vector>
 #include <cuda_runtime.h>
 #include "ec.cuh"
@@ -187,11 +188,82 @@ static void run(const char *name, double ops_per_thread, int blocks, int threads
            name, blocks, threads, best, total / best / 1e6, per_clk_sm, avg / best / 1e3, last ? "" : ",");
 }
 
-int main() {
+
+// ---- random table gather (the access pattern of the bucket accumulation): every thread reads BYTES bytes (16-byte vector
+// loads) at offset OFF inside an entry of STRIDE bytes chosen by a hash of (thread, iteration) from a table of `entries`
+// entries; UNROLL independent entries in flight per thread. Reports useful GB/s; run under
+// `ncu --metrics dram__bytes_read.sum` to see what the memory system really fetched per entry.
+template <int BYTES, int UNROLL>
+__global__ void k_gather(const uint4 *__restrict__ table, size_t entries, int stride16, int off16, int iters, uint4 *out) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    uint64_t h = (uint64_t)tid * 0x9E3779B97F4A7C15ull + 12345;
+#pragma unroll 1
+    for (int i = 0; i < iters; i += UNROLL) {
+        uint4 v[UNROLL][BYTES / 16];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            h = h * 6364136223846793005ull + 1442695040888963407ull;
+            const size_t e = (size_t)((h >> 20) % entries);
+            const uint4 *p = table + e * (size_t)stride16 + off16;
+#pragma unroll
+            for (int k = 0; k < BYTES / 16; k++) v[u][k] = __ldg(p + k);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+            for (int k = 0; k < BYTES / 16; k++) { acc.x ^= v[u][k].x; acc.y += v[u][k].y; acc.z ^= v[u][k].z; acc.w += v[u][k].w; }
+    }
+    out[tid] = acc;
+}
+template <int BYTES, int UNROLL>
+static void run_gather(const char *name, const uint4 *table, size_t table_bytes, int stride, int off, uint4 *out, int sms, bool last) {
+    const size_t entries = table_bytes / stride;
+    const int blocks = sms * 8, threads = 256, iters = 512;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    k_gather<BYTES, UNROLL><<<blocks, threads>>>(table, entries, stride / 16, off / 16, iters, out);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+        CK(cudaEventRecord(e0));
+        k_gather<BYTES, UNROLL><<<blocks, threads>>>(table, entries, stride / 16, off / 16, iters, out);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    const double n = (double)blocks * threads * iters;
+    printf("  \"%s\": {\"bytes_per_entry\": %d, \"stride\": %d, \"offset\": %d, \"in_flight_per_thread\": %d, \"ms\": %.4f, \"M_entries_per_s\": %.1f, \"useful_GB_s\": %.1f}%s\n",
+           name, BYTES, stride, off, UNROLL, best, n / best / 1e3, n * BYTES / best / 1e6, last ? "" : ",");
+}
+static int gather_main(int sms) {
+    const size_t bytes = (size_t)8 << 30;   // 8 GB: far beyond the 126 MB L2, like the 7.25 GB CHES table
+    uint4 *table, *out;
+    CK(cudaMalloc(&table, bytes));
+    CK(cudaMemset(table, 1, bytes));
+    CK(cudaMalloc(&out, (size_t)sms * 8 * 256 * 16));
+    printf("{\n");
+    run_gather<96, 2>("entry96_stride96_full", table, bytes, 96, 0, out, sms, false);        // the shipped table: {x, y} at 96 k
+    run_gather<48, 4>("entry96_stride96_x_only", table, bytes, 96, 0, out, sms, false);      // forward pass: x only
+    run_gather<96, 2>("entry96_stride128_full", table, bytes, 128, 0, out, sms, false);      // entries padded to one 128-byte line
+    run_gather<48, 4>("entry96_stride128_x_only", table, bytes, 128, 0, out, sms, false);
+    run_gather<48, 4>("entry48_stride64_aligned", table, bytes, 64, 0, out, sms, false);     // separate x table, 64-byte slots
+    run_gather<32, 4>("sector32_stride32", table, bytes, 32, 0, out, sms, false);
+    run_gather<64, 4>("line64_stride64", table, bytes, 64, 0, out, sms, false);
+    run_gather<128, 2>("line128_stride128", table, bytes, 128, 0, out, sms, false);
+    run_gather<192, 1>("g2_entry192_stride192", table, bytes, 192, 0, out, sms, false);
+    run_gather<192, 1>("g2_entry192_stride256", table, bytes, 256, 0, out, sms, true);
+    printf("}\n");
+    return 0;
+}
+
+int main(int argc, char **argv) {
     int dev = 0;
     CK(cudaSetDevice(dev));
     cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, dev));
     int sms = pr.multiProcessorCount;
+    if (argc > 1 && std::string(argv[1]) == "gather") return gather_main(sms);
     long long *d_cyc; CK(cudaMalloc(&d_cyc, sizeof(long long) * sms * 64));
     void *d_out; CK(cudaMalloc(&d_out, (size_t)sms * 64 * 1024 * 192));
     // field inputs: arbitrary residues (Montgomery form of something) — take multiples of ONE via adds on host? use raw
