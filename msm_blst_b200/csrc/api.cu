@@ -45,7 +45,6 @@ std::vector<int> build_chunk_first(const int *values, size_t count, uint32_t vsp
     return cf;
 }
 uint32_t pick_vspan_host(size_t max_value, uint32_t nwindows) {
-    if (const char *e = getenv("MSMB200_VSPAN")) return (uint32_t)atoi(e);
     // ~32 K chunks in total (measured optimum on B200: G1 n=2^21 -> 64, G2 n=2^18 -> 16), 8 <= v <= 64, power of two
     uint32_t v = 8;
     while (v < 64 && ((max_value + 1) * nwindows + v - 1) / v > 32768 + 1024) v <<= 1;
@@ -165,9 +164,8 @@ static void compute_reduce_plan(HostReducePlan &H, const int *values, size_t nbw
     H.nbits_w = nbits;
 }
 int build_reduce_plan(Ctx *c, ReducePlan &plan, const int *values, size_t nbw, uint32_t nwindows) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    plan.s1_coop = getenv("MSMB200_S1COOP") && atoi(getenv("MSMB200_S1COOP")) != 0;
+    const int sms = c->sms;
+    plan.s1_coop = false;
     HostReducePlan H;
     compute_reduce_plan(H, values, nbw, nwindows, 4 * sms, c->ops->resident_blocks(0), c->ops->resident_blocks(1), c->ops->resident_blocks(2),
                         plan.s1_coop);
@@ -202,6 +200,8 @@ static int ctx_init_common(Ctx *c, int group, int device) {
     if (const char *e = getenv("MSMB200_ACCUM")) c->accum_env = atoi(e);
     if (const char *e = getenv("MSMB200_REDUCE")) c->reduce_env = atoi(e);
     if (const char *e = getenv("MSMB200_BA_BATCH_MAX")) c->ba_batch_max = std::max(1, atoi(e));
+    if (const char *e = getenv("MSMB200_VSPAN")) c->vspan_env = std::max(0, atoi(e));
+    c->no_overlap = getenv("MSMB200_NO_OVERLAP") != nullptr;
     return MSMB200_OK;
 }
 
@@ -214,7 +214,7 @@ static void ctx_release(Ctx *c) {
                       &c->item_start, &c->cursor, &c->item_begin, &c->item_cnt, &c->order, &c->len_hist, &c->len_start, &c->len_cursor,
                       &c->partial, &c->chunk_a, &c->chunk_b, &c->result, &c->flat, &c->signs, &c->pidx, &c->heavy, &c->light, &c->medium,
                       &c->ba_totals, &c->ba_tile_sums, &c->ba_bases, &c->ba_adesc, &c->ba_cdesc, &c->ba_heavy, &c->pts_a, &c->pts_b, &c->ba_scratch,
-                      &c->bucket_sum, &c->iota, &c->ba_counters, &c->ba_sm_arrivals, &c->ba_lane_totals, &c->maxcount, &c->red_a, &c->red_b, &c->red_c, &c->red_d};
+                      &c->bucket_sum, &c->iota, &c->ba_counters, &c->ba_sm_arrivals, &c->maxcount, &c->red_a, &c->red_b, &c->red_c, &c->red_d};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     free_reduce_plan(c->plan_ches); free_reduce_plan(c->plan_bgmw); free_reduce_plan(c->plan_pip);
     void *ptrs[] = {c->d_bucket_vals, c->d_v2i, c->d_dtab, c->d_chunk_first, c->d_points, c->d_table_ches, c->d_table_bgmw};
@@ -312,7 +312,7 @@ int msmb200_host_reduce_plan_eval(const int *values, size_t nbw, int resident_st
                                   uint64_t *out, uint32_t *out_info) {
     if (nbw < 2 || !x || !out || resident_stage1 < 1 || resident_coop < 1 || groups_per_warp < 1) return MSMB200_EINVAL;
     HostReducePlan H;
-    compute_reduce_plan(H, values, nbw, 1, 4 * 148, resident_stage1, resident_coop, groups_per_warp, false);
+    compute_reduce_plan(H, values, nbw, 1, 4 * 148 /* the B200 shape the CPU tests evaluate plans for */, resident_stage1, resident_coop, groups_per_warp, false);
     auto run = [](const HostListPlan &lp, const std::vector<uint64_t> &in) {
         std::vector<uint64_t> o(lp.start.size() - 1, 0);
         for (size_t i = 0; i + 1 < lp.start.size(); i++)
@@ -370,7 +370,7 @@ int msmb200_ctx_create(msmb200_ctx **out, int group, const msmb200_config *cfg, 
     CREATE_CUDA(cudaMalloc(&c->d_bucket_vals, c->bucket_set.size() * sizeof(int)));
     CREATE_CUDA(cudaMalloc(&c->d_v2i, v2i.size() * sizeof(int)));
     CREATE_CUDA(cudaMalloc(&c->d_dtab, dtab.size() * sizeof(uint32_t)));
-    c->red_vspan = pick_vspan_host((size_t)c->bucket_set.back(), 1);
+    c->red_vspan = c->vspan_env ? (uint32_t)c->vspan_env : pick_vspan_host((size_t)c->bucket_set.back(), 1);
     std::vector<int> cf = build_chunk_first(c->bucket_set.data(), c->bucket_set.size(), c->red_vspan, &c->red_nchunks);
     c->h_chunk_first = cf;
     CREATE_CUDA(cudaMalloc(&c->d_chunk_first, cf.size() * sizeof(int)));
@@ -425,8 +425,6 @@ int msmb200_set_tuning(msmb200_ctx *ctx, const char *key, int value) {
     if (k == "ba_batch_max") c->ba_batch_max = std::max(1, value);
     else if (k == "ba_batch") c->ba_batch_fixed = value;
     else if (k == "ba_stagger") c->ba_stagger = value;
-    else if (k == "ba_split") c->ba_split = value;
-    else if (k == "ba_batch_max_split") c->ba_batch_max_split = std::max(1, value);
     else if (k == "item_len") c->item_len_fixed = value;
     else return ctx_fail(c, MSMB200_EINVAL, "unknown tuning key " + k);
     return MSMB200_OK;
@@ -610,7 +608,7 @@ int msmb200_msm(msmb200_ctx *ctx, int method, const void *scalars_host, void *ou
     Ctx *c = C(ctx);
     MSM_CUDA(c, cudaSetDevice(c->device));
     if (ensure(c, c->scalars, c->n * 32)) return MSMB200_ECUDA;
-    if (method == MSMB200_CHES && !getenv("MSMB200_NO_OVERLAP")) {
+    if (method == MSMB200_CHES && !c->no_overlap) {
         // chunked upload overlapped with the digit decomposition (msm_impl)
         c->h_scalars_pending = scalars_host;
         int rc = c->ops->msm(c, method, c->scalars.p, nullptr, true);

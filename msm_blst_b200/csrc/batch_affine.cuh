@@ -29,7 +29,6 @@ constexpr int BA_RMAX = 32;                   // rounds: counts are < 2^32
 constexpr uint32_t BA_FINAL = 0x80000000u;    // output descriptor: bucket_sum[b] instead of the next round's buffer
 constexpr uint32_t BA_HEAVY = 2048;           // buckets with more entries are planned by a whole block
 constexpr int BA_THREADS = 128;
-enum { BA_FWD = 0, BA_BWD = 1, BA_FUSED = 2 };   // what one launch of ba_round_kernel does (see there)
 // resident blocks per SM the round kernel is compiled for (register budget 65536 / (128 x blocks) per thread)
 #ifndef BA_MIN_BLOCKS_FP
 #define BA_MIN_BLOCKS_FP 4
@@ -37,16 +36,7 @@ enum { BA_FWD = 0, BA_BWD = 1, BA_FUSED = 2 };   // what one launch of ba_round_
 #ifndef BA_MIN_BLOCKS_FP2
 #define BA_MIN_BLOCKS_FP2 2
 #endif
-#ifndef BA_MIN_BLOCKS_FWD_FP
-#define BA_MIN_BLOCKS_FWD_FP 4
-#endif
-#ifndef BA_MIN_BLOCKS_FWD_FP2
-#define BA_MIN_BLOCKS_FWD_FP2 2
-#endif
-template <class F> struct ba_cfg {
-    static constexpr int MIN_BLOCKS = sizeof(F) > 48 ? BA_MIN_BLOCKS_FP2 : BA_MIN_BLOCKS_FP;
-    static constexpr int MIN_BLOCKS_FWD = sizeof(F) > 48 ? BA_MIN_BLOCKS_FWD_FP2 : BA_MIN_BLOCKS_FWD_FP;   // forward-only launch
-};
+template <class F> struct ba_cfg { static constexpr int MIN_BLOCKS = sizeof(F) > 48 ? BA_MIN_BLOCKS_FP2 : BA_MIN_BLOCKS_FP; };
 
 // filled by the host once the per-round totals are known
 struct BaRounds {
@@ -267,7 +257,6 @@ template <class F2> __device__ __forceinline__ void f_inv_warp_fp2(F2 &r, const 
     fp_neg(r.c1, t0);
 }
 __device__ __forceinline__ void f_inv_warp(fp2_t &r, const fp2_t &a) { f_inv_warp_fp2(r, a); }
-__device__ __forceinline__ void f_inv_warp(fp2v_t &r, const fp2v_t &a) { f_inv_warp_fp2(r, a); }
 
 template <class F> __device__ __forceinline__ void f_ld(F &r, const F *p) {
     const uint4 *s = reinterpret_cast<const uint4 *>(p);
@@ -404,8 +393,6 @@ template <class F> struct ba_smem {
     static constexpr int FWD_CH = FWD_DESC + FWD_STAGES * FWD_STAGE_CH, BWD_CH = BWD_DESC + 2 * BWD_X_CH + 2 * FCH;
     // Fp: 25 / 27 chunks of 2 KB -> 54 KB per block, 4 blocks (16 warps) per SM; Fp2: 43 / 51 chunks -> 102 KB, 2 blocks
     static constexpr int BYTES = (FWD_CH > BWD_CH ? FWD_CH : BWD_CH) * BA_THREADS * 16;
-    static constexpr int BYTES_FWD = FWD_CH * BA_THREADS * 16, BYTES_BWD = BWD_CH * BA_THREADS * 16;
-    static constexpr int bytes(int phase) { return phase == BA_FWD ? BYTES_FWD : phase == BA_BWD ? BYTES_BWD : BYTES; }
 };
 
 // Work distribution of one round. The kernel is PERSISTENT (`grid` = the co-resident blocks) and every WARP is an
@@ -424,16 +411,10 @@ struct BaSched {
 };
 __device__ __forceinline__ uint32_t ba_smid() { uint32_t r; asm("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 
-// PHASE: BA_FUSED = forward, inversion and backward pass of a batch by the same warp (phases of different warps overlap);
-// BA_FWD / BA_BWD = the round as TWO launches: the forward pass alone is bound by DRAM (one multiplication per slot, two
-// random 48-byte reads), inversion + backward pass by the multiplier, so each launch runs against ONE limit with every
-// resident warp in the same regime. Uniform batches (batch k = rows [k * batch, (k + 1) * batch)), lane totals handed over
-// in `totals[k * 32 + lane]`.
-template <class F, bool FIRST, int PHASE>
-static __global__ void __launch_bounds__(BA_THREADS, (PHASE == BA_FWD ? ba_cfg<F>::MIN_BLOCKS_FWD : ba_cfg<F>::MIN_BLOCKS)) ba_round_kernel(ba_io<F> io, const uint4 *__restrict__ adesc, uint32_t nadds,
+template <class F, bool FIRST>
+static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_round_kernel(ba_io<F> io, const uint4 *__restrict__ adesc, uint32_t nadds,
                                                                      const uint2 *__restrict__ cdesc, uint32_t ncopies,
-                                                                     uint4 *__restrict__ scratch, size_t scratch_stride, BaSched sched, uint32_t round,
-                                                                     F *__restrict__ totals) {
+                                                                     uint4 *__restrict__ scratch, size_t scratch_stride, BaSched sched, uint32_t round) {
     using SM = ba_smem<F>;
     constexpr int FCH = SM::FCH;
     constexpr uint32_t IDX = 0x7fffffffu;
@@ -449,7 +430,7 @@ static __global__ void __launch_bounds__(BA_THREADS, (PHASE == BA_FWD ? ba_cfg<F
         uint32_t start = 0, n = 0;
         if (lane == 0) {
             n = sched.batch;
-            if (PHASE == BA_FUSED && sched.stagger) {
+            if (sched.stagger) {
                 if (first_batch) n = max(1u, (n * (sh_k + 1u)) / 3u);
                 const uint32_t seen = *(volatile uint32_t *)sched.counter;
                 const uint32_t left = seen < sched.rows ? sched.rows - seen : 0u;
@@ -469,7 +450,7 @@ static __global__ void __launch_bounds__(BA_THREADS, (PHASE == BA_FWD ? ba_cfg<F
         // ---- forward: denominators and their running product ----
         F run;
         f_set_one(run);
-        if (PHASE != BA_BWD) {
+        {
             constexpr int ND = SM::FWD_DESC, NS = SM::FWD_STAGES, SCH = SM::FWD_STAGE_CH;
             auto stage_ch = [&](uint32_t j) { return ND + (int)(j % NS) * SCH; };
             auto issue_desc = [&](uint32_t j) { ba_cp16(sbase + ba_chunk((int)(j % ND)), desc_src(j)); };
@@ -524,12 +505,6 @@ static __global__ void __launch_bounds__(BA_THREADS, (PHASE == BA_FWD ? ba_cfg<F
             ba_cp_wait<0>();
         }
         BA_STAMP(1);
-        const size_t total_at = ((size_t)(start / sched.batch)) * 32 + lane;   // uniform batches in the split launches
-        if (PHASE == BA_FWD) {
-            f_st(totals + total_at, run);
-            continue;
-        }
-        if (PHASE == BA_BWD) f_ld(run, totals + total_at);
         // ---- one inversion per lane (branch-free; every lane of the warp takes part) ----
         F inv;
         f_inv_warp(inv, run);
@@ -688,7 +663,6 @@ static __global__ void __launch_bounds__(BA_THREADS, (PHASE == BA_FWD ? ba_cfg<F
     }
     // ---- copies (odd last elements, single-entry buckets): no arithmetic; done last, in the
     // shadow of the blocks that are still adding ----
-    if (PHASE == BA_FWD) return;
     for (size_t ci = (size_t)blockIdx.x * BA_THREADS + threadIdx.x; ci < ncopies; ci += (size_t)gridDim.x * BA_THREADS) {
         const uint2 dsc = cdesc[ci];
         F x, y;

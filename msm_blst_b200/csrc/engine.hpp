@@ -69,12 +69,12 @@ struct Ctx {
         flat, signs, pidx, heavy, light, medium, maxcount;
     // batch-affine accumulation (batch_affine.cuh): per-round totals / scans / slot descriptors, ping-pong point buffers, the
     // prefix-product scratch, one affine sum per bucket, identity index for the reducers
-    DevBuf ba_totals, ba_tile_sums, ba_bases, ba_adesc, ba_cdesc, ba_heavy, pts_a, pts_b, ba_scratch, bucket_sum, iota, ba_counters, ba_sm_arrivals, ba_lane_totals;
+    DevBuf ba_totals, ba_tile_sums, ba_bases, ba_adesc, ba_cdesc, ba_heavy, pts_a, pts_b, ba_scratch, bucket_sum, iota, ba_counters, ba_sm_arrivals;
     uint32_t *h_totals = nullptr;   // pinned read-back of ba_totals
     size_t iota_n = 0;
     int ba_resident = 0;            // co-resident ba_round_kernel blocks per SM (occupancy query, cached)
-    int ba_resident_fwd = 0, ba_resident_bwd = 0;   // the same for the forward-only and the inversion + backward launches
-    int ba_split = 0, ba_batch_max_split = 110;      // each round as two launches (forward | inversion + backward); slots per lane per batch there
+    int vspan_env = 0;              // MSMB200_VSPAN at creation (0: automatic)
+    bool no_overlap = false;        // MSMB200_NO_OVERLAP at creation: upload all scalars before the first kernel
     int ba_batch_max = 110, ba_batch_fixed = 0, ba_stagger = 1;  // slots per lane per round: upper bound / forced value (MSMB200_BA_BATCH at creation)
     int sms = 148;                  // cudaDevAttrMultiProcessorCount of the context's device
     int item_len_fixed = 0;         // XYZZ work-item length override (0 = automatic)

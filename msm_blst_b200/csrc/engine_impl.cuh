@@ -55,20 +55,12 @@ static inline void shard_slice(const Ctx *c, uint32_t nchunks, uint32_t *chunk_l
 }
 
 // value span of a reduction chunk: aim at ~32 K chunks in total, between 8 and 64 values per chunk
-static inline uint32_t pick_vspan(size_t max_value, uint32_t nwindows) {
-    if (const char *e = getenv("MSMB200_VSPAN")) return (uint32_t)atoi(e);
+static inline uint32_t pick_vspan(const Ctx *c, size_t max_value, uint32_t nwindows) {
+    if (c->vspan_env) return (uint32_t)c->vspan_env;
     // ~32 K chunks in total (measured optimum on B200: G1 n=2^21 -> 64, G2 n=2^18 -> 16), 8 <= v <= 64, power of two
     uint32_t v = 8;
     while (v < 64 && ((max_value + 1) * nwindows + v - 1) / v > 32768 + 1024) v <<= 1;
     return v;
-}
-
-// experimental register-resident G2 accumulator (fp2v_t: inlined Fp2 operations); a no-op for G1
-template <class F> static inline void launch_accumulate_regacc(unsigned, cudaStream_t, const void *, const uint32_t *, const uint32_t *, const uint32_t *,
-                                                              const uint32_t *, const uint64_t *, void *) {}
-template <> inline void launch_accumulate_regacc<fp2_t>(unsigned grid, cudaStream_t st, const void *table, const uint32_t *sorted, const uint32_t *item_begin,
-                                                        const uint32_t *item_cnt, const uint32_t *order, const uint64_t *totals, void *partial) {
-    accumulate_kernel<fp2v_t><<<grid, 128, 0, st>>>((const aff_t<fp2v_t> *)table, sorted, item_begin, item_cnt, order, totals, (xyzz_t<fp2v_t> *)partial);
 }
 
 static __global__ void iota_kernel(uint32_t *out, size_t n) {
@@ -132,30 +124,20 @@ static int ba_accumulate(Ctx *c, const aff_t<F> *d_table, uint32_t *count, size_
     MSM_CUDA(c, cudaEventRecord(c->ev[2], st));
     // ---- arithmetic rounds ----
     if (c->ba_resident <= 0) {
-        auto resident = [&](auto kern, int bytes) {
-            int nbk = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, kern, BA_THREADS, bytes) != cudaSuccess || nbk < 1) nbk = 2;
-            return nbk;
-        };
-#define BA_SMEM_ATTR(FIRST_, PHASE_) MSM_CUDA(c, cudaFuncSetAttribute(ba_round_kernel<F, FIRST_, PHASE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba_smem<F>::bytes(PHASE_)))
-        BA_SMEM_ATTR(true, BA_FUSED); BA_SMEM_ATTR(false, BA_FUSED); BA_SMEM_ATTR(true, BA_FWD); BA_SMEM_ATTR(false, BA_FWD); BA_SMEM_ATTR(true, BA_BWD); BA_SMEM_ATTR(false, BA_BWD);
-#undef BA_SMEM_ATTR
-        c->ba_resident = resident(ba_round_kernel<F, false, BA_FUSED>, ba_smem<F>::bytes(BA_FUSED));
-        c->ba_resident_fwd = resident(ba_round_kernel<F, false, BA_FWD>, ba_smem<F>::bytes(BA_FWD));
-        c->ba_resident_bwd = resident(ba_round_kernel<F, false, BA_BWD>, ba_smem<F>::bytes(BA_BWD));
+        int nbk = 0;
+        MSM_CUDA(c, cudaFuncSetAttribute(ba_round_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba_smem<F>::BYTES));
+        MSM_CUDA(c, cudaFuncSetAttribute(ba_round_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba_smem<F>::BYTES));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, ba_round_kernel<F, false>, BA_THREADS, ba_smem<F>::BYTES) != cudaSuccess || nbk < 1) nbk = 2;
+        c->ba_resident = nbk;
     }
-    const bool split = c->ba_split != 0;
-    const size_t wave = (size_t)c->sms * (split ? c->ba_resident_bwd : c->ba_resident);   // co-resident blocks: the round kernel is persistent
-    const size_t wave_fwd = (size_t)c->sms * c->ba_resident_fwd;
+    const size_t wave = (size_t)c->sms * c->ba_resident;   // co-resident blocks: the round kernel is persistent
     const size_t nwarps = wave * (BA_THREADS / 32);
-    const int batch_max = split ? c->ba_batch_max_split : c->ba_batch_max;
-    if (ensure(c, c->ba_counters, 2 * (BA_RMAX + 1) * 4)) return MSMB200_ECUDA;
+    if (ensure(c, c->ba_counters, (BA_RMAX + 1) * 4)) return MSMB200_ECUDA;
     if (!c->ba_sm_arrivals.p) {
         if (ensure(c, c->ba_sm_arrivals, 1024 * 4)) return MSMB200_ECUDA;
         MSM_CUDA(c, cudaMemsetAsync(c->ba_sm_arrivals.p, 0, 1024 * 4, st));
     }
-    MSM_CUDA(c, cudaMemsetAsync(c->ba_counters.p, 0, 2 * (BA_RMAX + 1) * 4, st));
-    if (split && ensure(c, c->ba_lane_totals, ((((size_t)T[0] + 31) / 32) + 1) * 32 * sizeof(F))) return MSMB200_ECUDA;   // at most one lane row per slot row
+    MSM_CUDA(c, cudaMemsetAsync(c->ba_counters.p, 0, (BA_RMAX + 1) * 4, st));
     // ping-pong point buffers between rounds, x[] and y[] separate: round r reads buffer r & 1 and writes buffer (r + 1) & 1
     F *bx[2] = {(F *)c->pts_b.p, (F *)c->pts_a.p};
     F *by[2] = {(F *)c->pts_b.p + e_even, (F *)c->pts_a.p + e_odd};
@@ -164,10 +146,10 @@ static int ba_accumulate(Ctx *c, const aff_t<F> *d_table, uint32_t *count, size_
         BaSched sched;
         sched.rows = (A + 31) / 32;
         const size_t share = (sched.rows + nwarps - 1) / nwarps;   // rows per warp if the round were split evenly
-        if (share > (size_t)batch_max) {   // several batches per warp: equal full batches (fused: staggered start, shrinking tail)
-            const size_t nb_ = (share + batch_max - 1) / batch_max;
+        if (share > (size_t)c->ba_batch_max) {   // several batches per warp: equal full batches, staggered start, shrinking tail
+            const size_t nb_ = (share + c->ba_batch_max - 1) / c->ba_batch_max;
             sched.batch = (uint32_t)((share + nb_ - 1) / nb_);
-            sched.stagger = !split && c->ba_stagger ? 1u : 0u;
+            sched.stagger = c->ba_stagger ? 1u : 0u;
         } else {
             sched.batch = (uint32_t)std::max<size_t>(1, share);
             sched.stagger = 0;
@@ -186,25 +168,11 @@ static int ba_accumulate(Ctx *c, const aff_t<F> *d_table, uint32_t *count, size_
         io.in_x = bx[r & 1]; io.in_y = by[r & 1];
         io.out_x = bx[(r + 1) & 1]; io.out_y = by[(r + 1) & 1];
         io.bucket_sum = (aff_t<F> *)c->bucket_sum.p;
-        uint4 *scr = (uint4 *)c->ba_scratch.p;
-        F *lt = (F *)c->ba_lane_totals.p;
-#define BA_LAUNCH(FIRST_, PHASE_, GRID_, SCHED_) \
-    ba_round_kernel<F, FIRST_, PHASE_><<<GRID_, BA_THREADS, ba_smem<F>::bytes(PHASE_), st>>>(io, ad, A, cd, Cn, scr, scratch_stride, SCHED_, r, lt)
-        if (split && A != 0) {
-            BaSched sf = sched;
-            sf.counter = (uint32_t *)c->ba_counters.p + (BA_RMAX + 1) + r;
-            const unsigned grid_f = (unsigned)std::max<size_t>(1, std::min<size_t>(wave_fwd, add_blocks));
-            if (r == 0) { BA_LAUNCH(true, BA_FWD, grid_f, sf); BA_LAUNCH(true, BA_BWD, grid, sched); }
-            else { BA_LAUNCH(false, BA_FWD, grid_f, sf); BA_LAUNCH(false, BA_BWD, grid, sched); }
-            c->launches += 2;
-        } else if (split) {   // copies only
-            if (r == 0) BA_LAUNCH(true, BA_BWD, grid, sched); else BA_LAUNCH(false, BA_BWD, grid, sched);
-            c->launches += 1;
-        } else {
-            if (r == 0) BA_LAUNCH(true, BA_FUSED, grid, sched); else BA_LAUNCH(false, BA_FUSED, grid, sched);
-            c->launches += 1;
-        }
-#undef BA_LAUNCH
+        if (r == 0)
+            ba_round_kernel<F, true><<<grid, BA_THREADS, ba_smem<F>::BYTES, st>>>(io, ad, A, cd, Cn, (uint4 *)c->ba_scratch.p, scratch_stride, sched, r);
+        else
+            ba_round_kernel<F, false><<<grid, BA_THREADS, ba_smem<F>::BYTES, st>>>(io, ad, A, cd, Cn, (uint4 *)c->ba_scratch.p, scratch_stride, sched, r);
+        c->launches += 1;
     }
     MSM_CUDA(c, cudaGetLastError());
     return MSMB200_OK;
@@ -218,10 +186,11 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     const size_t nb = (size_t)L.nbw * L.nwindows;
     const size_t m = L.m;
     // work-item length: long enough that a typical bucket is one item, short enough that there are at least
-    // ~8 items per resident thread (148 SMs x 384 threads) even when buckets are few and heavy
+    // ~8 items per resident thread (SMs x 384 threads) even when buckets are few and heavy
+    const size_t sms = (size_t)c->sms, subparts = 4 * sms;   // 148 / 592 on B200
     size_t avg = std::max<size_t>(1, m / std::max<size_t>(1, nb));
     uint32_t item_len = (uint32_t)std::min<size_t>(1024, std::max<size_t>(128, 8 * avg));
-    if (nb < 148 * 384 * 2) item_len = (uint32_t)std::max<size_t>(32, std::min<size_t>(item_len, m / (148 * 384 * 8)));
+    if (nb < sms * 384 * 2) item_len = (uint32_t)std::max<size_t>(32, std::min<size_t>(item_len, m / (sms * 384 * 8)));
     // Small problems use short work items (>= ~3 warps per SM sub-partition of equal-length chains); the partials of a
     // split bucket are folded by one quad (combine_light_kernel) or, beyond heavy_items partials, by one block.
     const bool split_reduce = use_split_reduce(c, L);
@@ -229,12 +198,12 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     // more: one block each (combine_heavy_kernel)
     const uint32_t heavy_items = 8, medium_items = 64;
     if (split_reduce) {
-        const size_t want_items = (size_t)3 * 592 * 32;
+        const size_t want_items = (size_t)3 * subparts * 32;
         if (nb < want_items) item_len = (uint32_t)std::max<size_t>(8, std::min<size_t>(item_len, m / want_items));
     }
     // The longest chain is the critical path: with ~3 warps sharing a sub-partition it advances at a third of the pipe
-    // rate, so keep item_len * 3 below half of the ideal duration of the whole phase (m / (592 * 32) additions per lane).
-    item_len = (uint32_t)std::max<size_t>(8, std::min<size_t>(item_len, m / ((size_t)592 * 32 * 6)));
+    // rate, so keep item_len * 3 below half of the ideal duration of the whole phase (m / (sub-partitions * 32) additions per lane).
+    item_len = (uint32_t)std::max<size_t>(8, std::min<size_t>(item_len, m / (subparts * 32 * 6)));
     if (c->item_len_fixed > 0) item_len = (uint32_t)c->item_len_fixed;
     const size_t max_items = std::min(nb, m) + m / item_len + 1;
     const size_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
@@ -288,15 +257,11 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         c->launches += 8;
         MSM_CUDA(c, cudaEventRecord(c->ev[2], st));
         // ---- accumulate: XYZZ mixed additions, one thread per work item ----
-        if (sizeof(F) > 48 && getenv("MSMB200_G2_REGACC"))  // experimental: Fp2 accumulator kept in registers
-            launch_accumulate_regacc<F>(blocks_for(max_items, 128), st, d_table, (const uint32_t *)c->sorted.p, (const uint32_t *)c->item_begin.p,
-                                        (const uint32_t *)c->item_cnt.p, (const uint32_t *)c->order.p, totals, c->partial.p);
-        else
-            accumulate_kernel<F><<<blocks_for(max_items, 128), 128, 0, st>>>(d_table, (const uint32_t *)c->sorted.p,
+        accumulate_kernel<F><<<blocks_for(max_items, 128), 128, 0, st>>>(d_table, (const uint32_t *)c->sorted.p,
                                                                              (const uint32_t *)c->item_begin.p, (const uint32_t *)c->item_cnt.p,
                                                                              (const uint32_t *)c->order.p, totals, (xyzz_t<F> *)c->partial.p);
         {
-            unsigned max_heavy = (unsigned)std::min<size_t>(m / item_len + 1, 592);
+            unsigned max_heavy = (unsigned)std::min<size_t>(m / item_len + 1, subparts);
             combine_heavy_kernel<FC><<<max_heavy, 128, 0, st>>>(count, (const uint32_t *)c->item_start.p, (const uint32_t *)c->heavy.p, item_len,
                                                                (xyzz_t<FC> *)c->partial.p);
         }
@@ -364,11 +329,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         }
         jac_t<F> *d_jac = d_out_jac ? (jac_t<F> *)d_out_jac : (jac_t<F> *)c->result.p;
         aff_t<F> *d_aff = (aff_t<F> *)((char *)c->result.p + sizeof(jac_t<F>));
-        if (getenv("MSMB200_SERIAL_FINALIZE"))
-            bits_finalize_kernel<FC><<<1, 32, 0, st>>>((const xyzz_t<FC> *)c->red_d.p, nw, P.nbits_w, L.wbits, (jac_t<FC> *)d_jac,
-                                                       want_affine ? (aff_t<FC> *)d_aff : nullptr);
-        else
-            bits_finalize_coop_kernel<FC><<<1, 32, 0, st>>>((const xyzz_t<FC> *)c->red_d.p, nw, P.nbits_w, L.wbits, (xyzz_t<FC> *)c->red_c.p,
+        bits_finalize_coop_kernel<FC><<<1, 32, 0, st>>>((const xyzz_t<FC> *)c->red_d.p, nw, P.nbits_w, L.wbits, (xyzz_t<FC> *)c->red_c.p,
                                                             (jac_t<FC> *)d_jac, want_affine ? (aff_t<FC> *)d_aff : nullptr);
         c->launches += 1;
         if (want_affine) MSM_CUDA(c, cudaMemcpyAsync(c->h_result, d_aff, sizeof(aff_t<F>), cudaMemcpyDeviceToHost, st));
@@ -448,7 +409,7 @@ static int pippenger_impl(Ctx *c, const void *d_points, size_t npoints, const vo
     size_t m = npoints * (size_t)tiles, nb = (size_t)nbw * tiles;
     int rc = prepare_entries(c, m, nb);
     if (rc) return rc;
-    const uint32_t vs = pick_vspan(nbw - 1, (uint32_t)tiles), nch = (nbw - 1 + vs - 1) / vs;
+    const uint32_t vs = pick_vspan(c, nbw - 1, (uint32_t)tiles), nch = (nbw - 1 + vs - 1) / vs;
     uint32_t clo, ccnt;
     shard_slice(c, nch, &clo, &ccnt);
     const uint32_t blo = 1 + clo * vs, bhi = std::min<uint32_t>(nbw, 1 + (clo + ccnt) * vs);
@@ -519,7 +480,7 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
         uint32_t nbw = (1u << (cfg.e_bgmw - 1)) + 1u;
         int rc = prepare_entries(c, m, nbw);
         if (rc) return rc;
-        const uint32_t vs = pick_vspan(nbw - 1, 1), nch = (nbw - 1 + vs - 1) / vs;
+        const uint32_t vs = pick_vspan(c, nbw - 1, 1), nch = (nbw - 1 + vs - 1) / vs;
         uint32_t clo, ccnt;
         shard_slice(c, nch, &clo, &ccnt);
         const uint32_t blo = 1 + clo * vs, bhi = std::min<uint32_t>(nbw, 1 + (clo + ccnt) * vs);
@@ -570,10 +531,7 @@ static int shim_aux_impl(Ctx *c, int what, const ShimAux &x) {
 template <class F> static int sum_partials_impl(Ctx *c, const void *d_partials, int count) {
     if (ensure(c, c->result, sizeof(jac_t<F>) + sizeof(aff_t<F>)) || ensure(c, c->red_c, sizeof(xyzz_t<F>) + 64)) return MSMB200_ECUDA;
     aff_t<F> *d_aff = (aff_t<F> *)((char *)c->result.p + sizeof(jac_t<F>));
-    if (getenv("MSMB200_SERIAL_FINALIZE"))
-        sum_partials_kernel<F><<<1, 32, 0, c->stream>>>((const jac_t<F> *)d_partials, count, d_aff);
-    else
-        sum_partials_coop_kernel<F><<<1, 32, 0, c->stream>>>((const jac_t<F> *)d_partials, count, (xyzz_t<F> *)c->red_c.p, d_aff);
+    sum_partials_coop_kernel<F><<<1, 32, 0, c->stream>>>((const jac_t<F> *)d_partials, count, (xyzz_t<F> *)c->red_c.p, d_aff);
     MSM_CUDA(c, cudaMemcpyAsync(c->h_result, d_aff, sizeof(aff_t<F>), cudaMemcpyDeviceToHost, c->stream));
     MSM_CUDA(c, cudaStreamSynchronize(c->stream));
     return MSMB200_OK;

@@ -87,37 +87,4 @@ static __device__ __noinline__ void f_inv(fp2_t &r, const fp2_t &a) {
     fp_neg(r.c1, t0);
 }
 
-// ---- Fp2, "value" flavour: identical layout and results, but multiplication / squaring are inlined around the
-// by-value Fp multiplier, so a kernel instantiated with it can keep Fp2 operands in registers instead of the
-// L1-backed local memory the out-of-line fp2_t operations use (experimental G2 accumulator, MSMB200_G2_REGACC=1).
-struct __align__(16) fp2v_t : fp2_t {};
-__device__ __forceinline__ void f_mul(fp2v_t &r, const fp2v_t &a, const fp2v_t &b) {
-    fp_t aa, bb, v0, v1;
-    fp_add(aa, a.c0, a.c1);
-    fp_add(bb, b.c0, b.c1);
-    fp_mul(bb, bb, aa);
-    fp_mul(v0, a.c0, b.c0);
-    fp_mul(v1, a.c1, b.c1);
-    fp_sub(r.c0, v0, v1);
-    fp_sub(bb, bb, v0);
-    fp_sub(r.c1, bb, v1);
-}
-__device__ __forceinline__ void f_sqr(fp2v_t &r, const fp2v_t &a) {
-    fp_t s, d, m;
-    fp_add(s, a.c0, a.c1);
-    fp_sub(d, a.c0, a.c1);
-    fp_mul(m, a.c0, a.c1);
-    fp_mul(r.c0, s, d);
-    fp_add(r.c1, m, m);
-}
-__device__ __forceinline__ void f_add(fp2v_t &r, const fp2v_t &a, const fp2v_t &b) { f_add((fp2_t &)r, (const fp2_t &)a, (const fp2_t &)b); }
-__device__ __forceinline__ void f_sub(fp2v_t &r, const fp2v_t &a, const fp2v_t &b) { f_sub((fp2_t &)r, (const fp2_t &)a, (const fp2_t &)b); }
-__device__ __forceinline__ void f_cneg(fp2v_t &r, const fp2v_t &a, bool f) { f_cneg((fp2_t &)r, (const fp2_t &)a, f); }
-__device__ __forceinline__ void f_dbl(fp2v_t &r, const fp2v_t &a) { f_dbl((fp2_t &)r, (const fp2_t &)a); }
-__device__ __forceinline__ void f_mul3(fp2v_t &r, const fp2v_t &a) { f_mul3((fp2_t &)r, (const fp2_t &)a); }
-__device__ __forceinline__ bool f_is_zero(const fp2v_t &a) { return f_is_zero((const fp2_t &)a); }
-__device__ __forceinline__ bool f_eq(const fp2v_t &a, const fp2v_t &b) { return f_eq((const fp2_t &)a, (const fp2_t &)b); }
-__device__ __forceinline__ void f_set_zero(fp2v_t &r) { f_set_zero((fp2_t &)r); }
-__device__ __forceinline__ void f_set_one(fp2v_t &r) { f_set_one((fp2_t &)r); }
-
 }  // namespace msmb200

@@ -639,7 +639,7 @@ static __global__ void __launch_bounds__(256) tree_tail_kernel(xyzz_t<F> *in, ui
 //   stage 1   val = lo + 2^c_lo * hi: every bucket sum is added to the list of its lo digit and to the list of
 //             its hi digit (2 additions per bucket, the reference's count) -> two dense arrays of <= 2^11 sums;
 //   stage 2   every dense entry v is added to the list of each set bit of v (sliced, then the slices summed);
-//   final     Horner over the bit positions (bits_finalize_kernel).
+//   final     Horner over the bit positions (bits_finalize_coop_kernel).
 // Every stage is a LIST SUM: a static plan (built once on the host from the bucket values, ReducePlan in engine.hpp)
 // names the members of every list. Stage 1 cuts the digit lists into equal slices and gives each slice to one lane
 // (list_sum_kernel); the slices of a list, and all later stages, are summed by quads (list_sum_coop_kernel).
@@ -682,43 +682,6 @@ static __global__ void __launch_bounds__(128) list_sum_kernel(const void *__rest
     out[gl] = acc;
 }
 
-// Horner over bit positions: L[w * nbits_w + k] is the sum of everything whose value has bit k set in window w, i.e.
-// the result is sum_w sum_k 2^(w * wbits + k) L[w][k]. Replaces the tail of integrate_buckets and the outer loop of
-// POINTonE1s_mult_pippenger (src/multi_scalar.c:565-575), xyzz_to_Jacobian and (want_affine) blst_p1_to_affine.
-template <class F>
-static __global__ void bits_finalize_kernel(const xyzz_t<F> *__restrict__ L, uint32_t nwindows, uint32_t nbits_w, uint32_t wbits,
-                                            jac_t<F> *__restrict__ out_jac, aff_t<F> *__restrict__ out_aff) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    xyzz_t<F> acc;
-    xyzz_set_inf(acc);
-    uint32_t pos_prev = 0;
-    bool first = true;
-#pragma unroll 1
-    for (int w = (int)nwindows - 1; w >= 0; w--) {
-#pragma unroll 1
-        for (int k = (int)nbits_w - 1; k >= 0; k--) {
-            const uint32_t pos = (uint32_t)w * wbits + (uint32_t)k;
-            if (!first && !xyzz_is_inf(acc)) {
-#pragma unroll 1
-                for (uint32_t d = pos; d < pos_prev; d++) { xyzz_t<F> a = acc; xyzz_double(acc, a); }
-            }
-            first = false;
-            pos_prev = pos;
-            xyzz_t<F> s;
-            load_xyzz(s, L + (size_t)w * nbits_w + k);
-            xyzz_add_cold(acc, s);
-        }
-    }
-    jac_t<F> j;
-    if (xyzz_is_inf(acc)) jac_set_inf(j);
-    else xyzz_to_jac(j, acc);
-    if (out_jac) *out_jac = j;
-    if (out_aff) {
-        aff_t<F> a;
-        jac_to_affine(a, j);
-        *out_aff = a;
-    }
-}
 
 // Lane-cooperative variants (coop.cuh: a point is distributed over a GROUP of 4 lanes for G1, 8 lanes for G2): list
 // sums with one group per team slot (tq groups per list, tq a power of two <= groups per warp), and the Horner pass
@@ -823,6 +786,9 @@ template <class C> __device__ __forceinline__ void dq_shift(C &acc, uint32_t my_
         if (i < my_doublings) acc = d;
     }
 }
+// Horner over bit positions: L[w * nbits_w + k] is the sum of everything whose value has bit k set in window w, i.e. the
+// result is sum_w sum_k 2^(w * wbits + k) L[w][k]. Replaces the tail of integrate_buckets and the outer loop of
+// POINTonE1s_mult_pippenger (src/multi_scalar.c:565-575), xyzz_to_Jacobian and (want_affine) blst_p1_to_affine.
 // One warp of NG groups. Entries in descending bit position: t = 0..G-1 <-> (w = nwindows-1 - t / nbits_w,
 // k = nbits_w-1 - t % nbits_w), position w * wbits + k. Group j runs Horner over entries [j*len, (j+1)*len); the NG
 // partial results are combined by a tree in which the group holding the higher positions is doubled down to its
@@ -918,20 +884,6 @@ static __global__ void finalize_kernel(const xyzz_t<F> *__restrict__ row_sums, u
         jac_to_affine(a, j);
         *out_aff = a;
     }
-}
-// sum of Jacobian partials (one per GPU) + to_affine: the G-1 dadds after the NCCL all-gather
-template <class F>
-static __global__ void sum_partials_kernel(const jac_t<F> *__restrict__ partials, int count, aff_t<F> *__restrict__ out_aff) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    jac_t<F> acc;
-    jac_set_inf(acc);
-    for (int k = 0; k < count; k++) {
-        jac_t<F> p = partials[k];
-        jac_add(acc, acc, p);
-    }
-    aff_t<F> a;
-    jac_to_affine(a, acc);
-    *out_aff = a;
 }
 
 // Lane-cooperative form: one warp of NG groups, group j folds partials j, j+NG, ... (Jacobian (X, Y, Z) read as XYZZ
