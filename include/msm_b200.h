@@ -162,6 +162,8 @@ int msmb200_affine_serialize(int group, const void *affine_host, unsigned char *
 int msmb200_last_timings(msmb200_ctx *ctx, float out_ms[6]);
 /* Number of kernels launched by the last msm call. */
 int msmb200_last_launches(msmb200_ctx *ctx);
+/* Bucket accumulator the last MSM ran: 1 = XYZZ work items (xyzz_dadd_affine per entry), 2 = batch-affine rounds. */
+int msmb200_last_accumulator(msmb200_ctx *ctx);
 
 /* Live roofline denominators (register-only microbenchmarks): full 32x32+64-bit multiply-accumulates
  * per second with IMAD.WIDE.U32, and dependent-chain mul_mont_384 per second, on `device`. */

@@ -90,6 +90,7 @@ def lib():
         L.msmb200_affine_serialize.argtypes = [ci, vp, vp]
         L.msmb200_last_timings.argtypes = [vp, vp]
         L.msmb200_last_launches.argtypes = [vp]
+        L.msmb200_last_accumulator.argtypes = [vp]
         L.msmb200_measure_peaks.argtypes = [ci, vp, vp]
         L.msmb200_measure_peaks_ex.argtypes = [ci, vp]
         L.msmb200_test_field_op.argtypes = [ci, ci, ci, vp, vp, vp, sz]
@@ -374,3 +375,7 @@ class MsmContext:
 
     def last_launches(self):
         return int(lib().msmb200_last_launches(self._h))
+
+    def last_accumulator(self):
+        """1 = XYZZ work items, 2 = batch-affine rounds (what the last MSM used)."""
+        return int(lib().msmb200_last_accumulator(self._h))

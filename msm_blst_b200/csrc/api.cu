@@ -202,6 +202,7 @@ static int ctx_init_common(Ctx *c, int group, int device) {
     if (const char *e = getenv("MSMB200_BA_BATCH_MAX")) c->ba_batch_max = std::max(1, atoi(e));
     if (const char *e = getenv("MSMB200_VSPAN")) c->vspan_env = std::max(0, atoi(e));
     c->no_overlap = getenv("MSMB200_NO_OVERLAP") != nullptr;
+    c->table_stride = (uint32_t)(getenv("MSMB200_PACKED_TABLES") ? c->ops->aff_bytes : (c->ops->aff_bytes + 127) & ~(size_t)127);
     return MSMB200_OK;
 }
 
@@ -468,8 +469,8 @@ int msmb200_download(msmb200_ctx *ctx, int which, size_t first, size_t count, vo
     if (!src) return ctx_fail(c, MSMB200_ESTATE, "requested array not built");
     if (first + count > total) return ctx_fail(c, MSMB200_EINVAL, "range out of bounds");
     MSM_CUDA(c, cudaSetDevice(c->device));
-    size_t ab = c->ops->aff_bytes;
-    MSM_CUDA(c, cudaMemcpyAsync(out_host, (const char *)src + first * ab, count * ab, cudaMemcpyDeviceToHost, c->stream));
+    const size_t ab = c->ops->aff_bytes, stride = which == 0 ? ab : c->table_stride;   // out: always the reference's packed layout
+    if (count) MSM_CUDA(c, cudaMemcpy2DAsync(out_host, ab, (const char *)src + first * stride, stride, ab, count, cudaMemcpyDeviceToHost, c->stream));
     MSM_CUDA(c, cudaStreamSynchronize(c->stream));
     return MSMB200_OK;
 }
@@ -519,11 +520,21 @@ int msmb200_table_save(msmb200_ctx *ctx, int which, const char *path, int format
     bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
     const size_t ab = c->ops->aff_bytes, chunk = (size_t)1 << 20;
     std::vector<unsigned char> host(std::min(entries, chunk) * ab);
-    void *d_stage = nullptr;
-    if (format == 1 && cudaMalloc(&d_stage, std::min(entries, chunk) * ab) != cudaSuccess) { fclose(f); return ctx_fail(c, MSMB200_ECUDA, "cudaMalloc"); }
+    const size_t stride = which == 0 ? ab : c->table_stride;   // the context's own tables are padded to whole lines; files are packed
+    void *d_stage = nullptr, *d_packed = nullptr;
+    if ((format == 1 && cudaMalloc(&d_stage, std::min(entries, chunk) * ab) != cudaSuccess) ||
+        (stride != ab && cudaMalloc(&d_packed, std::min(entries, chunk) * ab) != cudaSuccess)) {
+        if (d_stage) cudaFree(d_stage);
+        fclose(f);
+        return ctx_fail(c, MSMB200_ECUDA, "cudaMalloc");
+    }
     for (size_t off = 0; ok && off < entries; off += chunk) {
         const size_t cnt = std::min(chunk, entries - off);
-        const void *src = (const char *)*slot + off * ab;
+        const void *src = (const char *)*slot + off * stride;
+        if (stride != ab) {
+            if (cudaMemcpy2DAsync(d_packed, ab, src, stride, ab, cnt, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) { ok = false; break; }
+            src = d_packed;
+        }
         if (format == 1) {
             if (c->ops->table_io(c, 0, 1, src, d_stage, cnt, nullptr)) { ok = false; break; }
             src = d_stage;
@@ -532,6 +543,7 @@ int msmb200_table_save(msmb200_ctx *ctx, int which, const char *path, int format
              fwrite(host.data(), ab, cnt, f) == cnt;
     }
     if (d_stage) cudaFree(d_stage);
+    if (d_packed) cudaFree(d_packed);
     ok = (fclose(f) == 0) && ok;
     return ok ? MSMB200_OK : ctx_fail(c, MSMB200_ECUDA, std::string("writing ") + path + " failed");
 }
@@ -557,15 +569,20 @@ int msmb200_table_load(msmb200_ctx *ctx, int which, const char *path) {
         if (points_digest(c, &dig)) { fclose(f); return MSMB200_ECUDA; }
         if (dig != h.points_digest) { fclose(f); return ctx_fail(c, MSMB200_EINVAL, "table file was built from other fixed points"); }
     }
-    const size_t ab = c->ops->aff_bytes, chunk = (size_t)1 << 20;
-    if (!*slot && cudaMalloc(slot, entries * ab) != cudaSuccess) { fclose(f); *slot = nullptr; return ctx_fail(c, MSMB200_ECUDA, "cudaMalloc"); }
+    const size_t ab = c->ops->aff_bytes, chunk = (size_t)1 << 20, stride = which == 0 ? ab : c->table_stride;
+    if (!*slot) {
+        if (cudaMalloc(slot, entries * stride) != cudaSuccess) { fclose(f); *slot = nullptr; return ctx_fail(c, MSMB200_ECUDA, "cudaMalloc"); }
+        if (stride != ab) cudaMemsetAsync(*slot, 0, entries * stride, c->stream);
+    }
     *have = false;
     if (which == 0) c->have_ches = c->have_bgmw = false;
     std::vector<unsigned char> host(std::min(entries, chunk) * ab);
-    void *d_stage = nullptr;
+    void *d_stage = nullptr, *d_packed = nullptr;
     uint32_t *d_bad = nullptr, bad = 0;
-    if (cudaMalloc(&d_stage, std::min(entries, chunk) * ab) != cudaSuccess || cudaMalloc((void **)&d_bad, 4) != cudaSuccess) {
+    if (cudaMalloc(&d_stage, std::min(entries, chunk) * ab) != cudaSuccess || cudaMalloc((void **)&d_bad, 4) != cudaSuccess ||
+        (stride != ab && cudaMalloc(&d_packed, std::min(entries, chunk) * ab) != cudaSuccess)) {
         if (d_stage) cudaFree(d_stage);
+        if (d_bad) cudaFree(d_bad);
         fclose(f);
         return ctx_fail(c, MSMB200_ECUDA, "cudaMalloc");
     }
@@ -575,12 +592,14 @@ int msmb200_table_load(msmb200_ctx *ctx, int which, const char *path) {
         const size_t cnt = std::min(chunk, entries - off);
         ok = fread(host.data(), ab, cnt, f) == cnt &&
              cudaMemcpyAsync(d_stage, host.data(), cnt * ab, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
-             c->ops->table_io(c, 1, (int)h.format, d_stage, (char *)*slot + off * ab, cnt, d_bad) == MSMB200_OK &&
+             c->ops->table_io(c, 1, (int)h.format, d_stage, stride != ab ? d_packed : (void *)((char *)*slot + off * ab), cnt, d_bad) == MSMB200_OK &&
+             (stride == ab || cudaMemcpy2DAsync((char *)*slot + off * stride, stride, d_packed, ab, ab, cnt, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess) &&
              cudaStreamSynchronize(c->stream) == cudaSuccess;  // the host buffer is reused
     }
     fclose(f);
     if (ok) ok = cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
     cudaFree(d_stage); cudaFree(d_bad);
+    if (d_packed) cudaFree(d_packed);
     if (!ok) return ctx_fail(c, MSMB200_ECUDA, std::string("reading ") + path + " failed");
     if (bad) return ctx_fail(c, MSMB200_EINVAL, std::to_string(bad) + " entries are not valid curve points (range, flags or y^2 = x^3 + B)");
     *have = true;
@@ -695,6 +714,7 @@ int msmb200_last_timings(msmb200_ctx *ctx, float out_ms[6]) {
     return MSMB200_OK;
 }
 int msmb200_last_launches(msmb200_ctx *ctx) { return ctx ? C(ctx)->launches : MSMB200_EINVAL; }
+int msmb200_last_accumulator(msmb200_ctx *ctx) { return ctx ? C(ctx)->last_accum : MSMB200_EINVAL; }
 
 // Serialisation is a pure byte shuffle of one 96/192-byte result plus a from-Montgomery multiplication; it is
 // done on the device like everything else (point_op 6 would be overkill) — here via the field-op kernel.

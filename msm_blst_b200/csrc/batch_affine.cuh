@@ -308,12 +308,16 @@ static __device__ __noinline__ ba_cold_t<F> ba_classify_cold(const F *px, const 
 // bytes. Final results (one per bucket) go to bucket_sum as {x, y} for the reducers.
 template <class F> struct ba_io {
     const aff_t<F> *table;       // round 0 only
+    uint32_t tstride16;          // distance between table entries in 16-byte units (packed: sizeof(aff_t<F>) / 16; padded own tables: 8 / 16)
     const F *in_x, *in_y;        // rounds >= 1
     F *out_x, *out_y;
     aff_t<F> *bucket_sum;
 };
-template <class F, bool FIRST> __device__ __forceinline__ const F *ba_px(const ba_io<F> &io, uint32_t i) { return FIRST ? &io.table[i].x : io.in_x + i; }
-template <class F, bool FIRST> __device__ __forceinline__ const F *ba_py(const ba_io<F> &io, uint32_t i) { return FIRST ? &io.table[i].y : io.in_y + i; }
+template <class F> __device__ __forceinline__ const aff_t<F> *ba_entry(const ba_io<F> &io, uint32_t i) {
+    return reinterpret_cast<const aff_t<F> *>(reinterpret_cast<const uint4 *>(io.table) + (size_t)i * io.tstride16);
+}
+template <class F, bool FIRST> __device__ __forceinline__ const F *ba_px(const ba_io<F> &io, uint32_t i) { return FIRST ? &ba_entry(io, i)->x : io.in_x + i; }
+template <class F, bool FIRST> __device__ __forceinline__ const F *ba_py(const ba_io<F> &io, uint32_t i) { return FIRST ? &ba_entry(io, i)->y : io.in_y + i; }
 template <class F> __device__ __forceinline__ void ba_store_point(uint32_t out, const ba_io<F> &io, const F &x, const F &y) {
     if (out & BA_FINAL) {
         aff_t<F> *dst = io.bucket_sum + (out & ~BA_FINAL);
@@ -362,8 +366,8 @@ template <class F> __device__ __forceinline__ void ba_ld_stage(F &v, const unsig
 // a line an entry occupies travels as one request. The owner's descriptor is read from the shared-memory ring (copied
 // there by the owner; visible after cp.async.wait_group + __syncwarp), the chunks land in the owner's stage.
 template <class F, int NCH>
-__device__ __forceinline__ void ba_coop_gather(const aff_t<F> *__restrict__ table, const unsigned char *shared, uint32_t sbase, int desc_chunk, int first_chunk,
-                                               int dst_p, int dst_q) {
+__device__ __forceinline__ void ba_coop_gather(const aff_t<F> *__restrict__ table, uint32_t stride16, const unsigned char *shared, uint32_t sbase, int desc_chunk,
+                                               int first_chunk, int dst_p, int dst_q) {
     constexpr int EPI = 32 / NCH;                 // entries per warp instruction
     constexpr int NI = (64 + EPI - 1) / EPI;      // 32 slots x 2 operands
     const uint32_t lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u, sub = lane / NCH, c = lane % NCH;
@@ -373,7 +377,7 @@ __device__ __forceinline__ void ba_coop_gather(const aff_t<F> *__restrict__ tabl
         if (sub < (uint32_t)EPI && e < 64u) {
             const uint32_t o = e >> 1, which = e & 1u;
             const uint32_t idx = *reinterpret_cast<const uint32_t *>(shared + ((size_t)desc_chunk * BA_THREADS + wbase + o) * 16 + which * 4) & 0x7fffffffu;
-            const uint4 *src = reinterpret_cast<const uint4 *>(table + idx) + first_chunk + c;
+            const uint4 *src = reinterpret_cast<const uint4 *>(table) + (size_t)idx * stride16 + first_chunk + c;
             ba_cp16(sbase + (uint32_t)((((which ? dst_q : dst_p) + (int)c) * BA_THREADS + (int)(wbase + o)) * 16), src);
         }
     }
@@ -457,7 +461,7 @@ static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_r
             auto issue_data = [&](uint32_t j) {   // needs the descriptor of slot j in the ring
                 const uint4 m = *reinterpret_cast<const uint4 *>(ba_shared + ba_chunk((int)(j % ND)));
                 const int c0 = stage_ch(j);
-                if (FIRST) ba_coop_gather<F, FCH>(io.table, ba_shared, sbase, (int)(j % ND), 0, c0, c0 + FCH);   // x = chunks 0 .. FCH - 1 of an entry
+                if (FIRST) ba_coop_gather<F, FCH>(io.table, io.tstride16, ba_shared, sbase, (int)(j % ND), 0, c0, c0 + FCH);   // x = chunks 0 .. FCH - 1 of an entry
                 else {
                     ba_cp_field(sbase, c0, ba_px<F, FIRST>(io, m.x & IDX));
                     ba_cp_field(sbase, c0 + FCH, ba_px<F, FIRST>(io, m.y & IDX));
@@ -524,14 +528,14 @@ static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_r
                 const size_t s = min(slot_of(j), (size_t)last);
 #pragma unroll
                 for (int k = 0; k < FCH; k++) ba_cp16(sbase + ba_chunk(c0 + k), scratch + (size_t)k * scratch_stride + s);
-                if (FIRST) ba_coop_gather<F, FCH>(io.table, ba_shared, sbase, (int)(j % ND), 0, c0 + FCH, c0 + 2 * FCH);
+                if (FIRST) ba_coop_gather<F, FCH>(io.table, io.tstride16, ba_shared, sbase, (int)(j % ND), 0, c0 + FCH, c0 + 2 * FCH);
                 else {
                     ba_cp_field(sbase, c0 + FCH, ba_px<F, FIRST>(io, m.x & IDX));
                     ba_cp_field(sbase, c0 + 2 * FCH, ba_px<F, FIRST>(io, m.y & IDX));
                 }
             };
             auto issue_y = [&](uint32_t j) {
-                if (FIRST) { ba_coop_gather<F, FCH>(io.table, ba_shared, sbase, (int)(j % ND), FCH, Y0, Y0 + FCH); return; }
+                if (FIRST) { ba_coop_gather<F, FCH>(io.table, io.tstride16, ba_shared, sbase, (int)(j % ND), FCH, Y0, Y0 + FCH); return; }
                 const uint4 m = desc_at(j);
                 ba_cp_field(sbase, Y0, ba_py<F, FIRST>(io, m.x & IDX));
                 ba_cp_field(sbase, Y0 + FCH, ba_py<F, FIRST>(io, m.y & IDX));

@@ -60,6 +60,9 @@ struct Ctx {
 
     // points and tables (affine, Montgomery)
     void *d_points = nullptr;      bool have_points = false;
+    // the context's own precomputation tables: entries padded to whole 128-byte lines (stride 128 / 256 bytes) unless
+    // MSMB200_PACKED_TABLES was set at creation; downloads and table files always use the reference's packed layout
+    uint32_t table_stride = 0;
     void *d_table_ches = nullptr;  bool have_ches = false;
     void *d_table_bgmw = nullptr;  bool have_bgmw = false;
 
@@ -97,6 +100,7 @@ struct Ctx {
     cudaEvent_t ev[8] = {};
     float last_ms[6] = {0, 0, 0, 0, 0, 0};
     int launches = 0;
+    int last_accum = 0;             // accumulator the last MSM used: 1 XYZZ work items, 2 batch-affine rounds
 };
 
 struct ShimAux {

@@ -30,6 +30,7 @@ struct Layout {
     uint32_t nchunks;        // reduction chunks per window (all of them)
     uint32_t chunk_lo = 0, chunk_cnt = 0;  // the slice this context reduces (bucket-range sharding); cnt 0 = all
     const ReducePlan *plan = nullptr;      // digit-splitting reduction plan (nullptr: chunked running sums only)
+    uint32_t tstride16 = 0;                // table entry stride in 16-byte units (0: packed, sizeof(aff_t<F>) / 16)
 };
 
 static inline bool use_split_reduce(const Ctx *c, const Layout &L) {
@@ -74,7 +75,7 @@ static __global__ void iota_kernel(uint32_t *out, size_t n) {
 // exclusive scans of all rounds in one pass, the counting-sort scatter, the slot descriptors, then one arithmetic
 // kernel per round. Records ev[2] between planning and arithmetic ("sort" / "accumulate" phases).
 template <class F>
-static int ba_accumulate(Ctx *c, const aff_t<F> *d_table, uint32_t *count, size_t nb, size_t m) {
+static int ba_accumulate(Ctx *c, const aff_t<F> *d_table, uint32_t tstride16, uint32_t *count, size_t nb, size_t m) {
     cudaStream_t st = c->stream;
     if (ensure(c, c->ba_totals, (3 * BA_RMAX + 1) * 4)) return MSMB200_ECUDA;
     if (!c->h_totals) MSM_CUDA(c, cudaMallocHost((void **)&c->h_totals, (3 * BA_RMAX + 1) * 4));
@@ -165,6 +166,7 @@ static int ba_accumulate(Ctx *c, const aff_t<F> *d_table, uint32_t *count, size_
         const uint2 *cd = (const uint2 *)c->ba_cdesc.p + rd.coff[r];
         ba_io<F> io;
         io.table = d_table;
+        io.tstride16 = tstride16;
         io.in_x = bx[r & 1]; io.in_y = by[r & 1];
         io.out_x = bx[(r + 1) & 1]; io.out_y = by[(r + 1) & 1];
         io.bucket_sum = (aff_t<F> *)c->bucket_sum.p;
@@ -185,6 +187,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     cudaStream_t st = c->stream;
     const size_t nb = (size_t)L.nbw * L.nwindows;
     const size_t m = L.m;
+    const uint32_t tstride16 = L.tstride16 ? L.tstride16 : (uint32_t)(sizeof(aff_t<F>) / 16);
     // work-item length: long enough that a typical bucket is one item, short enough that there are at least
     // ~8 items per resident thread (SMs x 384 threads) even when buckets are few and heavy
     const size_t sms = (size_t)c->sms, subparts = 4 * sms;   // 148 / 592 on B200
@@ -211,6 +214,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
     int mode = c->accum_mode;
     if (c->accum_env) mode = c->accum_env;
     if (mode == 0) mode = default_accumulator<F>(m);
+    c->last_accum = mode == 2 ? 2 : 1;
     if (ensure(c, c->sorted, (m + 2) * 4) || ensure(c, c->result, sizeof(jac_t<F>) + sizeof(aff_t<F>))) return MSMB200_ECUDA;
     if (mode != 2 &&   // workspace of the XYZZ work-item path only
         (ensure(c, c->packed, nb * 8) || ensure(c, c->scanned, nb * 8) || ensure(c, c->tile_sums, (ntiles + 1) * 8) ||
@@ -257,7 +261,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         c->launches += 8;
         MSM_CUDA(c, cudaEventRecord(c->ev[2], st));
         // ---- accumulate: XYZZ mixed additions, one thread per work item ----
-        accumulate_kernel<F><<<blocks_for(max_items, 128), 128, 0, st>>>(d_table, (const uint32_t *)c->sorted.p,
+        accumulate_kernel<F><<<blocks_for(max_items, 128), 128, 0, st>>>(d_table, tstride16, (const uint32_t *)c->sorted.p,
                                                                              (const uint32_t *)c->item_begin.p, (const uint32_t *)c->item_cnt.p,
                                                                              (const uint32_t *)c->order.p, totals, (xyzz_t<F> *)c->partial.p);
         {
@@ -281,7 +285,7 @@ static int run_buckets(Ctx *c, const Layout &L, const aff_t<F> *d_table, void *d
         bucket_points = c->partial.p;
         bucket_point_index = (const uint32_t *)c->item_start.p;
     } else {
-        int rc = ba_accumulate<F>(c, d_table, count, nb, m);
+        int rc = ba_accumulate<F>(c, d_table, tstride16, count, nb, m);
         if (rc) return rc;
         bucket_points = c->bucket_sum.p;
         bucket_point_index = (const uint32_t *)c->iota.p;
@@ -472,6 +476,7 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
         Layout L{m, (uint32_t)nb, 1, 0, c->d_bucket_vals, cfg.d, c->d_chunk_first, c->red_vspan, c->red_nchunks};
         L.chunk_lo = clo; L.chunk_cnt = ccnt;
         L.plan = &c->plan_ches;
+        L.tstride16 = c->table_stride / 16;
         return run_buckets<F, FC>(c, L, (const aff_t<F> *)c->d_table_ches, d_out_jac, want_affine);
     }
     if (method == MSMB200_BGMW95) {
@@ -492,6 +497,7 @@ template <class F, class FC> static int msm_impl(Ctx *c, int method, const void 
         Layout L{m, nbw, 1, 0, nullptr, 1, nullptr, vs, nch};
         L.chunk_lo = clo; L.chunk_cnt = ccnt;
         L.plan = dense_plan(c, c->plan_bgmw, nbw, 1, &c->plan_bgmw_windows);
+        L.tstride16 = c->table_stride / 16;
         return run_buckets<F, FC>(c, L, (const aff_t<F> *)c->d_table_bgmw, d_out_jac, want_affine);
     }
     return ctx_fail(c, MSMB200_EINVAL, "unknown method");
@@ -559,8 +565,11 @@ template <class F> static int table_build_impl(Ctx *c, int which) {
     int h = which == 0 ? cfg.h : cfg.h_bgmw, e = which == 0 ? cfg.e : cfg.e_bgmw, nmult = which == 0 ? 3 : 1;
     size_t entries = c->n * (size_t)h * nmult;
     void **slot = which == 0 ? &c->d_table_ches : &c->d_table_bgmw;
-    if (!*slot) MSM_CUDA(c, cudaMalloc(slot, entries * sizeof(aff_t<F>)));
-    table_build_kernel<F><<<blocks_for(c->n, 128), 128, 0, c->stream>>>((const aff_t<F> *)c->d_points, c->n, h, e, nmult, (aff_t<F> *)*slot);
+    if (!*slot) {
+        MSM_CUDA(c, cudaMalloc(slot, entries * (size_t)c->table_stride));
+        if (c->table_stride != sizeof(aff_t<F>)) MSM_CUDA(c, cudaMemsetAsync(*slot, 0, entries * (size_t)c->table_stride, c->stream));   // the padding is never read as data
+    }
+    table_build_kernel<F><<<blocks_for(c->n, 128), 128, 0, c->stream>>>((const aff_t<F> *)c->d_points, c->n, h, e, nmult, (aff_t<F> *)*slot, c->table_stride / 16);
     MSM_CUDA(c, cudaGetLastError());
     MSM_CUDA(c, cudaStreamSynchronize(c->stream));
     (which == 0 ? c->have_ches : c->have_bgmw) = true;

@@ -412,17 +412,26 @@ static __global__ void order_items_kernel(const uint32_t *__restrict__ item_cnt,
 // [3] bucket accumulation (XYZZ path): replaces the hot loop of POINTonE1_tile_pippenger_d_CHES /
 // _BGMW95 / s_tile_pippenger (src/multi_scalar.c:437-461,:522-544,:397-417 -> xyzz_dadd_affine).
 // One thread per work item; items sorted longest-first so the warps of a block have equal trip counts.
-// Each table entry (96 B / 192 B, 32-byte aligned) is fetched with 16-byte vector loads.
+// Each table entry (96 B / 192 B) is fetched with 16-byte vector loads. Entries lie `stride16` 16-byte units apart: 6 / 12
+// in the reference's packed layout (caller-owned tables, the fixed points), 8 / 16 in the context's own precomputation
+// tables, which are padded to whole 128-byte lines (the memory system fetches lines: a packed 96-byte entry straddles two
+// of them half of the time, profiles/r2_gather_microbench.json).
 // ------------------------------------------------------------------------------------------------
+template <class F> __device__ __forceinline__ const aff_t<F> *table_entry(const aff_t<F> *table, size_t idx, uint32_t stride16) {
+    return reinterpret_cast<const aff_t<F> *>(reinterpret_cast<const uint4 *>(table) + idx * stride16);
+}
+template <class F> __device__ __forceinline__ aff_t<F> *table_entry(aff_t<F> *table, size_t idx, uint32_t stride16) {
+    return reinterpret_cast<aff_t<F> *>(reinterpret_cast<uint4 *>(table) + idx * stride16);
+}
 template <class F>
-__device__ __forceinline__ void load_affine(aff_t<F> &p, const aff_t<F> *__restrict__ table, uint32_t idx) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(table + idx);
+__device__ __forceinline__ void load_affine(aff_t<F> &p, const aff_t<F> *__restrict__ table, uint32_t idx, uint32_t stride16) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(table) + (size_t)idx * stride16;
     uint4 *dst = reinterpret_cast<uint4 *>(&p);
 #pragma unroll
     for (int k = 0; k < (int)(sizeof(aff_t<F>) / 16); k++) dst[k] = __ldg(src + k);
 }
 template <class F>
-static __global__ void __launch_bounds__(128) accumulate_kernel(const aff_t<F> *__restrict__ table, const uint32_t *__restrict__ sorted,
+static __global__ void __launch_bounds__(128) accumulate_kernel(const aff_t<F> *__restrict__ table, uint32_t stride16, const uint32_t *__restrict__ sorted,
                                                          const uint32_t *__restrict__ item_begin, const uint32_t *__restrict__ item_cnt,
                                                          const uint32_t *__restrict__ order, const uint64_t *__restrict__ totals,
                                                          xyzz_t<F> *__restrict__ partial) {
@@ -436,7 +445,7 @@ static __global__ void __launch_bounds__(128) accumulate_kernel(const aff_t<F> *
     for (uint32_t k = 0; k < cnt; k++) {
         uint32_t v = sorted[beg + k];
         aff_t<F> p;
-        load_affine(p, table, v & 0x7fffffffu);
+        load_affine(p, table, v & 0x7fffffffu, stride16);
         xyzz_add_affine(acc, p, (v >> 31) != 0);
     }
     partial[it] = acc;
@@ -540,7 +549,7 @@ static __global__ void __launch_bounds__(64) reduce_chunks_kernel(const void *__
                 // bucket sum: XYZZ partial of the bucket's first work item, or (batch-affine path) ONE affine point
                 if (AFFINE_IN) {
                     aff_t<F> a;
-                    load_affine(a, (const aff_t<F> *)bucket_points, item_start[b]);
+                    load_affine(a, (const aff_t<F> *)bucket_points, item_start[b], (uint32_t)(sizeof(aff_t<F>) / 16));
                     xyzz_add_affine(tmp, a, false);
                 } else {
                     xyzz_t<F> s;
@@ -670,7 +679,7 @@ static __global__ void __launch_bounds__(128) list_sum_kernel(const void *__rest
         } else if (count[b] != 0) {
             if (MODE == 1) {
                 aff_t<F> a;
-                load_affine(a, (const aff_t<F> *)src, item_start[b]);
+                load_affine(a, (const aff_t<F> *)src, item_start[b], (uint32_t)(sizeof(aff_t<F>) / 16));
                 xyzz_add_affine(acc, a, false);
             } else {
                 xyzz_t<F> s;
@@ -1014,14 +1023,14 @@ template <class F> __device__ __forceinline__ void jac_from_affine(jac_t<F> &j, 
 // entry; one thread per fixed point, one shared inversion per (i, j).
 template <class F>
 static __global__ void __launch_bounds__(128) table_build_kernel(const aff_t<F> *__restrict__ points, size_t n, int h, int e, int nmult,
-                                                          aff_t<F> *__restrict__ table) {
+                                                          aff_t<F> *__restrict__ table, uint32_t stride16) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     aff_t<F> q = points[i];
 #pragma unroll 1
     for (int j = 0; j < h; j++) {
         size_t base = (i * h + j) * nmult;
-        table[base] = q;
+        *table_entry(table, base, stride16) = q;
         jac_t<F> jq, d, t3;
         jac_from_affine(jq, q);
         jac_double(d, jq);                        // 2Q (Z stays 0 for infinity)
@@ -1032,7 +1041,7 @@ static __global__ void __launch_bounds__(128) table_build_kernel(const aff_t<F> 
         for (int k = 1; k < e; k++) jac_double(nx, nx);
         aff_t<F> a2, a3, an;
         to_affine3(&a2, d, &a3, t3, &an, nx);
-        if (nmult == 3) { table[base + 1] = a2; table[base + 2] = a3; }
+        if (nmult == 3) { *table_entry(table, base + 1, stride16) = a2; *table_entry(table, base + 2, stride16) = a3; }
         q = an;
     }
 }

@@ -51,10 +51,10 @@ body = [(a, t) for a, t in ins if a >= start]
 end = next(i for i, (_, t) in enumerate(body) if opcode(t).startswith("RET"))
 write("r2_sass_fp_mul_fn.txt", "fp_mul_fn (Montgomery multiplication, csrc/fp.cuh) inside peak_fp_mul_kernel, sm_100a, commit %s" % rev, body[: end + 1])
 # the batch-affine hot kernel: histogram of the whole kernel including its out-of-line routines
-for fun, out in (("_ZN7msmb20015ba_round_kernelINS_4fp_tELb1EEEvNS_5ba_ioIT_EEPK5uint4jPK5uint2jPS5_mNS_7BaSchedEj", "r2_sass_ba_round_kernel_fp_first.txt"),):
+for fun, out in (("_ZN7msmb20015ba_round_kernelINS_4fp_tELb0EEEvNS_5ba_ioIT_EEPK5uint4jPK5uint2jPS5_mNS_7BaSchedEj", "r2_sass_ba_round_kernel_fp.txt"),):
     try:
         ins = instrs(sass(fun))
-        write(out, "ba_round_kernel<fp_t, true> incl. fp_mul_fn / fp_sqr_fn / fp_inv_warp_fn copies, sm_100a, commit %s" % rev, ins, listing=False)
+        write(out, "ba_round_kernel<fp_t, false> (rounds >= 1) incl. fp_mul_fn / fp_sqr_fn / fp_inv_warp_fn copies, sm_100a, commit %s" % rev, ins, listing=False)
     except Exception as ex:
         print("skipped", fun, ex)
 print(open(os.path.join(ROOT, "profiles", "r2_sass_fp_mul_fn.txt")).read()[:1500])
