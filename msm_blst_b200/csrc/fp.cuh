@@ -8,6 +8,7 @@
 //   cneg_fp, mul_by_3_fp                                  reference src/fields.h:21,:42
 // Constants: reference src/consts.c:10-26, src/consts.h:12-22 (same bytes, read as 32-bit limbs).
 #pragma once
+#include "inv.cuh"
 #include <cstdint>
 
 namespace msmb200 {
@@ -329,77 +330,11 @@ __device__ __forceinline__ uint32_t fp_rr_limb(int i) {
     case 8: return 0xb519952du; case 9: return 0x9a793e85u; case 10: return 0x92cae3aau; default: return 0x11988fe5u;
     }
 }
-// 1/a in Montgomery form, 0 -> 0 like the reference's reciprocal_fp (src/recip.c:58-92). Binary extended GCD
-// on the plain integer A = a*R mod p (not constant time: the MSM path is not, src/ec_ops.h:634): ~760 shift /
-// subtract steps of 12-limb carry chains instead of the ~570 dependent Montgomery multiplications of Fermat's
-// a^(p-2). The result A^-1 is brought back with two multiplications by RR: A^-1 * R^2 = (a^-1) * R.
-static __device__ __noinline__ void fp_inv(fp_t &r, const fp_t &a) {
-    uint32_t u[12], v[12], b[12], c[12];
-    if (fp_is_zero(a)) { fp_set_zero(r); return; }
-#pragma unroll
-    for (int i = 0; i < 12; i++) { u[i] = a.l[i]; v[i] = fp_p_limb(i); b[i] = 0; c[i] = 0; }
-    b[0] = 1;
-    auto shr1 = [](uint32_t *x) {
-#pragma unroll
-        for (int i = 0; i < 11; i++) x[i] = __funnelshift_r(x[i], x[i + 1], 1);
-        x[11] >>= 1;
-    };
-    auto add_p = [](uint32_t *x) {
-        x[0] = add_cc(x[0], fp_p_limb(0));
-#pragma unroll
-        for (int i = 1; i < 11; i++) x[i] = addc_cc(x[i], fp_p_limb(i));
-        x[11] = addc(x[11], fp_p_limb(11));
-    };
-    auto is_one = [](const uint32_t *x) {
-        uint32_t acc = x[0] ^ 1u;
-#pragma unroll
-        for (int i = 1; i < 12; i++) acc |= x[i];
-        return acc == 0;
-    };
-    // x -= y, returns borrow mask
-    auto sub = [](uint32_t *x, const uint32_t *y) {
-        x[0] = sub_cc(x[0], y[0]);
-#pragma unroll
-        for (int i = 1; i < 12; i++) x[i] = subc_cc(x[i], y[i]);
-        return subc(0, 0);
-    };
-    auto less = [](const uint32_t *x, const uint32_t *y) {  // x < y
-        uint32_t t = sub_cc(x[0], y[0]);
-#pragma unroll
-        for (int i = 1; i < 12; i++) t = subc_cc(x[i], y[i]);
-        (void)t;
-        return subc(0, 0) != 0;
-    };
-    bool res_is_b;
-#pragma unroll 1
-    for (;;) {
-#pragma unroll 1
-        while (!(u[0] & 1u)) {
-            shr1(u);
-            if (b[0] & 1u) add_p(b);
-            shr1(b);
-        }
-        if (is_one(u)) { res_is_b = true; break; }
-#pragma unroll 1
-        while (!(v[0] & 1u)) {
-            shr1(v);
-            if (c[0] & 1u) add_p(c);
-            shr1(c);
-        }
-        if (is_one(v)) { res_is_b = false; break; }
-        if (!less(u, v)) {
-            sub(u, v);
-            if (sub(b, c)) add_p(b);
-        } else {
-            sub(v, u);
-            if (sub(c, b)) add_p(c);
-        }
-    }
-    fp_t x, rr;
-#pragma unroll
-    for (int i = 0; i < 12; i++) { x.l[i] = res_is_b ? b[i] : c[i]; rr.l[i] = fp_rr_limb(i); }
-    fp_mul(x, x, rr);
-    fp_mul(r, x, rr);
-}
+// 1/a in Montgomery form, 0 -> 0 like the reference's reciprocal_fp (src/recip.c:58-92): the branch-free safegcd of
+// inv.cuh (about 25 K instructions, no data-dependent inner loops). Each thread stops when ITS g reaches zero; the
+// batch-affine kernels use the warp-voting variant (batch_affine.cuh). The earlier shift / subtract binary GCD took about
+// 45 K instructions with divergent inner loops and made the single-thread finalize 0.06 ms slower.
+struct s30_thread_vote { MSMB200_HD bool operator()(bool done) const { return done; } };
+static __device__ __noinline__ void fp_inv(fp_t &r, const fp_t &a) { s30_inverse_words(r.l, a.l, s30_thread_vote()); }
 
 }  // namespace msmb200
