@@ -90,7 +90,8 @@ int msmb200_set_stream(msmb200_ctx *ctx, void *cuda_stream);
 /* Multi-GPU by BUCKET RANGE (the alternative of SURVEY §8e): every context holds all points and tables; context
  * `rank` of `world` accumulates and reduces only its 1/world slice of the bucket-reduction chunks, so both hot
  * loops scale 1/world; the per-context results are Jacobian partials that sum to the full MSM (same gather as the
- * point-sharded mode). Default rank 0 of 1. */
+ * point-sharded mode). A sharded context (world > 1) always reduces with the chunked reducer (mode 1 below), the one that
+ * works on a range of chunks. Default rank 0 of 1. */
 int msmb200_set_bucket_shard(msmb200_ctx *ctx, int rank, int world);
 
 /* Bucket-accumulation algorithm: 0 = library default, 1 = XYZZ mixed additions, one thread per work item (the

@@ -391,11 +391,14 @@ static __device__ unsigned long long ba_dbg[BA_RMAX][BA_DBG_BLOCKS][4];
 #endif
 template <class F> struct ba_smem {
     static constexpr int FCH = (int)(sizeof(F) / 16);        // 16-byte chunks per field element
+    // Fp: 25 / 27 chunks of 2 KB -> 54 KB per block, 4 blocks (16 warps) per SM; Fp2: 43 / 51 chunks -> 102 KB, 2 blocks.
+    // (Fp2 with ONE x stage and two forward stages fits three blocks at 168 registers, no spills in rounds >= 1 — and is
+    // slower: G2 n=2^18 accumulate 3.69 instead of 3.44 ms, gpurun_out/r2ah_sweep.log. The stage counts stay parameters.)
     static constexpr int FWD_DESC = 4, FWD_STAGES = 3;       // descriptor ring / data stages (x1, x2, descriptor copy)
     static constexpr int FWD_STAGE_CH = 2 * FCH + 1;
-    static constexpr int BWD_DESC = 3, BWD_X_CH = 3 * FCH;   // descriptor ring; one x stage: prefix product, x1, x2 (two stages), one y stage: y1, y2
-    static constexpr int FWD_CH = FWD_DESC + FWD_STAGES * FWD_STAGE_CH, BWD_CH = BWD_DESC + 2 * BWD_X_CH + 2 * FCH;
-    // Fp: 25 / 27 chunks of 2 KB -> 54 KB per block, 4 blocks (16 warps) per SM; Fp2: 43 / 51 chunks -> 102 KB, 2 blocks
+    static constexpr int BWD_DESC = 3, BWD_X_CH = 3 * FCH;   // descriptor ring; one x stage: prefix product, x1, x2; one y stage: y1, y2
+    static constexpr int BWD_X_STAGES = 2;
+    static constexpr int FWD_CH = FWD_DESC + FWD_STAGES * FWD_STAGE_CH, BWD_CH = BWD_DESC + BWD_X_STAGES * BWD_X_CH + 2 * FCH;
     static constexpr int BYTES = (FWD_CH > BWD_CH ? FWD_CH : BWD_CH) * BA_THREADS * 16;
 };
 
@@ -473,16 +476,15 @@ static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_r
             ba_cp_commit();
             ba_cp_wait<0>();
             if (FIRST) __syncwarp();        // round 0: the lanes read each other's descriptors and fill each other's stages
-            issue_data(0);
-            ba_cp_commit();
-            issue_data(1);
-            ba_cp_commit();
+            constexpr int D = NS - 1;       // data of slot j + D is requested while slot j is processed
+#pragma unroll
+            for (int k = 0; k < D; k++) { issue_data((uint32_t)k); ba_cp_commit(); }
 #pragma unroll 1
             for (uint32_t j = 0; j < niter; j++) {
-                ba_cp_wait<1>();            // everything committed before the previous iteration's group has landed
+                ba_cp_wait<D - 1>();        // everything but the D - 1 most recent groups has landed: the data of slot j
                 if (FIRST) __syncwarp();
-                issue_data(j + 2);          // descriptor j + 2 arrived with the group of iteration j - 2
-                issue_desc(j + 4);
+                issue_data(j + D);          // its descriptor arrived with the group of iteration j - 2 (or the prologue)
+                issue_desc(j + D + 2);
                 ba_cp_commit();
                 const size_t s = slot_of(j);
                 if (s < nadds) {
@@ -515,11 +517,12 @@ static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_r
         BA_STAMP(2);
         // ---- backward: slopes and results ----
         {
-            // shared-memory plan: descriptor ring of 3 (slots j, j - 1 live; j - 2 arriving), TWO stages of {prefix product,
+            // shared-memory plan: descriptor ring of 3 (slots j, j - 1 live; j - 2 arriving), NXS stages of {prefix product,
             // x1, x2} and ONE stage of {y1, y2}: the y coordinates of slot j - 1 are requested in the middle of slot j, right
-            // after slot j has taken its own into registers — three multiplications before they are needed.
-            constexpr int ND = SM::BWD_DESC, XCH = SM::BWD_X_CH, X0 = ND, Y0 = ND + 2 * XCH;
-            auto xstage = [&](uint32_t j) { return X0 + (int)(j & 1u) * XCH; };
+            // after slot j has taken its own into registers — three multiplications before they are needed. With a single x
+            // stage (Fp2) the x part of slot j - 1 is requested at the same point; with two (Fp) at the top of slot j.
+            constexpr int ND = SM::BWD_DESC, XCH = SM::BWD_X_CH, NXS = SM::BWD_X_STAGES, X0 = ND, Y0 = ND + NXS * XCH;
+            auto xstage = [&](uint32_t j) { return X0 + (int)(j % NXS) * XCH; };
             auto desc_at = [&](uint32_t j) { return *reinterpret_cast<const uint4 *>(ba_shared + ba_chunk((int)(j % ND))); };
             auto issue_desc = [&](uint32_t j) { ba_cp16(sbase + ba_chunk((int)(j % ND)), desc_src(j)); };
             auto issue_x = [&](uint32_t j) {   // needs the descriptor of slot j in the ring
@@ -551,7 +554,7 @@ static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_r
             for (uint32_t j = niter; j-- > 0;) {
                 ba_cp_wait<0>();            // operands of slot j and the descriptor of slot j - 1 have landed
                 if (FIRST) __syncwarp();    // round 0: ... for every lane of the warp (cooperative gather)
-                if (j >= 1) issue_x(j - 1);
+                if (NXS == 2 && j >= 1) issue_x(j - 1);
                 if (j >= 2) issue_desc(j - 2);
                 ba_cp_commit();
                 const size_t s = slot_of(j);
@@ -582,7 +585,10 @@ static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_r
                     ba_ld_stage(y1, ba_shared, Y0);
                     ba_ld_stage(t, ba_shared, Y0 + FCH);
                     __syncwarp();
-                    if (j >= 1) issue_y(j - 1);
+                    if (j >= 1) {
+                        if (NXS == 1) issue_x(j - 1);
+                        issue_y(j - 1);
+                    }
                     ba_cp_commit();
                     if (!live) continue;
                     f_cneg(y1, y1, (m.x >> 31) != 0);
@@ -613,8 +619,11 @@ static __global__ void __launch_bounds__(BA_THREADS, ba_cfg<F>::MIN_BLOCKS) ba_r
                     continue;
                 }
                 // later rounds: every lane copies for itself and reads only what its slot's case needs
-                auto next_y = [&]() {       // exactly once per iteration, once the y stage has been read (or is not needed)
-                    if (j >= 1) issue_y(j - 1);
+                auto next_y = [&]() {       // exactly once per iteration, once the stages have been read (or are not needed)
+                    if (j >= 1) {
+                        if (NXS == 1) issue_x(j - 1);
+                        issue_y(j - 1);
+                    }
                     ba_cp_commit();
                 };
                 if (s >= nadds) { next_y(); continue; }

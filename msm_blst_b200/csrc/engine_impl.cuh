@@ -36,7 +36,9 @@ struct Layout {
 static inline bool use_split_reduce(const Ctx *c, const Layout &L) {
     int mode = c->reduce_mode;
     if (c->reduce_env) mode = c->reduce_env;
-    return L.plan && L.plan->valid && mode != 1 && (L.nwindows == 1 || L.plan->nbits_w <= L.wbits);
+    // bucket-range sharding reduces a RANGE of chunks: only the chunked reducer honours chunk_lo / chunk_cnt, so a sharded
+    // context uses it (the digit-splitting plan covers all buckets and would redo the full reduction on every rank)
+    return L.plan && L.plan->valid && mode != 1 && c->shard_world <= 1 && (L.nwindows == 1 || L.plan->nbits_w <= L.wbits);
 }
 // dense plans (value == local index) are built on first use and cached per (buckets per window, windows)
 static inline const ReducePlan *dense_plan(Ctx *c, ReducePlan &slot, size_t nbw, uint32_t nwindows, uint32_t *key_windows) {

@@ -6,8 +6,9 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle_lib as O
 import msm_blst_b200 as M
-CASES = ((2, 15, ["15", "16", "17"]), (2, 16, ["15", "16", "16_beta", "17", "18"]), (2, 17, ["16", "17", "18"]),
-         (1, 18, ["17", "18", "20"]), (1, 19, ["18", "19", "20"]), (1, 20, ["19", "20", "21"]))
+CASES = ((2, 15, ["13", "15", "16_beta"]), (2, 16, ["15", "16_beta", "16", "17"]), (2, 17, ["15", "16_beta", "16", "17"]), (2, 18, ["16_beta", "16", "18"]),
+         (1, 18, ["16", "17", "18"]), (1, 19, ["16", "18", "19"]), (1, 20, ["19", "20", "21"]), (1, 21, ["20_beta", "21"]))
+if len(sys.argv) > 1: CASES = [c for c in CASES if str(c[0]) == sys.argv[1]]
 for g, nexp, cfgs in CASES:
     n = 1 << nexp
     sc = O.gen_scalars(1, n)
