@@ -716,6 +716,31 @@ def test_batch_affine_full_size_known_answer(M, golden):
     ctx.close()
 
 
+@pytest.mark.parametrize("group,cfgname,reps", [(1, "16", 12), (2, "13", 12), (1, "20", 3)])
+def test_batch_affine_rounds_repeatable_on_fresh_scalars(M, group, cfgname, reps):
+    """The batch-affine rounds stage their operands through shared memory with cp.async, fill each other's stages in round 0
+    (warp-cooperative gather) and take their batches from an atomic counter, so the work split differs from run to run: every
+    repetition, on a fresh scalar set and back to back without synchronisation in between, must still give the closed form;
+    the XYZZ accumulator is the cross-check on the first set. Also covers a table in the packed layout (pointers of a caller)
+    next to the context's padded one: method 4 gathers from the packed fixed points."""
+    ctx = M.MsmContext(group, cfgname)
+    ctx.init_fix_point_list()
+    ctx.init_pippenger_CHES_q_over_5()
+    ctx.set_accumulator(2)
+    for rep in range(reps):
+        sc = O.gen_scalars(900 + 7 * rep + group, ctx.n)
+        exp, _ = O.closed_form(group, sc)
+        got = ctx.msm(1, sc)
+        assert ctx.last_accumulator() == 2
+        assert (got == exp).all(), rep
+        if rep == 0:
+            assert (ctx.msm(4, sc) == exp).all()
+            ctx.set_accumulator(1)
+            assert (ctx.msm(1, sc) == exp).all() and ctx.last_accumulator() == 1
+            ctx.set_accumulator(2)
+    ctx.close()
+
+
 @pytest.mark.parametrize("field", [1, 2])
 def test_warp_batch_inversion_vs_plain_inverse(M, field):
     """Montgomery's trick across the warp (one inversion per 32 lanes, used by the batch-affine rounds) returns the
