@@ -470,6 +470,17 @@ def run_workload(args, workload, method, env, with_sampler, with_cpu_baseline, p
             out["roofline_hbm"] = {"bound": "hbm", "kernel": "bucket accumulation (table gather)", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                                    "frac": gbs / hbm_peak, "traffic": (nc or {}).get("dram_bytes_accumulate_phase"),
                                    "algorithmic_bytes": cm["gather_bytes"], "peak_source": hbm_src}
+            if batch_affine:
+                # what the pairwise rounds move by construction, per addition: forward pass x1, x2 in + prefix product out; backward pass
+                # prefix, x1, x2, y1, y2 in + the affine result out; two 16-byte descriptor reads
+                fe = 48 if group == 1 else 96
+                ba_bytes = (cm["adds"] - (full_cfg.bsize if method in (1, 2) else 0)) * (2 * fe + fe + fe + 4 * fe + 2 * fe + 32)
+                out["roofline_hbm"]["algorithmic_bytes_batch_affine"] = ba_bytes
+                out["roofline_hbm"]["achieved_batch_affine"] = ba_bytes / (acc_ms * 1e-3) / 1e9
+                out["roofline_hbm"]["note"] = ("algorithmic_bytes = the reference algorithm's table gather (n*h entries, read once). The batch-affine rounds trade "
+                                               "multiplications for memory traffic: every round streams its operands twice (forward / backward pass) and writes "
+                                               "its results for the next round - algorithmic_bytes_batch_affine; the measured traffic exceeds it by the 128-byte "
+                                               "line granularity of the round-0 table reads (48 / 96 useful bytes per line).")
             if with_cpu_baseline:
                 out["cpu_baseline"] = cpu_baseline_leg(group, cfgname, method, n, sets, ctx)
     ctx.close()
