@@ -741,6 +741,31 @@ def test_batch_affine_rounds_repeatable_on_fresh_scalars(M, group, cfgname, reps
     ctx.close()
 
 
+@pytest.mark.parametrize("group", [1, 2])
+def test_packed_and_padded_tables_agree(M, group, monkeypatch):
+    """The context's own tables are padded to whole 128-byte lines; MSMB200_PACKED_TABLES keeps the reference's packed layout
+    (the layout caller-owned tables have). Both accumulators must give the same result on both, and the download is the
+    packed reference layout either way."""
+    cfgname = "13"
+    sc = O.gen_scalars(77 + group, 1 << 13)
+    exp, _ = O.closed_form(group, sc)
+    tables = []
+    for packed in (False, True):
+        if packed:
+            monkeypatch.setenv("MSMB200_PACKED_TABLES", "1")
+        ctx = M.MsmContext(group, cfgname)
+        ctx.init_fix_point_list()
+        ctx.init_pippenger_CHES_q_over_5()
+        ctx.init_pippenger_BGMW95()
+        for accum in (1, 2):
+            ctx.set_accumulator(accum)
+            for method in (1, 2, 3):
+                assert (ctx.msm(method, sc) == exp).all(), (packed, accum, method)
+        tables.append((ctx.download(1).copy(), ctx.download(2).copy()))
+        ctx.close()
+    assert (tables[0][0] == tables[1][0]).all() and (tables[0][1] == tables[1][1]).all()
+
+
 @pytest.mark.parametrize("field", [1, 2])
 def test_warp_batch_inversion_vs_plain_inverse(M, field):
     """Montgomery's trick across the warp (one inversion per 32 lanes, used by the batch-affine rounds) returns the
