@@ -389,16 +389,25 @@ static __device__ unsigned long long ba_dbg[BA_RMAX][BA_DBG_BLOCKS][4];
 #else
 #define BA_STAMP(k) do { } while (0)
 #endif
+// Staging depth (measured, gpurun_out/r2ap_stages.log): ONE stage ahead is enough in both passes — a slot is 1 (forward) or 5
+// (backward) multiplications long — and the shallow rings are faster than two / three stages (G1 n=2^21 accumulate 7.29 vs
+// 7.50 ms, G2 n=2^18 3.39 vs 3.45 ms): 36 KB instead of 54 KB per block leave the L1 more room for the descriptor, prefix
+// and round-buffer lines that pass through it.
+#ifndef BA_FWD_STAGES
+#define BA_FWD_STAGES 2
+#endif
+#ifndef BA_BWD_X_STAGES
+#define BA_BWD_X_STAGES 1
+#endif
 template <class F> struct ba_smem {
     static constexpr int FCH = (int)(sizeof(F) / 16);        // 16-byte chunks per field element
-    // Fp: 25 / 27 chunks of 2 KB -> 54 KB per block, 4 blocks (16 warps) per SM; Fp2: 43 / 51 chunks -> 102 KB, 2 blocks.
-    // (Fp2 with ONE x stage and two forward stages fits three blocks at 168 registers, no spills in rounds >= 1 — and is
-    // slower: G2 n=2^18 accumulate 3.69 instead of 3.44 ms, gpurun_out/r2ah_sweep.log. The stage counts stay parameters.)
-    static constexpr int FWD_DESC = 4, FWD_STAGES = 3;       // descriptor ring / data stages (x1, x2, descriptor copy)
+    static constexpr int FWD_DESC = 4, FWD_STAGES = BA_FWD_STAGES;   // descriptor ring / data stages (x1, x2, descriptor copy)
     static constexpr int FWD_STAGE_CH = 2 * FCH + 1;
     static constexpr int BWD_DESC = 3, BWD_X_CH = 3 * FCH;   // descriptor ring; one x stage: prefix product, x1, x2; one y stage: y1, y2
-    static constexpr int BWD_X_STAGES = 2;
+    static constexpr int BWD_X_STAGES = BA_BWD_X_STAGES;
     static constexpr int FWD_CH = FWD_DESC + FWD_STAGES * FWD_STAGE_CH, BWD_CH = BWD_DESC + BWD_X_STAGES * BWD_X_CH + 2 * FCH;
+    // Fp: 18 / 18 chunks of 2 KB -> 36 KB per block, 4 blocks (16 warps) per SM by registers; Fp2: 30 / 33 chunks -> 66 KB, 2 blocks
+    // by registers (three blocks at 168 registers were measured slower: profiles/experiments/README.md)
     static constexpr int BYTES = (FWD_CH > BWD_CH ? FWD_CH : BWD_CH) * BA_THREADS * 16;
 };
 

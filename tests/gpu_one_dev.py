@@ -5,6 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle_lib as O
 import msm_blst_b200 as M
+import msm_blst_b200.api as _A
+if os.environ.get("MSMB200_DEV_LIB"): _A.LIB_PATH = os.path.abspath(os.environ["MSMB200_DEV_LIB"])
 g, cfg, accum, bmax, reps = int(sys.argv[1]), sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
 method = int(sys.argv[6]) if len(sys.argv) > 6 and "=" not in sys.argv[6] else 1
 tune = [a.split("=") for a in sys.argv[6:] if "=" in a]
