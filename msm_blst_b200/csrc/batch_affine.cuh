@@ -340,6 +340,13 @@ __device__ __forceinline__ uint32_t ba_smem_addr(const void *p) { return (uint32
 __device__ __forceinline__ void ba_cp16(uint32_t dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+// the same past L1 (table entries are read once per pass and never again by this SM). Measured (gpurun_out/r2aq log): Fp2
+// gains (G2 n=2^18 accumulate 3.39 -> 3.31 ms, n=2^20 11.48 -> 11.32 ms), Fp does not (7.2-7.3 ms either way), so only the
+// Fp2 gather bypasses L1.
+template <bool BYPASS_L1> __device__ __forceinline__ void ba_cp16_stream(uint32_t dst, const void *src) {
+    if (BYPASS_L1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else ba_cp16(dst, src);
+}
 template <class F> __device__ __forceinline__ void ba_prefetch_l2(const F *p) {   // both 128-byte lines an element can touch
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p) + sizeof(F) - 16));
@@ -378,7 +385,7 @@ __device__ __forceinline__ void ba_coop_gather(const aff_t<F> *__restrict__ tabl
             const uint32_t o = e >> 1, which = e & 1u;
             const uint32_t idx = *reinterpret_cast<const uint32_t *>(shared + ((size_t)desc_chunk * BA_THREADS + wbase + o) * 16 + which * 4) & 0x7fffffffu;
             const uint4 *src = reinterpret_cast<const uint4 *>(table) + (size_t)idx * stride16 + first_chunk + c;
-            ba_cp16(sbase + (uint32_t)((((which ? dst_q : dst_p) + (int)c) * BA_THREADS + (int)(wbase + o)) * 16), src);
+            ba_cp16_stream<(NCH > 3)>(sbase + (uint32_t)((((which ? dst_q : dst_p) + (int)c) * BA_THREADS + (int)(wbase + o)) * 16), src);
         }
     }
 }
