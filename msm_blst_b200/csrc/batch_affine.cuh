@@ -7,17 +7,19 @@
 // Shape of the computation. Every bucket is a list of k points; round r turns it into ceil(k / 2) points by adding
 // neighbours (2i, 2i + 1); an odd last element is copied. After ceil(log2(max k)) rounds every bucket is ONE affine
 // point (bucket_sum[b]). All additions of a round, over all buckets, are independent "slots".
-//   * The slots of a round are enumerated by 8-byte descriptors (input position, output position | FINAL bucket), built
-//     before any arithmetic from the bucket histogram alone (ba_totals / ba_scan_* / ba_emit_*): the arithmetic kernel
-//     never sees bucket boundaries, only real additions — no lane is spent on padding.
-//   * ba_round_kernel: a block owns B x 128 consecutive slots; lane t handles slots j * 128 + t (j < B), so descriptor,
-//     point and scratch accesses of a warp are contiguous. Forward pass: denominator d_j, running product, the product
-//     BEFORE d_j goes to a global scratch array (the DRAM system is nearly idle in this phase). One inversion PER LANE by
-//     the branch-free safegcd of inv.cuh (all lanes run the same instruction stream, mostly on the idle ALU pipe).
-//     Backward pass: slopes and results, 4M + 1S; the forward pass costs 1M.
-//   * The same engine sums the digit lists of the bucket REDUCTION (src/multi_scalar.c:301-321), whose plan is static.
+//   * The slots of a round are enumerated by 16-byte RESOLVED descriptors {p, q, out, 0} (operand indices in the round's
+//     source array: the precomputation table in round 0, bit 31 = negate; the previous round's points later; out = position
+//     in the next round's buffer or FINAL | bucket), built before any arithmetic from the bucket histogram alone
+//     (ba_totals / ba_scan_* / ba_emit_*): the arithmetic kernel never sees bucket boundaries, only real additions.
+//   * ba_round_kernel is persistent: every WARP takes batches of up to ~110 rows (a row = 32 consecutive slots, lane t
+//     handles slot 32 j + t, so descriptor, round-buffer and scratch accesses of a warp are contiguous) from an atomic
+//     counter. Forward pass: denominator d_j, running product; the product BEFORE d_j goes to a global scratch array. One
+//     inversion PER LANE by the branch-free safegcd of inv.cuh (all lanes run the same instruction stream, mostly on the
+//     otherwise idle ALU pipe). Backward pass: slopes and results, 4M + 1S; the forward pass costs 1M.
+//   * Operands reach the lanes through shared memory (cp.async), one slot ahead: 36 KB per block, 4 blocks per SM for Fp.
+//     Round 0 gathers table entries warp-cooperatively (ba_coop_gather): the memory system is bound by REQUESTS there.
 // Montgomery-form, fully reduced affine results: the bytes equal what any other correct summation order produces once
-// normalised.
+// normalised. What was measured on the way (and what lost) is in profiles/experiments/README.md.
 #pragma once
 #include <cstdint>
 #include "ec.cuh"
@@ -346,10 +348,6 @@ __device__ __forceinline__ void ba_cp16(uint32_t dst, const void *src) {
 template <bool BYPASS_L1> __device__ __forceinline__ void ba_cp16_stream(uint32_t dst, const void *src) {
     if (BYPASS_L1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     else ba_cp16(dst, src);
-}
-template <class F> __device__ __forceinline__ void ba_prefetch_l2(const F *p) {   // both 128-byte lines an element can touch
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p) + sizeof(F) - 16));
 }
 __device__ __forceinline__ void ba_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void ba_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
