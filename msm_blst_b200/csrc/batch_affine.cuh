@@ -335,9 +335,11 @@ template <class F> __device__ __forceinline__ void ba_store_point(uint32_t out, 
 // A lane does only 1 (forward) or 5 (backward) multiplications per slot, each an out-of-line call, and a call waits for
 // every register load still in flight — so nothing the hot loops need may be a pending register load. Descriptors and
 // operands are copied global -> shared ahead of use instead: thread t owns 16-byte chunk k of a stage at
-// (k * 128 + t) * 16 (conflict-free) and reads back only what it copied itself, so cp.async.wait_group is the only
-// synchronisation. Forward: descriptors four slots ahead, x coordinates two slots ahead (one multiplication per slot
-// hides little). Backward: descriptors two slots ahead, prefix product and both points one slot ahead.
+// (k * 128 + t) * 16 (conflict-free). In rounds >= 1 a thread reads back only what it copied itself, so
+// cp.async.wait_group is the only synchronisation; in round 0 the lanes of a warp fill each other's stages
+// (ba_coop_gather) and a __syncwarp follows the wait. Forward: descriptors three slots ahead, x coordinates one slot
+// ahead. Backward: the descriptor of slot j - 2 is requested at the top of slot j, the operands of slot j - 1 in the middle
+// of slot j, right after slot j has taken its own into registers (three multiplications of lead).
 __device__ __forceinline__ uint32_t ba_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ba_cp16(uint32_t dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
