@@ -12,10 +12,12 @@ namespace msmb200 {
 static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
 // Default accumulator (msmb200_set_accumulator(ctx, 0)): batch-affine rounds (2) once the problem is large enough that
-// its rounds are throughput-bound, XYZZ work items (1) below — measured crossover on B200 (profiles/r2_accum_sweep.log):
-// G1 between 2^19 and 2^20 points (6.8 M / 12.6 M entries), G2 around 2^16 points (1 M entries).
+// its rounds are throughput-bound, XYZZ work items (1) below — measured crossover on B200 (profiles/r2_accum_sweep.log and,
+// on the final kernels, gpurun_out/r2ar log: sort + accumulate + reduce, the reduction being cheaper on affine bucket sums):
+// G1 between 6.8 M and 12.6 M entries (n=2^19: 2.96 vs 3.03 ms, n=2^20: 5.68 vs 5.16 ms), G2 at about 0.5 M entries
+// (n=2^15: 1.44 vs 1.38 ms, n=2^16: 2.58 vs 2.46 ms, n=2^17: 3.03 vs 2.86 ms).
 template <class F> static inline int default_accumulator(size_t entries) {
-    return entries >= (sizeof(F) > 48 ? ((size_t)1 << 20) : ((size_t)1 << 23)) ? 2 : 1;
+    return entries >= (sizeof(F) > 48 ? ((size_t)1 << 19) : ((size_t)1 << 23)) ? 2 : 1;
 }
 
 struct Layout {
