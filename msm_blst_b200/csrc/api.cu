@@ -249,12 +249,14 @@ struct ShimCall {
     ~ShimCall() { g_shim_last_ms[group] = ms(); lap("return"); }
 };
 static Ctx *g_shim[3] = {nullptr, nullptr, nullptr};
-static Ctx *shim_ctx(int group) {
+// may_fail: return nullptr instead of aborting (entry points that have an error channel)
+static Ctx *shim_ctx(int group, bool may_fail = false) {
     std::lock_guard<std::mutex> lk(g_shim_mu);
     if (!g_shim[group]) {
         Ctx *c = new Ctx();
         const char *dev = getenv("MSMB200_DEVICE");
         if (ctx_init_common(c, group, dev ? atoi(dev) : 0) != MSMB200_OK) {
+            if (may_fail) { g_create_err = c->err; delete c; return nullptr; }
             fprintf(stderr, "msm_b200: cannot initialise CUDA for blst shim: %s\n", c->err.c_str());
             abort();  // the blst signatures have no error channel; never fall back to the CPU
         }
@@ -1245,7 +1247,8 @@ void msmb200_blst_p2_construct_nh_scalars_nh_points(int nh_scalars[], unsigned c
 double msmb200_blst_last_call_ms(int group) { return group == 1 || group == 2 ? g_shim_last_ms[group] : -1.0; }
 int msmb200_blst_register_table(int group, const void *host_table, size_t entries) {
     if ((group != 1 && group != 2) || !host_table || entries == 0 || entries > ((size_t)1 << 31)) return MSMB200_EINVAL;
-    Ctx *c = shim_ctx(group);
+    Ctx *c = shim_ctx(group, true);
+    if (!c) return MSMB200_ECUDA;   // no CUDA device: msmb200_last_error(NULL) says why
     ShimCall call_lock(group);
     cudaSetDevice(c->device);
     if (!shim_upload_table(c, g_state[group], (const unsigned char *)host_table, entries) || cudaStreamSynchronize(c->stream) != cudaSuccess)

@@ -114,6 +114,22 @@ def test_parameter_search_check_other_radices(product_lib):
     print("invalid parameter pairs found:", seen_invalid)
 
 
+def test_blst_register_table_needs_a_gpu(product_lib):
+    """The int-returning shim entry point reports a missing CUDA device instead of aborting (the void blst-named shims abort)."""
+    import ctypes as C
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    t = np.zeros((16, 96), dtype=np.uint8)
+    L = product_lib.lib()
+    assert L.msmb200_blst_register_table(1, t.ctypes.data_as(C.c_void_p), 16) != 0
+    assert L.msmb200_blst_register_table(3, t.ctypes.data_as(C.c_void_p), 16) != 0     # bad group
+    assert L.msmb200_blst_register_table(1, None, 16) != 0
+    assert L.msmb200_blst_last_call_ms(7) < 0
+
+
 def test_no_cpu_fallback(product_lib):
     """Without a CUDA device every compute entry point returns an error; with one, bad arguments do."""
     import torch
