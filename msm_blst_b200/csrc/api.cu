@@ -141,6 +141,11 @@ static void compute_reduce_plan(HostReducePlan &H, const int *values, size_t nbw
         return n * nwindows;
     };
     while (slice1 < (1u << 20) && (double)count_slices(slice1) > lanes1) slice1 += std::max(1u, slice1 / 16);  // ragged last slices
+    // Fp2 (groups of 8 lanes: gpw == 4): a cooperative addition of stage 1b costs about half of a whole stage-1 step, so
+    // short slices are made half as long again — fewer slices for stage 1b to fold. Measured (gpurun_out/r2as_slice_scale.log):
+    // G2 reduce 0.85 -> 0.71 ms at n=2^16, 0.97 -> 0.88 ms at 2^18, 0.38 -> 0.34 ms at 2^15; at n=2^21 (slices of 31) and for
+    // Fp the one-wave length is the optimum.
+    if (gpw == 4 && slice1 <= 16) slice1 += slice1 / 2;
     if (const char *e = getenv("MSMB200_SLICE1")) slice1 = (uint32_t)std::max(1, atoi(e));
     H.slice1 = slice1;
     slice_lists(start, slice1, H.s1.start, H.s1b.start, H.s1b.idx);
