@@ -106,7 +106,8 @@ int msmb200_set_accumulator(msmb200_ctx *ctx, int mode);
 int msmb200_set_reducer(msmb200_ctx *ctx, int mode);
 
 /* Performance knobs of one context (never change results). Keys: "ba_batch_max" (upper bound of the batch-affine slots
- * per lane per round), "ba_batch" (forced value, 0 = automatic), "item_len" (XYZZ work-item length, 0 = automatic).
+ * per lane per round), "ba_batch" (forced value, 0 = automatic), "ba_stagger" (staggered first batches of the round kernel,
+ * default 1), "item_len" (XYZZ work-item length, 0 = automatic).
  * The same keys are read once from the environment at context creation as MSMB200_<KEY IN CAPITALS>. */
 int msmb200_set_tuning(msmb200_ctx *ctx, const char *key, int value);
 
@@ -114,11 +115,15 @@ int msmb200_set_tuning(msmb200_ctx *ctx, const char *key, int value);
 int msmb200_set_points(msmb200_ctx *ctx, const void *points_affine_host);
 /* init_fix_point_list (main_p1.cpp:52-66): P_i = 2^(first+i+1) * G computed on the device. */
 int msmb200_generate_fix_points(msmb200_ctx *ctx, size_t first);
-/* init_pippenger_CHES_q_over_5 table loop (main_p1.cpp:156-172): T3nh[3(i*h+j)+m-1] = m q^j P_i. */
+/* init_pippenger_CHES_q_over_5 table loop (main_p1.cpp:156-172): T3nh[3(i*h+j)+m-1] = m q^j P_i. In HBM every entry of the
+ * context's own tables sits on its own 128-byte line (G2: two lines); that layout is internal (MSMB200_PACKED_TABLES at
+ * context creation keeps the packed one). */
 int msmb200_table_build_ches(msmb200_ctx *ctx);
 /* init_pippenger_BGMW95 (main_p1.cpp:94-122): TBGMW[i*h'+j] = q'^j P_i. */
 int msmb200_table_build_bgmw95(msmb200_ctx *ctx);
-/* Copy `count` affine entries starting at `first` back to host. which: 0 = fixed points, 1 = T3nh, 2 = TBGMW. */
+/* Copy `count` affine entries starting at `first` back to host, ALWAYS in the reference's packed array layout
+ * (blst_pN_affine[count], byte-identical to PRECOMPUTATION_POINTS_LIST_3nh / _BGMW95). which: 0 = fixed points, 1 = T3nh,
+ * 2 = TBGMW. */
 int msmb200_download(msmb200_ctx *ctx, int which, size_t first, size_t count, void *out_host);
 /* Table persistence (the reference rebuilds its tables on every run, main_p1.cpp:615-617). which: 0 fixed
  * points, 1 CHES 3nh table, 2 BGMW95 table. format 0: the in-memory blst_pN_affine layout (Montgomery limbs); format 1:
